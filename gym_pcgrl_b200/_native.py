@@ -1,0 +1,127 @@
+"""ctypes loader for the C-ABI shared library (csrc/ -> libpcgrl_b200.so) and thin torch glue.
+
+The product path has NO CPU fallback: if the library is missing or CUDA is unavailable every entry
+point raises.  torch is used only to own device memory and streams; all signatures below pass raw
+pointers to the ``extern "C"`` functions declared in include/pcgrl_b200.h.
+"""
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpcgrl_b200.so")
+
+EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
+           "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host"]
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libpcgrl_b200.so (built by ``__graft_entry__.build()`` / ``python -m gym_pcgrl_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                "CUDA extension %s is missing -- build it with `python -m gym_pcgrl_b200.build` "
+                "(there is no CPU fallback for the step path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.pcgrl_abi_version.restype = C.c_int
+        L.pcgrl_last_error.restype = C.c_char_p
+        L.pcgrl_config_validate.restype = C.c_int
+        L.pcgrl_config_validate.argtypes = [C.POINTER(_abi.PcgrlConfig)]
+        L.pcgrl_scratch_bytes.restype = C.c_size_t
+        L.pcgrl_scratch_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
+        L.pcgrl_reset.restype = C.c_int
+        L.pcgrl_reset.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_step.restype = C.c_int
+        L.pcgrl_step.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_rollout.restype = C.c_int
+        L.pcgrl_rollout.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pcgrl_get_stats.restype = C.c_int
+        L.pcgrl_get_stats.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.pcgrl_seed.restype = C.c_int
+        L.pcgrl_seed.argtypes = [C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_step_host.restype = C.c_int
+        L.pcgrl_step_host.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p,
+                                      C.POINTER(_abi.PcgrlHostIO), C.c_int, C.c_void_p]
+        if L.pcgrl_abi_version() != _abi.ABI_VERSION:
+            raise NativeError("libpcgrl_b200.so ABI %d != python ABI %d" % (L.pcgrl_abi_version(), _abi.ABI_VERSION))
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().pcgrl_last_error()
+        raise NativeError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def require_cuda(device):
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError("gym_pcgrl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise NativeError("device must be a CUDA device, got %r" % (device,))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def stream_ptr(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def validate(cfg):
+    check(lib().pcgrl_config_validate(C.byref(cfg)), "pcgrl_config_validate")
+
+
+def alloc_buffers(cfg, n, device):
+    """Allocate the caller-owned state tensors of n envs on `device` and the struct pointing at them."""
+    import torch
+    h, w = cfg.height, cfg.width
+    tens = {}
+    for name, dtype, shape in _abi.BUFFER_SPECS:
+        tens[name] = torch.zeros((n,) + shape(h, w), dtype=getattr(torch, "int32" if dtype == "uint32" else dtype), device=device)
+    tens["tile_prob"][:] = torch.tensor(list(cfg.tile_prob), dtype=torch.float64, device=device)[None, :]
+    tens["status"] = torch.zeros(4, dtype=torch.int32, device=device)
+    nbytes = int(lib().pcgrl_scratch_bytes(C.byref(cfg), n))
+    tens["scratch"] = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+    b = _abi.PcgrlBuffers()
+    for name, _, _ in _abi.BUFFER_SPECS:
+        setattr(b, name, tens[name].data_ptr())
+    b.scratch, b.scratch_bytes, b.status = tens["scratch"].data_ptr(), nbytes, tens["status"].data_ptr()
+    return tens, b
+
+
+def get_stats(prob, maps):
+    """Stand-alone batched Problem.get_stats (pcgrl_get_stats): uint8 CUDA [N,H,W] -> int32 [N, MAX_STATS]."""
+    import torch
+    from ._config import build_config
+    from .envs.reps import REPRESENTATIONS
+    dev = require_cuda(maps.device)
+    n, h, w = maps.shape
+    if (h, w) != (prob._height, prob._width):
+        raise ValueError("map shape %s does not match the problem's (height, width) = %s" % ((h, w), (prob._height, prob._width)))
+    cfg = build_config(prob, REPRESENTATIONS["wide"](), 1, 1, auto_reset=False)
+    validate(cfg)
+    maps = maps.to(torch.uint8).contiguous()
+    out = torch.zeros((n, _abi.MAX_STATS), dtype=torch.int32, device=dev)
+    nbytes = int(lib().pcgrl_scratch_bytes(C.byref(cfg), n))
+    scratch = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().pcgrl_get_stats(C.byref(cfg), maps.data_ptr(), out.data_ptr(), n, scratch.data_ptr(), nbytes,
+                                    status.data_ptr(), stream_ptr(dev)), "pcgrl_get_stats")
+    if int(status[0].item()) != 0:
+        raise NativeError("pcgrl_get_stats hit a device capacity limit (status=%s)" % status.tolist())
+    return out

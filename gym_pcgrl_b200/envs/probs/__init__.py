@@ -1,0 +1,15 @@
+"""PROBLEMS registry (same keys as gym_pcgrl/envs/probs/__init__.py:9-16; "smb" is out of scope,
+SURVEY.md 2 row 4b)."""
+from .binary_prob import BinaryProblem
+from .ddave_prob import DDaveProblem
+from .mdungeon_prob import MDungeonProblem
+from .sokoban_prob import SokobanProblem
+from .zelda_prob import ZeldaProblem
+
+PROBLEMS = {
+    "binary": BinaryProblem,
+    "ddave": DDaveProblem,
+    "mdungeon": MDungeonProblem,
+    "sokoban": SokobanProblem,
+    "zelda": ZeldaProblem,
+}

@@ -1,0 +1,164 @@
+/*
+ * pcgrl_b200.h -- C ABI of the B200-native batched PCGRL environment hot path.
+ *
+ * Drop-in boundary for the one data-parallel hot path of amidos2006/gym-pcgrl:
+ * N lock-step PcgrlEnv.step()/reset() calls (reference: gym_pcgrl/envs/pcgrl_env.py:66-76,129-150),
+ * i.e. Representation.update -> Problem.get_stats -> get_reward / get_episode_over.
+ *
+ * The reference is pure Python and has no FFI of its own; the entry points below are what a
+ * ctypes binding inside the reference's PcgrlEnv / a VecEnv worker (utils.py:60-71) would call
+ * (see INTEGRATION.md).  Conventions:
+ *   - plain C, POD structs, raw pointers + sizes, no torch / C++ types;
+ *   - every `pcgrl_*` device entry point only ENQUEUES work on the given CUDA stream
+ *     (cudaStream_t passed as void*); it never synchronises, never allocates device memory and
+ *     never throws.  The `*_host` entry point is the exception: it takes HOST buffers, copies
+ *     in/out and synchronises the stream before returning;
+ *   - all buffers are caller-owned (torch tensors in the Python host layer);
+ *   - return value: 0 = OK, <0 = invalid argument (text in pcgrl_last_error()), >0 = cudaError_t.
+ *
+ * The same POD structs are used by the CPU oracle (oracle/pcgrl_oracle.c, test infrastructure).
+ */
+#ifndef PCGRL_B200_H
+#define PCGRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGRL_ABI_VERSION 1
+
+/* PROBLEMS registry order (reference: gym_pcgrl/envs/probs/__init__.py:9-16; smb is out of scope) */
+enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_DDAVE = 3,
+       PCGRL_PROB_MDUNGEON = 4, PCGRL_NUM_PROBLEMS = 5 };
+/* REPRESENTATIONS (reference: gym_pcgrl/envs/reps/__init__.py:9-16; cast/multi variants are "next") */
+enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_NUM_REPS = 3 };
+
+#define PCGRL_MAX_DIM 32     /* width, height <= 32: one bitboard row per warp lane          */
+#define PCGRL_MAX_TILES 8    /* zelda / mdungeon alphabets                                    */
+#define PCGRL_MAX_STATS 12   /* stride of every stats row                                     */
+#define PCGRL_MT_WORDS 625   /* MT19937: 624 state words + word 624 = position (numpy `pos`)  */
+
+/* flags */
+#define PCGRL_FLAG_RANDOM_TILE 1u   /* narrow: random cursor (narrow_rep.py:104-106) vs raster scan (:107-113) */
+#define PCGRL_FLAG_WARP 2u          /* turtle: wrap at the edges (turtle_rep.py:105-125)                       */
+#define PCGRL_FLAG_RANDOM_START 4u  /* representation.py:41-45                                                */
+#define PCGRL_FLAG_RANDOM_PROBS 8u  /* binary_prob.py:68-72: redraw tile probabilities at every reset          */
+#define PCGRL_FLAG_AUTO_RESET 16u   /* VecEnv semantics: an env that is done is reset inside step()            */
+
+/*
+ * Stats row layout (int32, stride PCGRL_MAX_STATS), one order per problem == the key order of
+ * each Problem.get_stats dict in the reference:
+ *   binary   (binary_prob.py:81-86)     regions, path-length
+ *   zelda    (zelda_prob.py:80-112)     player, key, door, enemies, regions, nearest-enemy, path-length
+ *   sokoban  (sokoban_prob.py:133-145)  player, crate, target, regions, dist-win, len(solution)
+ *   ddave    (ddave_prob.py:149-169)    player, dist-floor, exit, diamonds, key, spikes, regions,
+ *                                       num-jumps, col-diamonds, dist-win, sol-length
+ *   mdungeon (mdungeon_prob.py:151-171) player, exit, potions, treasures, enemies, regions,
+ *                                       col-potions, col-treasures, col-enemies, dist-win, sol-length
+ *
+ * iparam[] (integer thresholds set by Problem.adjust_param):
+ *   binary   [0] target_path
+ *   zelda    [0] max_enemies  [1] target_enemy_dist [2] target_path
+ *   sokoban  [0] max_crates   [1] target_solution
+ *   ddave    [0] max_diamonds [1] min_spikes [2] target_jumps [3] target_solution
+ *   mdungeon [0] max_enemies  [1] max_potions [2] max_treasures [3] target_solution ; dparam[0] target_col_enemies
+ *
+ * reward_weight[] is in the order the terms are SUMMED in each Problem.get_reward (fp64, left to right):
+ *   binary   regions, path-length                                               (binary_prob.py:105-106)
+ *   zelda    player, key, door, enemies, regions, nearest-enemy, path-length    (zelda_prob.py:136-142)
+ *   sokoban  player, crate, target, regions, ratio, dist-win, sol-length        (sokoban_prob.py:169-175)
+ *   ddave    player, dist-floor, exit, spikes, diamonds, key, regions, num-jumps, dist-win, sol-length (ddave_prob.py:196-205)
+ *   mdungeon player, exit, enemies, treasures, potions, regions, col-enemies, dist-win, sol-length     (mdungeon_prob.py:197-205)
+ */
+typedef struct pcgrl_config {
+  int32_t problem;         /* PCGRL_PROB_*                                                     */
+  int32_t representation;  /* PCGRL_REP_*                                                      */
+  int32_t width, height;   /* Problem._width/_height (problem.py:12-13)                        */
+  int32_t num_tiles;       /* len(get_tile_types())                                            */
+  int32_t max_changes;     /* PcgrlEnv._max_changes (pcgrl_env.py:33,109)                      */
+  int32_t max_iterations;  /* PcgrlEnv._max_iterations (pcgrl_env.py:34,110)                   */
+  uint32_t flags;          /* PCGRL_FLAG_*                                                     */
+  int32_t solver_power;    /* ddave/mdungeon/sokoban _solver_power                             */
+  int32_t iparam[7];
+  double dparam[2];
+  double reward_weight[PCGRL_MAX_STATS];
+  double tile_prob[PCGRL_MAX_TILES]; /* Problem._prob values in tile order (un-normalised)     */
+} pcgrl_config;
+
+/*
+ * Caller-owned state of n environments.  Device pointers for pcgrl_* (host pointers for the
+ * oracle).  n is the batch dimension everywhere.
+ */
+typedef struct pcgrl_buffers {
+  uint8_t* map;         /* [n][H][W]  Representation._map, tile indices                         */
+  uint8_t* heatmap;     /* [n][H][W]  PcgrlEnv._heatmap counts (value-equal to the fp64 array)  */
+  uint8_t* pos;         /* [n][2]     (x, y) cursor of narrow / turtle; unused for wide         */
+  int32_t* iteration;   /* [n]        PcgrlEnv._iteration                                       */
+  int32_t* changes;     /* [n]        PcgrlEnv._changes                                         */
+  int32_t* stats;       /* [n][PCGRL_MAX_STATS]  PcgrlEnv._rep_stats (live state)               */
+  int32_t* start_stats; /* [n][PCGRL_MAX_STATS]  Problem._start_stats                           */
+  int32_t* info_stats;  /* [n][PCGRL_MAX_STATS]  stats at the end of the step, before any auto-reset (-> info) */
+  double* reward;       /* [n]        step output                                              */
+  uint8_t* done;        /* [n]        step output                                              */
+  uint32_t* rng;        /* [n][2][PCGRL_MT_WORDS] MT19937 streams: [0] representation, [1] problem */
+  double* tile_prob;    /* [n][PCGRL_MAX_TILES]  per-env Problem._prob values (binary redraws them) */
+  uint8_t* start_map;   /* [n][H][W]  Representation._old_map (used when RANDOM_START is off)   */
+  uint8_t* start_valid; /* [n]        1 once _old_map holds a map                               */
+  void* scratch;        /* solver work space, pcgrl_scratch_bytes() bytes (may be NULL if that is 0) */
+  size_t scratch_bytes;
+  int32_t* status;      /* [4] device-side diagnostics: [0] != 0 -> a capacity limit was hit    */
+} pcgrl_buffers;
+
+int pcgrl_abi_version(void);
+const char* pcgrl_last_error(void);
+
+/* Checks sizes/ids/limits of a config; 0 if the CUDA path supports it. */
+int pcgrl_config_validate(const pcgrl_config* cfg);
+
+/* Bytes of pcgrl_buffers.scratch needed for n_envs environments (0 for binary / zelda). */
+size_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int n_envs);
+
+/* PcgrlEnv.reset() for every env with mask[i] != 0 (all if mask == NULL).  pcgrl_env.py:66-76 */
+int pcgrl_reset(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const uint8_t* mask_or_null,
+                int n, void* stream);
+
+/* PcgrlEnv.step(action) for n envs.  actions: int32 [n] (narrow/turtle) or [n][3] = (x,y,tile)
+ * (wide).  pcgrl_env.py:129-150 */
+int pcgrl_step(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* actions, int n,
+               void* stream);
+
+/* T consecutive steps in one launch sequence: actions [T][n][adim]; reward_out [T][n], done_out [T][n]
+ * (both may be NULL).  Equivalent to T calls of pcgrl_step. */
+int pcgrl_rollout(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* actions,
+                  double* reward_out, uint8_t* done_out, int T, int n, void* stream);
+
+/* Stand-alone Problem.get_stats on n maps [n][H][W] -> stats_out [n][PCGRL_MAX_STATS]. */
+int pcgrl_get_stats(const pcgrl_config* cfg, const uint8_t* maps, int32_t* stats_out, int n,
+                    void* scratch, size_t scratch_bytes, int32_t* status, void* stream);
+
+/* Seeds both MT19937 streams of env i with numpy's RandomState(seeds[i]) (init_genrand). */
+int pcgrl_seed(const pcgrl_buffers* bufs, const uint32_t* seeds, int n, void* stream);
+
+/* End-to-end step with HOST buffers (the call a reference-side binding makes): copies h_actions
+ * to the device, runs pcgrl_step, copies map / heatmap / pos / reward / done (and info_stats if
+ * non-NULL) back to the host pointers, synchronises.  d_actions is a device staging buffer of
+ * n*adim int32.  Host pointers should be pinned for full copy bandwidth. */
+typedef struct pcgrl_host_io {
+  const int32_t* actions; /* in  [n][adim]            */
+  uint8_t* map;           /* out [n][H][W] or NULL    */
+  uint8_t* heatmap;       /* out [n][H][W] or NULL    */
+  uint8_t* pos;           /* out [n][2]    or NULL    */
+  double* reward;         /* out [n]                  */
+  uint8_t* done;          /* out [n]                  */
+  int32_t* info_stats;    /* out [n][PCGRL_MAX_STATS] or NULL */
+} pcgrl_host_io;
+int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions,
+                    const pcgrl_host_io* io, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGRL_B200_H */

@@ -1,0 +1,448 @@
+// pcgrl_b200.cu -- kernels + C ABI (include/pcgrl_b200.h) of the batched PcgrlEnv hot path, sm_100a.
+//
+// Kernels (one warp per environment, 4 warps per CTA):
+//   k_rollout<PROB>     fused PcgrlEnv.step x T for the graph-only problems (binary, zelda):
+//                       Representation.update -> get_stats -> get_reward/get_episode_over -> auto reset
+//   k_reset<PROB>       PcgrlEnv.reset
+//   k_get_stats<PROB>   stand-alone Problem.get_stats operator
+//   k_seed              numpy RandomState(seed) == MT19937 init_genrand
+// Solver problems (sokoban, ddave, mdungeon) run update / solver / finish as separate launches, see
+// pcgrl_solver.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pcgrl_env.cuh"
+#include "pcgrl_solver.cuh"
+
+using namespace pcgrl;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+#define WPB PCGRL_WARPS_PER_BLOCK
+
+template <int N>
+__device__ __forceinline__ void load_row(const int32_t* __restrict__ src, int* dst) {
+#pragma unroll
+  for (int i = 0; i < N; i++) dst[i] = src[i];
+}
+template <int N>
+__device__ __forceinline__ void store_row(int32_t* dst, const int* src, int lane) {
+#pragma unroll
+  for (int i = 0; i < N; i++) if (lane == i) dst[i] = src[i];
+}
+
+template <int PROB>
+__global__ void __launch_bounds__(32 * WPB) k_rollout(const __grid_constant__ pcgrl_config cfg,
+                                                      const __grid_constant__ pcgrl_buffers b,
+                                                      const int32_t* __restrict__ actions, double* reward_out,
+                                                      uint8_t* done_out, int T, int n) {
+  constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
+  __shared__ WarpSmem smem[WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * WPB + wib;
+  if (e >= n) return;
+  WarpSmem& sm = smem[wib];
+  const int W = cfg.width, H = cfg.height, cells = W * H;
+  const int adim = (cfg.representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
+  const EnvRefs r = env_refs(cfg, b, e);
+
+  Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
+  int x = 0, y = 0;
+  if (cfg.representation != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
+  int iteration = b.iteration[e], changes = b.changes[e];
+  int st[NS], start[NS];
+  load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
+  load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
+  WarpRng rng;
+  rng.init(r.rng_rep);
+
+  for (int t = 0; t < T; t++) {
+    const int32_t* act = actions + ((size_t)t * n + e) * adim;
+    iteration++;  // pcgrl_env.py:130
+    int old[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) old[i] = st[i];
+    int hx, hy;
+    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy);
+    if (change > 0) {  // pcgrl_env.py:135-138
+      changes += change;
+      bool unused;
+      map_stats<PROB>(board, cfg, lane, st, unused);
+    }
+    const double reward = problem_reward<PROB>(cfg, st, old);                     // :142
+    const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
+                      iteration >= cfg.max_iterations;                            // :143
+    if (lane == 0) {
+      b.reward[e] = reward;
+      b.done[e] = done ? 1 : 0;
+      if (reward_out) reward_out[(size_t)t * n + e] = reward;
+      if (done_out) done_out[(size_t)t * n + e] = done ? 1 : 0;
+    }
+    if (t == T - 1) store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+    if (done && auto_reset) {
+      bool unused;
+      env_reset<PROB>(cfg, b, e, lane, sm, rng, board, x, y, st, unused);
+#pragma unroll
+      for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
+      iteration = 0;
+      changes = 0;
+    } else if (change > 0) {
+      heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
+    }
+  }
+  rng.finish(lane);
+  if (lane == 0) {
+    if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
+    b.iteration[e] = iteration;
+    b.changes[e] = changes;
+  }
+  store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start, lane);
+}
+
+template <int PROB>
+__global__ void __launch_bounds__(32 * WPB) k_reset(const __grid_constant__ pcgrl_config cfg,
+                                                    const __grid_constant__ pcgrl_buffers b,
+                                                    const uint8_t* __restrict__ mask, SolverQueue q, int n) {
+  constexpr int NS = ProblemTraits<PROB>::NSTATS;
+  __shared__ WarpSmem smem[WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * WPB + wib;
+  if (e >= n) return;
+  if (mask && mask[e] == 0) return;
+  const EnvRefs r = env_refs(cfg, b, e);
+  WarpRng rng;
+  rng.init(r.rng_rep);
+  Board board;
+  int x = 0, y = 0, st[NS];
+  bool need_solver;
+  env_reset<PROB>(cfg, b, e, lane, smem[wib], rng, board, x, y, st, need_solver);
+  rng.finish(lane);
+  if (lane == 0) {
+    if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
+    b.iteration[e] = 0;
+    b.changes[e] = 0;
+    b.reward[e] = 0.0;
+    b.done[e] = 0;
+  }
+  store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  if constexpr (ProblemTraits<PROB>::SOLVER) if (need_solver) solver_enqueue(q, e, SOLVE_FOR_RESET, lane);
+}
+
+template <int PROB>
+__global__ void __launch_bounds__(32 * WPB) k_get_stats(const __grid_constant__ pcgrl_config cfg,
+                                                        const uint8_t* __restrict__ maps, int32_t* stats_out,
+                                                        SolverQueue q, int n) {
+  constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
+  __shared__ WarpSmem smem[WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * WPB + wib;
+  if (e >= n) return;
+  const Board board = load_board<NP>(maps + (size_t)e * cfg.width * cfg.height, cfg.width, cfg.height, lane, smem[wib].bits);
+  int st[NS];
+  bool need_solver;
+  map_stats<PROB>(board, cfg, lane, st, need_solver);
+  store_row<NS>(stats_out + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  if (lane >= NS && lane < PCGRL_MAX_STATS) stats_out[(size_t)e * PCGRL_MAX_STATS + lane] = 0;
+  if constexpr (ProblemTraits<PROB>::SOLVER) if (need_solver) solver_enqueue(q, e, SOLVE_STATS_ONLY, lane);
+}
+
+// Solver problems, phase A of PcgrlEnv.step: Representation.update + map part of get_stats.
+template <int PROB>
+__global__ void __launch_bounds__(32 * WPB) k_step_update(const __grid_constant__ pcgrl_config cfg,
+                                                          const __grid_constant__ pcgrl_buffers b,
+                                                          const int32_t* __restrict__ actions, SolverQueue q,
+                                                          int32_t* old_stats, uint8_t* heat_cell, int n) {
+  constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
+  __shared__ WarpSmem smem[WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * WPB + wib;
+  if (e >= n) return;
+  const int W = cfg.width, H = cfg.height;
+  const int adim = (cfg.representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const EnvRefs r = env_refs(cfg, b, e);
+  Board board = load_board<NP>(r.map, W, H, lane, smem[wib].bits);
+  int x = 0, y = 0;
+  if (cfg.representation != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
+  int st[NS];
+  load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
+  store_row<NS>(old_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);  // old_stats = self._rep_stats (pcgrl_env.py:132)
+  WarpRng rng;
+  rng.init(r.rng_rep);
+  int hx, hy;
+  const int change = apply_action(cfg, actions + (size_t)e * adim, board, r.map, rng, lane, x, y, hx, hy);
+  rng.finish(lane);
+  if (lane == 0) {
+    if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
+    b.iteration[e] += 1;
+    b.changes[e] += change;
+    heat_cell[3 * e] = (uint8_t)change;  // consumed by k_step_finish
+    heat_cell[3 * e + 1] = (uint8_t)hx;
+    heat_cell[3 * e + 2] = (uint8_t)hy;
+  }
+  if (change > 0) {
+    bool need_solver;
+    map_stats<PROB>(board, cfg, lane, st, need_solver);
+    store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+    if (need_solver) solver_enqueue(q, e, SOLVE_FOR_STEP, lane);
+  }
+}
+
+// Solver problems, phase B: get_reward / get_episode_over / info, heat map, auto reset (whose new map may
+// again need the solver -> second queue).
+template <int PROB>
+__global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant__ pcgrl_config cfg,
+                                                          const __grid_constant__ pcgrl_buffers b, SolverQueue q,
+                                                          const int32_t* __restrict__ old_stats,
+                                                          const uint8_t* __restrict__ heat_cell, int n) {
+  constexpr int NS = ProblemTraits<PROB>::NSTATS;
+  __shared__ WarpSmem smem[WPB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int e = blockIdx.x * WPB + wib;
+  if (e >= n) return;
+  const int W = cfg.width, H = cfg.height, cells = W * H;
+  int st[NS], old[NS], start[NS];
+  load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
+  load_row<NS>(old_stats + (size_t)e * PCGRL_MAX_STATS, old);
+  load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
+  const int iteration = b.iteration[e], changes = b.changes[e];
+  const double reward = problem_reward<PROB>(cfg, st, old);
+  const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes || iteration >= cfg.max_iterations;
+  if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
+  store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  const int change = heat_cell[3 * e], hx = heat_cell[3 * e + 1], hy = heat_cell[3 * e + 2];
+  if (done && (cfg.flags & PCGRL_FLAG_AUTO_RESET)) {
+    const EnvRefs r = env_refs(cfg, b, e);
+    WarpRng rng;
+    rng.init(r.rng_rep);
+    Board board;
+    int x = 0, y = 0;
+    bool need_solver;
+    env_reset<PROB>(cfg, b, e, lane, smem[wib], rng, board, x, y, st, need_solver);
+    rng.finish(lane);
+    if (lane == 0) {
+      if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
+      b.iteration[e] = 0;
+      b.changes[e] = 0;
+    }
+    store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+    store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+    if (need_solver) solver_enqueue(q, e, SOLVE_FOR_RESET, lane);
+  } else if (change > 0) {
+    heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);
+  }
+  (void)H;
+}
+
+__global__ void k_seed(uint32_t* rng, const uint32_t* __restrict__ seeds, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  uint32_t* a = rng + (size_t)e * 2 * PCGRL_MT_WORDS;
+  uint32_t* c = a + PCGRL_MT_WORDS;
+  uint32_t v = seeds[e];
+  a[0] = v; c[0] = v;
+  for (int i = 1; i < 624; i++) {  // init_genrand
+    v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+    a[i] = v; c[i] = v;
+  }
+  a[624] = 624; c[624] = 624;  // RandomState(seed).get_state()[2]
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: C ABI
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int rc, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return rc;
+}
+static int cuda_rc(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+extern "C" int pcgrl_abi_version(void) { return PCGRL_ABI_VERSION; }
+extern "C" const char* pcgrl_last_error(void) { return g_err; }
+
+extern "C" int pcgrl_config_validate(const pcgrl_config* c) {
+  static const int ntiles[PCGRL_NUM_PROBLEMS] = {2, 8, 5, 7, 8};
+  if (!c) return fail(-1, "config is NULL");
+  if (c->problem < 0 || c->problem >= PCGRL_NUM_PROBLEMS) return fail(-1, "unknown problem id");
+  if (c->representation < 0 || c->representation >= PCGRL_NUM_REPS) return fail(-1, "unknown representation id");
+  if (c->width < 1 || c->width > PCGRL_MAX_DIM || c->height < 1 || c->height > PCGRL_MAX_DIM)
+    return fail(-1, "width/height must be in [1, 32] (one bitboard row per warp lane)");
+  if (c->num_tiles != ntiles[c->problem]) return fail(-1, "num_tiles does not match the problem's tile alphabet");
+  if (c->max_changes < 1 || c->max_changes > 255) return fail(-1, "max_changes must be in [1, 255] (uint8 heat map)");
+  if (c->max_iterations < 1) return fail(-1, "max_iterations must be >= 1");
+  double tot = 0;
+  for (int t = 0; t < c->num_tiles; t++) {
+    if (!(c->tile_prob[t] >= 0)) return fail(-1, "tile probabilities must be >= 0");
+    tot += c->tile_prob[t];
+  }
+  if (!(tot > 0)) return fail(-1, "tile probabilities must not all be zero");
+  if (c->problem >= PCGRL_PROB_SOKOBAN) {
+    const int rc = solver_validate(c);
+    if (rc) return fail(-1, solver_validate_message(rc));
+  }
+  return 0;
+}
+
+extern "C" size_t pcgrl_scratch_bytes(const pcgrl_config* c, int n_envs) {
+  if (!c || n_envs <= 0 || c->problem < PCGRL_PROB_SOKOBAN) return 0;
+  return solver_scratch_bytes(c, n_envs);
+}
+
+static int check_common(const pcgrl_config* cfg, const pcgrl_buffers* b, int n) {
+  if (!cfg || !b) return fail(-1, "NULL config / buffers");
+  if (n <= 0) return fail(-1, "n must be > 0");
+  const int rc = pcgrl_config_validate(cfg);
+  if (rc) return rc;
+  if (!b->map || !b->heatmap || !b->pos || !b->iteration || !b->changes || !b->stats || !b->start_stats ||
+      !b->info_stats || !b->reward || !b->done || !b->rng || !b->tile_prob || !b->start_map || !b->start_valid ||
+      !b->status)
+    return fail(-1, "a pcgrl_buffers pointer is NULL");
+  if (cfg->problem >= PCGRL_PROB_SOKOBAN && (!b->scratch || b->scratch_bytes < pcgrl_scratch_bytes(cfg, n)))
+    return fail(-1, "scratch buffer too small: see pcgrl_scratch_bytes()");
+  return 0;
+}
+
+static inline dim3 env_grid(int n) { return dim3((unsigned)((n + WPB - 1) / WPB)); }
+
+template <int PROB>
+static int reset_impl(const pcgrl_config* cfg, const pcgrl_buffers* b, const uint8_t* mask, int n, cudaStream_t s) {
+  SolverQueue q = solver_queue(cfg, b->scratch, n, 0, b->status);
+  if constexpr (ProblemTraits<PROB>::SOLVER) solver_queue_clear(q, s);
+  k_reset<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, mask, q, n);
+  if constexpr (ProblemTraits<PROB>::SOLVER) solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q, b->scratch, n, s);
+  return cuda_rc(cudaGetLastError(), "pcgrl_reset launch");
+}
+
+extern "C" int pcgrl_reset(const pcgrl_config* cfg, const pcgrl_buffers* b, const uint8_t* mask, int n, void* stream) {
+  int rc = check_common(cfg, b, n);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (cfg->problem) {
+    case PCGRL_PROB_BINARY: return reset_impl<PCGRL_PROB_BINARY>(cfg, b, mask, n, s);
+    case PCGRL_PROB_ZELDA: return reset_impl<PCGRL_PROB_ZELDA>(cfg, b, mask, n, s);
+    case PCGRL_PROB_SOKOBAN: return reset_impl<PCGRL_PROB_SOKOBAN>(cfg, b, mask, n, s);
+    case PCGRL_PROB_DDAVE: return reset_impl<PCGRL_PROB_DDAVE>(cfg, b, mask, n, s);
+    default: return reset_impl<PCGRL_PROB_MDUNGEON>(cfg, b, mask, n, s);
+  }
+}
+
+template <int PROB>
+static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                         uint8_t* done_out, int T, int n, cudaStream_t s) {
+  k_rollout<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n);
+  return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
+}
+
+// one PcgrlEnv.step of a solver problem = update -> solver -> finish(+reset) -> solver
+template <int PROB>
+static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, cudaStream_t s) {
+  SolverQueue q1 = solver_queue(cfg, b->scratch, n, 0, b->status), q2 = solver_queue(cfg, b->scratch, n, 1, b->status);
+  int32_t* old_stats = solver_old_stats(cfg, b->scratch, n);
+  uint8_t* heat_cell = solver_heat_cell(cfg, b->scratch, n);
+  solver_queue_clear(q1, s);
+  solver_queue_clear(q2, s);
+  k_step_update<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, q1, old_stats, heat_cell, n);
+  solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q1, b->scratch, n, s);
+  k_step_finish<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, q2, old_stats, heat_cell, n);
+  if (cfg->flags & PCGRL_FLAG_AUTO_RESET) solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q2, b->scratch, n, s);
+  return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
+}
+
+template <int PROB>
+static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                          uint8_t* done_out, int T, int n, cudaStream_t s) {
+  const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
+  for (int t = 0; t < T; t++) {
+    int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s);
+    if (rc) return rc;
+    if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n, b->reward, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
+    if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n, b->done, (size_t)n, cudaMemcpyDeviceToDevice, s);
+  }
+  return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
+}
+
+extern "C" int pcgrl_rollout(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                             uint8_t* done_out, int T, int n, void* stream) {
+  int rc = check_common(cfg, b, n);
+  if (rc) return rc;
+  if (!actions) return fail(-1, "actions is NULL");
+  if (T <= 0) return fail(-1, "T must be > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (cfg->problem) {
+    case PCGRL_PROB_BINARY: return rollout_fused<PCGRL_PROB_BINARY>(cfg, b, actions, reward_out, done_out, T, n, s);
+    case PCGRL_PROB_ZELDA: return rollout_fused<PCGRL_PROB_ZELDA>(cfg, b, actions, reward_out, done_out, T, n, s);
+    case PCGRL_PROB_SOKOBAN: return rollout_solver<PCGRL_PROB_SOKOBAN>(cfg, b, actions, reward_out, done_out, T, n, s);
+    case PCGRL_PROB_DDAVE: return rollout_solver<PCGRL_PROB_DDAVE>(cfg, b, actions, reward_out, done_out, T, n, s);
+    default: return rollout_solver<PCGRL_PROB_MDUNGEON>(cfg, b, actions, reward_out, done_out, T, n, s);
+  }
+}
+
+extern "C" int pcgrl_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, void* stream) {
+  return pcgrl_rollout(cfg, b, actions, nullptr, nullptr, 1, n, stream);
+}
+
+template <int PROB>
+static int get_stats_impl(const pcgrl_config* cfg, const uint8_t* maps, int32_t* out, int n, void* scratch,
+                          int32_t* status, cudaStream_t s) {
+  SolverQueue q = solver_queue(cfg, scratch, n, 0, status);
+  if constexpr (ProblemTraits<PROB>::SOLVER) solver_queue_clear(q, s);
+  k_get_stats<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, maps, out, q, n);
+  if constexpr (ProblemTraits<PROB>::SOLVER) solver_launch<PROB>(cfg, out, nullptr, maps, q, scratch, n, s);
+  return cuda_rc(cudaGetLastError(), "pcgrl_get_stats launch");
+}
+
+extern "C" int pcgrl_get_stats(const pcgrl_config* cfg, const uint8_t* maps, int32_t* stats_out, int n, void* scratch,
+                               size_t scratch_bytes, int32_t* status, void* stream) {
+  if (!cfg || !maps || !stats_out || !status) return fail(-1, "NULL argument");
+  if (n <= 0) return fail(-1, "n must be > 0");
+  int rc = pcgrl_config_validate(cfg);
+  if (rc) return rc;
+  if (cfg->problem >= PCGRL_PROB_SOKOBAN && (!scratch || scratch_bytes < pcgrl_scratch_bytes(cfg, n)))
+    return fail(-1, "scratch buffer too small: see pcgrl_scratch_bytes()");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (cfg->problem) {
+    case PCGRL_PROB_BINARY: return get_stats_impl<PCGRL_PROB_BINARY>(cfg, maps, stats_out, n, scratch, status, s);
+    case PCGRL_PROB_ZELDA: return get_stats_impl<PCGRL_PROB_ZELDA>(cfg, maps, stats_out, n, scratch, status, s);
+    case PCGRL_PROB_SOKOBAN: return get_stats_impl<PCGRL_PROB_SOKOBAN>(cfg, maps, stats_out, n, scratch, status, s);
+    case PCGRL_PROB_DDAVE: return get_stats_impl<PCGRL_PROB_DDAVE>(cfg, maps, stats_out, n, scratch, status, s);
+    default: return get_stats_impl<PCGRL_PROB_MDUNGEON>(cfg, maps, stats_out, n, scratch, status, s);
+  }
+}
+
+extern "C" int pcgrl_seed(const pcgrl_buffers* b, const uint32_t* seeds, int n, void* stream) {
+  if (!b || !b->rng || !seeds) return fail(-1, "NULL argument");
+  if (n <= 0) return fail(-1, "n must be > 0");
+  k_seed<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->rng, seeds, n);
+  return cuda_rc(cudaGetLastError(), "pcgrl_seed launch");
+}
+
+extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions,
+                               const pcgrl_host_io* io, int n, void* stream) {
+  if (!io || !io->actions || !io->reward || !io->done || !d_actions) return fail(-1, "NULL host io pointer");
+  int rc = check_common(cfg, b, n);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t cells = (size_t)cfg->width * cfg->height;
+  const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
+  cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
+  rc = pcgrl_step(cfg, b, d_actions, n, stream);
+  if (rc) return rc;
+  if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
+  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, cells * n, cudaMemcpyDeviceToHost, s);
+  if (io->pos && cfg->representation != PCGRL_REP_WIDE) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(io->reward, b->reward, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(io->done, b->done, (size_t)n, cudaMemcpyDeviceToHost, s);
+  if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
+  return cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
+}

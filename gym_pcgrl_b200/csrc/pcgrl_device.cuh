@@ -1,0 +1,351 @@
+// pcgrl_device.cuh -- warp-level building blocks of the batched PcgrlEnv hot path (sm_100a).
+//
+// Execution model: ONE WARP PER ENVIRONMENT.  Lane r owns map row r as bitboards (bit x <-> column x):
+// three bit-planes of the tile index (tiles < 8).  Graph routines are frontier propagations
+//   next = (f | f<<1 | f>>1 | shfl_up(f) | shfl_down(f)) & passable
+// with warp votes for termination, so a BFS wave costs ~10 warp instructions and no memory traffic.
+// The reference's Python equivalents are cited per function (G = gym_pcgrl/envs).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pcgrl_b200.h"
+
+#define FULL_MASK 0xffffffffu
+#define PCGRL_WARPS_PER_BLOCK 4
+#define PCGRL_SBITS_STRIDE 34 /* 33 words used per plane (chunks + 1 guard) */
+
+namespace pcgrl {
+
+// ------------------------------------------------------------------------------------------------
+// per-warp shared scratch
+// ------------------------------------------------------------------------------------------------
+struct WarpSmem {
+  uint32_t bits[3 * PCGRL_SBITS_STRIDE];  // ballot words of the three tile bit-planes (row-major bit stream)
+  uint32_t draws[64];                     // tempered MT19937 outputs for one 32-cell chunk of gen_random_map
+};
+
+// ------------------------------------------------------------------------------------------------
+// MT19937 (numpy legacy RandomState) -- state lives in HBM: 624 words + word 624 = position.
+// The warp caches 32 consecutive tempered words in registers; a draw is one shuffle.
+// numpy: random/src/mt19937/mt19937.c (mt19937_gen), _legacy random_sample, _bounded_integers masked rejection.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// In-place twist by one warp.  Batches of 32 consecutive indices: new[i] depends on old[i], old[i+1] and
+// (i < 227 ? old[i+397] : new[i-227]); the dependency distance (227) exceeds the batch width, and every
+// lane reads its inputs before any lane of the batch writes, so the result equals the sequential loop.
+__device__ __noinline__ void mt_twist_warp(uint32_t* k, int lane) {
+  __syncwarp();
+  for (int base = 0; base < 624; base += 32) {
+    const int i = base + lane;
+    uint32_t a = 0, b = 0, c = 0;
+    if (i < 624) {
+      a = k[i];
+      b = k[(i + 1 == 624) ? 0 : i + 1];
+      c = k[(i < 227) ? i + 397 : i - 227];
+    }
+    __syncwarp();
+    if (i < 624) {
+      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      k[i] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+  }
+}
+
+struct WarpRng {
+  uint32_t* st;
+  int pos;         // numpy `pos`
+  int base;        // index held by lane 0 of `cache`, or < -31 when invalid
+  uint32_t cache;  // tempered st[base + lane]
+  bool dirty;
+
+  __device__ __forceinline__ void init(uint32_t* s) {
+    st = s;
+    pos = (int)s[624];
+    base = -1000;
+    cache = 0;
+    dirty = false;
+  }
+  __device__ __forceinline__ uint32_t next(int lane) {
+    if (pos >= 624) {
+      mt_twist_warp(st, lane);
+      pos = 0;
+      base = -1000;
+    }
+    if (pos - base >= 32) {
+      base = pos;
+      const int i = pos + lane;
+      cache = mt_temper((i < 624) ? st[i] : 0u);
+    }
+    const uint32_t v = __shfl_sync(FULL_MASK, cache, pos - base);
+    pos++;
+    dirty = true;
+    return v;
+  }
+  // RandomState.random_sample(): two draws -> 53-bit double
+  __device__ __forceinline__ double next_double(int lane) {
+    const uint32_t a = next(lane) >> 5, b = next(lane) >> 6;
+    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+  }
+  // RandomState.randint(n): masked rejection sampling, one 32-bit draw per attempt, none if n == 1
+  __device__ __forceinline__ int randint(int n, int lane) {
+    const uint32_t rng = (uint32_t)(n - 1);
+    if (rng == 0) return 0;
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t v;
+    do { v = next(lane) & mask; } while (v > rng);
+    return (int)v;
+  }
+  // `count` (<= 64) consecutive tempered draws into shared memory
+  __device__ __forceinline__ void fill(uint32_t* buf, int count, int lane) {
+    int filled = 0;
+    while (filled < count) {
+      if (pos >= 624) {
+        mt_twist_warp(st, lane);
+        pos = 0;
+      }
+      const int m = min(count - filled, 624 - pos);
+      for (int i = lane; i < m; i += 32) buf[filled + i] = mt_temper(st[pos + i]);
+      pos += m;
+      filled += m;
+    }
+    base = -1000;
+    dirty = true;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void finish(int lane) {
+    if (dirty && lane == 0) st[624] = (uint32_t)pos;
+    __syncwarp();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// bitboards
+// ------------------------------------------------------------------------------------------------
+struct Board {
+  uint32_t p0, p1, p2;  // bit-planes of this lane's row
+};
+
+__device__ __forceinline__ uint32_t row_mask(int W, int H, int lane) {
+  return (lane < H) ? ((W >= 32) ? FULL_MASK : ((1u << W) - 1u)) : 0u;
+}
+
+// mask of the cells of this row whose tile index is in TYPES (bit t of TYPES <-> tile t)
+template <unsigned TYPES>
+__device__ __forceinline__ uint32_t type_mask(const Board& b, uint32_t rmask) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    if ((TYPES >> t) & 1u) m |= ((t & 1) ? b.p0 : ~b.p0) & ((t & 2) ? b.p1 : ~b.p1) & ((t & 4) ? b.p2 : ~b.p2);
+  }
+  return m & rmask;
+}
+
+__device__ __forceinline__ int tile_at(const Board& b, int x) {
+  return (int)(((b.p0 >> x) & 1u) | (((b.p1 >> x) & 1u) << 1) | (((b.p2 >> x) & 1u) << 2));
+}
+
+__device__ __forceinline__ void set_tile(Board& b, int x, int t) {
+  const uint32_t bit = 1u << x;
+  b.p0 = (t & 1) ? (b.p0 | bit) : (b.p0 & ~bit);
+  b.p1 = (t & 2) ? (b.p1 | bit) : (b.p1 & ~bit);
+  b.p2 = (t & 4) ? (b.p2 | bit) : (b.p2 & ~bit);
+}
+
+// One 32-cell chunk of the row-major tile stream -> three ballot words in shared memory.
+template <int NPLANES>
+__device__ __forceinline__ void chunk_to_bits(uint32_t tile, int chunk, int lane, uint32_t* sbits) {
+  const uint32_t b0 = __ballot_sync(FULL_MASK, tile & 1u);
+  uint32_t b1 = 0, b2 = 0;
+  if (NPLANES > 1) {
+    b1 = __ballot_sync(FULL_MASK, tile & 2u);
+    b2 = __ballot_sync(FULL_MASK, tile & 4u);
+  }
+  if (lane == 0) {
+    sbits[chunk] = b0;
+    sbits[PCGRL_SBITS_STRIDE + chunk] = b1;
+    sbits[2 * PCGRL_SBITS_STRIDE + chunk] = b2;
+  }
+}
+
+// Row r = bits [r*W, r*W+W) of the stream: funnel shift of two adjacent ballot words.
+template <int NPLANES>
+__device__ __forceinline__ Board bits_to_board(uint32_t* sbits, int nchunks, int W, int H, int lane) {
+  if (lane == 0) {  // guard word read by the funnel shift of the last row
+    sbits[nchunks] = 0;
+    sbits[PCGRL_SBITS_STRIDE + nchunks] = 0;
+    sbits[2 * PCGRL_SBITS_STRIDE + nchunks] = 0;
+  }
+  __syncwarp();
+  Board b = {0u, 0u, 0u};
+  if (lane < H) {
+    const int off = lane * W, wi = off >> 5, sh = off & 31;
+    const uint32_t m = (W >= 32) ? FULL_MASK : ((1u << W) - 1u);
+    b.p0 = __funnelshift_r(sbits[wi], sbits[wi + 1], sh) & m;
+    if (NPLANES > 1) {
+      b.p1 = __funnelshift_r(sbits[PCGRL_SBITS_STRIDE + wi], sbits[PCGRL_SBITS_STRIDE + wi + 1], sh) & m;
+      b.p2 = __funnelshift_r(sbits[2 * PCGRL_SBITS_STRIDE + wi], sbits[2 * PCGRL_SBITS_STRIDE + wi + 1], sh) & m;
+    }
+  }
+  __syncwarp();
+  return b;
+}
+
+// Coalesced byte loads of one env's uint8[H][W] map (the packed map batch in HBM) -> bitboards.
+template <int NPLANES>
+__device__ __forceinline__ Board load_board(const uint8_t* __restrict__ g, int W, int H, int lane, uint32_t* sbits) {
+  const int cells = W * H, nchunks = (cells + 31) >> 5;
+  for (int c = 0; c < nchunks; c++) {
+    const int i = c * 32 + lane;
+    const uint32_t t = (i < cells) ? (uint32_t)g[i] : 0u;
+    chunk_to_bits<NPLANES>(t, c, lane, sbits);
+  }
+  return bits_to_board<NPLANES>(sbits, nchunks, W, H, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph routines on bitboards
+// ------------------------------------------------------------------------------------------------
+// 4-neighbourhood dilation (includes f).  Lane 0 / lane 31 receive their own word from the shuffles,
+// which is harmless here because f itself is OR-ed in.
+__device__ __forceinline__ uint32_t dilate(uint32_t f) {
+  return f | (f << 1) | (f >> 1) | __shfl_up_sync(FULL_MASK, f, 1) | __shfl_down_sync(FULL_MASK, f, 1);
+}
+
+// neighbours only (exact zero beyond the top / bottom rows)
+__device__ __forceinline__ uint32_t neighbours(uint32_t f, int lane) {
+  uint32_t up = __shfl_up_sync(FULL_MASK, f, 1), dn = __shfl_down_sync(FULL_MASK, f, 1);
+  if (lane == 0) up = 0;
+  if (lane == 31) dn = 0;
+  return (f << 1) | (f >> 1) | up | dn;
+}
+
+__device__ __forceinline__ int popc_all(uint32_t m) { return (int)__reduce_add_sync(FULL_MASK, (unsigned)__popc(m)); }
+
+// first set cell in row-major order (G/helper.py:16-23 location order); returns false if m is empty
+__device__ __forceinline__ bool first_cell(uint32_t m, int& row, int& col) {
+  const uint32_t rows = __ballot_sync(FULL_MASK, m != 0u);
+  if (rows == 0u) return false;
+  row = __ffs(rows) - 1;
+  col = __shfl_sync(FULL_MASK, __ffs(m) - 1, row);
+  return true;
+}
+
+__device__ __forceinline__ uint32_t cell_bit(int row, int col, int lane) { return (lane == row) ? (1u << col) : 0u; }
+
+// BFS from `seed` over `pass` (G/helper.py:222-237 run_dikjstra): returns the eccentricity of the seed inside
+// its component, the visited set and the last non-empty frontier (the cells at maximum distance).
+__device__ __forceinline__ int bfs_ecc(uint32_t seed, uint32_t pass, uint32_t& visited, uint32_t& last) {
+  uint32_t f = seed;
+  visited = seed;
+  int d = 0;
+  while (true) {
+    const uint32_t n = dilate(f) & pass & ~visited;
+    if (!__any_sync(FULL_MASK, n != 0u)) break;
+    visited |= n;
+    f = n;
+    d++;
+  }
+  last = f;
+  return d;
+}
+
+// flood fill without levels (component mask of seed)
+__device__ __forceinline__ uint32_t flood(uint32_t seed, uint32_t pass) {
+  uint32_t v = seed;
+  while (true) {
+    const uint32_t n = dilate(v) & pass;
+    if (!__any_sync(FULL_MASK, n != v)) break;
+    v = n;
+  }
+  return v;
+}
+
+// distance from seed to the target cell over `pass`, -1 if unreachable or the seed is not passable
+// (G/helper.py:222-237 semantics, used by zelda_prob.py:104-110)
+__device__ __forceinline__ int bfs_dist_to(uint32_t seed, uint32_t target, uint32_t pass) {
+  uint32_t f = seed & pass, visited = f;
+  int d = 0;
+  if (!__any_sync(FULL_MASK, f != 0u)) return -1;
+  while (true) {
+    if (__any_sync(FULL_MASK, (f & target) != 0u)) return d;
+    const uint32_t n = dilate(f) & pass & ~visited;
+    if (!__any_sync(FULL_MASK, n != 0u)) return -1;
+    visited |= n;
+    f = n;
+    d++;
+  }
+}
+
+// G/helper.py:197-207 calc_num_regions: number of 4-connected components of `pass`.
+__device__ __forceinline__ int count_regions(uint32_t pass, int lane) {
+  const uint32_t iso = pass & ~neighbours(pass, lane);  // single-cell components, all at once
+  int regions = popc_all(iso);
+  uint32_t remaining = pass & ~iso;
+  int row, col;
+  while (first_cell(remaining, row, col)) {
+    remaining &= ~flood(cell_bit(row, col, lane), remaining);
+    regions++;
+  }
+  return regions;
+}
+
+// G/helper.py:197-207 + :250-264 fused: regions and calc_longest_path of `pass`.
+// Per component (processed in row-major order of its first cell, like the reference): BFS from the first
+// cell, np.argmax tie-break = row-major-first cell of the last frontier, BFS from there, keep the max.
+// Exact prunings: single-cell components contribute 0; a component whose first sweep has eccentricity d1
+// has diameter <= 2*d1, so its second sweep is skipped when 2*d1 <= best.
+__device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane, int& regions_out, int& path_out) {
+  const uint32_t iso = pass & ~neighbours(pass, lane);
+  int regions = popc_all(iso), best = 0;
+  uint32_t remaining = pass & ~iso;
+  int row, col;
+  while (first_cell(remaining, row, col)) {
+    uint32_t visited, last;
+    const int d1 = bfs_ecc(cell_bit(row, col, lane), remaining, visited, last);
+    remaining &= ~visited;
+    regions++;
+    if (2 * d1 > best) {
+      first_cell(last, row, col);
+      uint32_t v2, l2;
+      const int d2 = bfs_ecc(cell_bit(row, col, lane), visited, v2, l2);
+      best = max(best, d2);
+    }
+  }
+  regions_out = regions;
+  path_out = best;
+}
+
+// G/helper.py:37-62 get_floor_dist(map, from, floor): sum over `from` cells of the number of cells strictly
+// between the cell and the first floor cell below it (H-1 if there is none).
+__device__ __forceinline__ int floor_dist(uint32_t from, uint32_t floor_m, int H, int lane) {
+  int total = 0, row, col;
+  while (first_cell(from, row, col)) {
+    from &= ~cell_bit(row, col, lane);
+    const uint32_t column = __ballot_sync(FULL_MASK, (floor_m >> col) & 1u);
+    const uint32_t below = (row >= 31) ? 0u : (column >> (row + 1));
+    total += below ? (__ffs(below) - 1) : (H - 1);
+  }
+  return total;
+}
+
+// G/helper.py:366-376 get_range_reward in fp64 (bounds may be +-inf)
+__device__ __forceinline__ double range_reward(double nv, double ov, double low, double high) {
+  if (nv >= low && nv <= high && ov >= low && ov <= high) return 0.0;
+  if (ov <= high && nv <= high) return fmin(nv, low) - fmin(ov, low);
+  if (ov >= low && nv >= low) return fmax(ov, high) - fmax(nv, high);
+  if (nv > high && ov < low) return high - nv + ov - low;
+  if (nv < low && ov > high) return high - ov + nv - low;
+  return 0.0;
+}
+
+}  // namespace pcgrl

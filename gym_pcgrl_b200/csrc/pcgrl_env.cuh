@@ -1,0 +1,160 @@
+// pcgrl_env.cuh -- PcgrlEnv.reset / Representation.update for one warp = one environment.
+// Reference: gym_pcgrl/envs/pcgrl_env.py:66-76,129-150; reps/{narrow,turtle,wide}_rep.py; helper.py:310-352.
+#pragma once
+#include "pcgrl_problems.cuh"
+
+namespace pcgrl {
+
+struct EnvRefs {  // per-env base pointers
+  uint8_t* map;
+  uint8_t* heat;
+  uint8_t* start_map;
+  uint32_t* rng_rep;
+  uint32_t* rng_prob;
+  double* tile_prob;
+};
+
+__device__ __forceinline__ EnvRefs env_refs(const pcgrl_config& cfg, const pcgrl_buffers& b, int e) {
+  const size_t cells = (size_t)cfg.width * cfg.height;
+  EnvRefs r;
+  r.map = b.map + (size_t)e * cells;
+  r.heat = b.heatmap + (size_t)e * cells;
+  r.start_map = b.start_map + (size_t)e * cells;
+  r.rng_rep = b.rng + (size_t)e * 2 * PCGRL_MT_WORDS;
+  r.rng_prob = r.rng_rep + PCGRL_MT_WORDS;
+  r.tile_prob = b.tile_prob + (size_t)e * PCGRL_MAX_TILES;
+  return r;
+}
+
+// Representation.update(action) -> (change, x, y) where (hx, hy) is the heat-map cell
+// (narrow_rep.py:99-114: the cursor AFTER it moved; turtle_rep.py:101-129; wide_rep.py:67-70).
+// The changed tile is written to the uint8 map in HBM (one byte) and to the bitboards of lane y.
+__device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32_t* __restrict__ act, Board& board,
+                                            uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy) {
+  const int W = cfg.width, H = cfg.height;
+  int change = 0, wx = x, wy = y, newt = -1;
+  if (cfg.representation == PCGRL_REP_NARROW) {
+    const int a = act[0];
+    if (a > 0) newt = (a - 1) & 7;
+  } else if (cfg.representation == PCGRL_REP_TURTLE) {
+    const int a = act[0];
+    if (a >= 4) newt = (a - 4) & 7;
+    else if (a >= 0) {
+      const bool warp = (cfg.flags & PCGRL_FLAG_WARP) != 0;
+      const int dx = (a == 0) ? -1 : (a == 1) ? 1 : 0, dy = (a == 2) ? -1 : (a == 3) ? 1 : 0;
+      x += dx;
+      if (x < 0) x = warp ? x + W : 0;
+      if (x >= W) x = warp ? x - W : W - 1;
+      y += dy;
+      if (y < 0) y = warp ? y + H : 0;
+      if (y >= H) y = warp ? y - H : H - 1;
+    }
+  } else {
+    wx = min(max(act[0], 0), W - 1);
+    wy = min(max(act[1], 0), H - 1);
+    newt = act[2] & 7;
+  }
+  if (newt >= 0) {
+    const int oldt = __shfl_sync(FULL_MASK, tile_at(board, wx), wy);
+    change = (oldt != newt) ? 1 : 0;
+    if (change) {
+      if (lane == wy) set_tile(board, wx, newt);
+      if (lane == 0) map[wy * W + wx] = (uint8_t)newt;
+    }
+  }
+  if (cfg.representation == PCGRL_REP_NARROW) {
+    if (cfg.flags & PCGRL_FLAG_RANDOM_TILE) {
+      x = rng.randint(W, lane);
+      y = rng.randint(H, lane);
+    } else {
+      x += 1;
+      if (x >= W) { x = 0; y += 1; if (y >= H) y = 0; }
+    }
+    hx = x; hy = y;
+  } else if (cfg.representation == PCGRL_REP_TURTLE) {
+    hx = x; hy = y;
+  } else {
+    hx = wx; hy = wy;
+  }
+  return change;
+}
+
+// _heatmap[y][x] += 1 (pcgrl_env.py:137) as a fire-and-forget 32-bit reduction on the containing word.
+__device__ __forceinline__ void heat_increment(uint8_t* heat_base, size_t byte_off, int lane) {
+  if (lane == 0) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(heat_base) + (byte_off >> 2);
+    atomicAdd(w, 1u << (8u * (uint32_t)(byte_off & 3)));
+  }
+}
+
+__device__ __forceinline__ void warp_fill_bytes(uint8_t* dst, int nbytes, uint8_t v, int lane) {
+  if ((((uintptr_t)dst) & 3) == 0 && (nbytes & 3) == 0) {
+    const uint32_t vv = 0x01010101u * v;
+    for (int i = lane; i < (nbytes >> 2); i += 32) reinterpret_cast<uint32_t*>(dst)[i] = vv;
+  } else {
+    for (int i = lane; i < nbytes; i += 32) dst[i] = v;
+  }
+}
+
+// PcgrlEnv.reset for one env, up to (and including) the map part of get_stats.  The caller finishes
+// Problem.reset (start_stats) -- after the solver for the solver problems.
+template <int PROB>
+__device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buffers& b, int e, int lane, WarpSmem& sm,
+                                       WarpRng& rng, Board& board, int& x, int& y, int* st, bool& need_solver) {
+  constexpr int NP = ProblemTraits<PROB>::NPLANES;
+  const int W = cfg.width, H = cfg.height, cells = W * H, T = cfg.num_tiles;
+  const EnvRefs r = env_refs(cfg, b, e);
+  const bool generate = (cfg.flags & PCGRL_FLAG_RANDOM_START) || (b.start_valid[e] == 0);
+  __syncwarp();
+  if (generate) {  // representation.py:41-43 -> helper.py:310-312 gen_random_map
+    // helper.py:343-352 get_int_prob, then RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]
+    double cdf[PCGRL_MAX_TILES];
+    double total = 0.0, acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < PCGRL_MAX_TILES; t++) if (t < T) total += r.tile_prob[t];
+#pragma unroll
+    for (int t = 0; t < PCGRL_MAX_TILES; t++) {
+      if (t < T) { acc += r.tile_prob[t] / total; cdf[t] = acc; }
+      else cdf[t] = __longlong_as_double(0x7ff0000000000000LL);
+    }
+#pragma unroll
+    for (int t = 0; t < PCGRL_MAX_TILES; t++) if (t < T) cdf[t] /= acc;
+    const int nchunks = (cells + 31) >> 5;
+    for (int c = 0; c < nchunks; c++) {
+      const int nin = min(32, cells - c * 32);
+      rng.fill(sm.draws, 2 * nin, lane);  // H*W random_sample() doubles in row-major order
+      uint32_t tile = 0;
+      if (lane < nin) {
+        const uint32_t a = sm.draws[2 * lane] >> 5, bb = sm.draws[2 * lane + 1] >> 6;
+        const double u = ((double)a * 67108864.0 + (double)bb) / 9007199254740992.0;
+#pragma unroll
+        for (int t = 0; t < PCGRL_MAX_TILES; t++) tile += (cdf[t] <= u) ? 1u : 0u;  // searchsorted(side='right')
+        r.map[c * 32 + lane] = (uint8_t)tile;
+        r.start_map[c * 32 + lane] = (uint8_t)tile;  // _old_map = _map.copy()
+      }
+      __syncwarp();
+      chunk_to_bits<NP>(tile, c, lane, sm.bits);
+    }
+    board = bits_to_board<NP>(sm.bits, nchunks, W, H, lane);
+    if (lane == 0) b.start_valid[e] = 1;
+  } else {  // representation.py:44-45
+    for (int i = lane; i < cells; i += 32) r.map[i] = r.start_map[i];
+    board = load_board<NP>(r.start_map, W, H, lane, sm.bits);
+  }
+  if (cfg.representation != PCGRL_REP_WIDE) {  // narrow_rep.py:30-31, turtle_rep.py:32-33
+    x = rng.randint(W, lane);
+    y = rng.randint(H, lane);
+  }
+  map_stats<PROB>(board, cfg, lane, st, need_solver);
+  if (PROB == PCGRL_PROB_BINARY && (cfg.flags & PCGRL_FLAG_RANDOM_PROBS)) {  // binary_prob.py:68-72 (problem stream)
+    WarpRng pr;
+    pr.init(r.rng_prob);
+    const double p_empty = pr.next_double(lane);
+    pr.finish(lane);
+    if (lane == 0) { r.tile_prob[0] = p_empty; r.tile_prob[1] = 1 - p_empty; }
+  }
+  warp_fill_bytes(r.heat, cells, 0, lane);  // pcgrl_env.py:72
+  __syncwarp();
+}
+
+}  // namespace pcgrl

@@ -1,0 +1,131 @@
+// pcgrl_problems.cuh -- Problem.get_stats / get_reward / get_episode_over on bitboards, one warp per env.
+// Reference: gym_pcgrl/envs/probs/{binary,zelda,sokoban,ddave,mdungeon}_prob.py (cited per function).
+#pragma once
+#include "pcgrl_device.cuh"
+
+namespace pcgrl {
+
+template <int PROB> struct ProblemTraits;
+template <> struct ProblemTraits<PCGRL_PROB_BINARY>   { static constexpr int NPLANES = 1, NSTATS = 2;  static constexpr bool SOLVER = false; };
+template <> struct ProblemTraits<PCGRL_PROB_ZELDA>    { static constexpr int NPLANES = 3, NSTATS = 7;  static constexpr bool SOLVER = false; };
+template <> struct ProblemTraits<PCGRL_PROB_SOKOBAN>  { static constexpr int NPLANES = 3, NSTATS = 6;  static constexpr bool SOLVER = true; };
+template <> struct ProblemTraits<PCGRL_PROB_DDAVE>    { static constexpr int NPLANES = 3, NSTATS = 11; static constexpr bool SOLVER = true; };
+template <> struct ProblemTraits<PCGRL_PROB_MDUNGEON> { static constexpr int NPLANES = 3, NSTATS = 11; static constexpr bool SOLVER = true; };
+
+// Everything of Problem.get_stats that is a map scan / flood fill / BFS.  For the solver problems the
+// play-through statistics keep their "not playable" defaults and *need_solver tells the caller that the
+// reference would call _run_game on this map.  st[] is warp-uniform.
+template <int PROB>
+__device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cfg, int lane, int* st, bool& need_solver) {
+  const int W = cfg.width, H = cfg.height;
+  const uint32_t rm = row_mask(W, H, lane);
+  need_solver = false;
+#pragma unroll
+  for (int i = 0; i < ProblemTraits<PROB>::NSTATS; i++) st[i] = 0;
+
+  if (PROB == PCGRL_PROB_BINARY) {  // binary_prob.py:81-86
+    regions_and_longest_path(type_mask<0x01u>(b, rm), lane, st[0], st[1]);
+  } else if (PROB == PCGRL_PROB_ZELDA) {  // zelda_prob.py:80-112
+    const uint32_t player = type_mask<0x04u>(b, rm), key = type_mask<0x08u>(b, rm), door = type_mask<0x10u>(b, rm);
+    const uint32_t enemies = type_mask<0xE0u>(b, rm);
+    st[0] = popc_all(player);
+    st[1] = popc_all(key);
+    st[2] = popc_all(door);
+    st[3] = popc_all(enemies);
+    st[4] = count_regions(type_mask<0xEDu>(b, rm), lane);  // empty, player, key, bat, spider, scorpion
+    if (st[0] == 1 && st[4] == 1) {
+      if (st[3] > 0) {  // nearest enemy: first BFS wave (d > 0) that touches an enemy; key and door block
+        const uint32_t pass = type_mask<0xE5u>(b, rm);
+        uint32_t f = player, visited = player;
+        int d = 0, min_dist = W * H;
+        while (true) {
+          const uint32_t nx = dilate(f) & pass & ~visited;
+          if (!__any_sync(FULL_MASK, nx != 0u)) break;
+          visited |= nx;
+          f = nx;
+          d++;
+          if (__any_sync(FULL_MASK, (f & enemies) != 0u)) { min_dist = min(min_dist, d); break; }
+        }
+        st[5] = min_dist;
+      }
+      if (st[1] == 1 && st[2] == 1) {  // player -> key (door blocks), key -> door; either leg may be -1
+        st[6] += bfs_dist_to(player, key, type_mask<0xEDu>(b, rm));
+        st[6] += bfs_dist_to(key, door, type_mask<0xFDu>(b, rm));
+      }
+    }
+  } else if (PROB == PCGRL_PROB_SOKOBAN) {  // sokoban_prob.py:133-145
+    st[0] = popc_all(type_mask<0x04u>(b, rm));
+    st[1] = popc_all(type_mask<0x08u>(b, rm));
+    st[2] = popc_all(type_mask<0x10u>(b, rm));
+    st[3] = count_regions(type_mask<0x1Du>(b, rm), lane);
+    st[4] = W * H * (W + H);
+    st[5] = 0;
+    need_solver = (st[0] == 1 && st[1] == st[2] && st[1] > 0 && st[3] == 1);
+  } else if (PROB == PCGRL_PROB_DDAVE) {  // ddave_prob.py:149-169
+    st[0] = popc_all(type_mask<0x04u>(b, rm));
+    st[1] = floor_dist(type_mask<0x04u>(b, rm), type_mask<0x02u>(b, rm), H, lane);
+    st[2] = popc_all(type_mask<0x08u>(b, rm));
+    st[3] = popc_all(type_mask<0x10u>(b, rm));
+    st[4] = popc_all(type_mask<0x20u>(b, rm));
+    st[5] = popc_all(type_mask<0x40u>(b, rm));
+    st[6] = count_regions(type_mask<0x3Du>(b, rm), lane);  // empty, player, diamond, key, exit
+    st[9] = W * H;
+    need_solver = (st[0] == 1 && st[2] == 1 && st[4] == 1 && st[6] == 1);
+  } else {  // mdungeon_prob.py:151-171
+    st[0] = popc_all(type_mask<0x04u>(b, rm));
+    st[1] = popc_all(type_mask<0x08u>(b, rm));
+    st[2] = popc_all(type_mask<0x10u>(b, rm));
+    st[3] = popc_all(type_mask<0x20u>(b, rm));
+    st[4] = popc_all(type_mask<0xC0u>(b, rm));
+    st[5] = count_regions(type_mask<0xFDu>(b, rm), lane);
+    st[9] = W * H;
+    need_solver = (st[0] == 1 && st[1] == 1 && st[5] == 1);
+  }
+}
+
+// Problem.get_reward: fp64, terms summed left to right exactly as the reference writes them
+// (compiled with -fmad=false so no product is fused into the adds).
+template <int PROB>
+__device__ __forceinline__ double problem_reward(const pcgrl_config& cfg, const int* n, const int* o) {
+  const double* w = cfg.reward_weight;
+  const int32_t* ip = cfg.iparam;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  if (PROB == PCGRL_PROB_BINARY)  // binary_prob.py:98-106
+    return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], INF, INF) * w[1];
+  if (PROB == PCGRL_PROB_ZELDA)  // zelda_prob.py:124-142
+    return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 1, 1) * w[1] +
+           range_reward(n[2], o[2], 1, 1) * w[2] + range_reward(n[3], o[3], 2, ip[0]) * w[3] +
+           range_reward(n[4], o[4], 1, 1) * w[4] + range_reward(n[5], o[5], ip[1], INF) * w[5] +
+           range_reward(n[6], o[6], INF, INF) * w[6];
+  if (PROB == PCGRL_PROB_SOKOBAN)  // sokoban_prob.py:157-175
+    return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 1, ip[0]) * w[1] +
+           range_reward(n[2], o[2], 1, ip[0]) * w[2] + range_reward(n[3], o[3], 1, 1) * w[3] +
+           range_reward(abs(n[1] - n[2]), abs(o[1] - o[2]), -INF, -INF) * w[4] +
+           range_reward(n[4], o[4], -INF, -INF) * w[5] + range_reward(n[5], o[5], INF, INF) * w[6];
+  if (PROB == PCGRL_PROB_DDAVE)  // ddave_prob.py:181-205
+    return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 0, 0) * w[1] +
+           range_reward(n[2], o[2], 1, 1) * w[2] + range_reward(n[5], o[5], ip[1], INF) * w[3] +
+           range_reward(n[3], o[3], -INF, ip[0]) * w[4] + range_reward(n[4], o[4], 1, 1) * w[5] +
+           range_reward(n[6], o[6], 1, 1) * w[6] + range_reward(n[7], o[7], INF, INF) * w[7] +
+           range_reward(n[9], o[9], -INF, -INF) * w[8] + range_reward(n[10], o[10], INF, INF) * w[9];
+  // mdungeon_prob.py:183-205
+  return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 1, 1) * w[1] +
+         range_reward(n[4], o[4], 1, ip[0]) * w[2] + range_reward(n[3], o[3], -INF, ip[2]) * w[3] +
+         range_reward(n[2], o[2], -INF, ip[1]) * w[4] + range_reward(n[5], o[5], 1, 1) * w[5] +
+         range_reward(n[8], o[8], INF, INF) * w[6] + range_reward(n[9], o[9], -INF, -INF) * w[7] +
+         range_reward(n[10], o[10], INF, INF) * w[8];
+}
+
+// Problem.get_episode_over
+template <int PROB>
+__device__ __forceinline__ bool problem_over(const pcgrl_config& cfg, const int* n, const int* start) {
+  const int32_t* ip = cfg.iparam;
+  if (PROB == PCGRL_PROB_BINARY) return n[0] == 1 && n[1] - start[1] >= ip[0];   // binary_prob.py:119-120
+  if (PROB == PCGRL_PROB_ZELDA) return n[5] >= ip[1] && n[6] >= ip[2];            // zelda_prob.py:155-156
+  if (PROB == PCGRL_PROB_SOKOBAN) return n[5] >= ip[1];                           // sokoban_prob.py:188-189
+  if (PROB == PCGRL_PROB_DDAVE) return n[10] >= ip[3] && n[7] > ip[2];            // ddave_prob.py:218-220
+  return n[10] >= ip[3] && n[4] > 0 &&                                            // mdungeon_prob.py:218-221
+         (double)n[8] / (double)(n[4] > 1 ? n[4] : 1) > cfg.dparam[0];
+}
+
+}  // namespace pcgrl

@@ -1,0 +1,607 @@
+// pcgrl_solver.cuh -- the bounded BFS / A* play-through solvers of sokoban, ddave and mdungeon on the GPU.
+//
+// Reference: gym_pcgrl/envs/probs/{sokoban,ddave,mdungeon}/engine.py (State, Node, BFSAgent, AStarAgent) and
+// the _run_game methods of the three *_prob.py files.  The result of a search depends on the exact pop
+// order of CPython's binary heap under ties, on visited-set semantics and on best-node tie-breaks, so the
+// search itself is reproduced operation by operation; what is B200-specific is the placement:
+//
+//   * envs whose map satisfies the solver precondition are compacted into a work queue by the step kernels;
+//   * one CTA per (queued env, pass): the 4 passes of _run_game run SPECULATIVELY IN PARALLEL, a pass is
+//     cancelled as soon as a pass earlier in the reference's order has won; the last CTA to finish merges
+//     the 4 results in the reference's order;
+//   * binary heap (packed 32-bit entries: priority | node index) and the visited hash table live in shared
+//     memory (~112 KB per CTA); the append-only node store (32 B per node) lives in HBM scratch and stays
+//     L2 resident;
+//   * states are fixed-width: 5 key words (exactly the information of State.getKey) + 3 payload words.
+//
+// Limits (checked by pcgrl_config_validate / reported through status[0]): width, height <= 14,
+// width*height <= 128, solver_power in [1, 8000], at most 16 crates/targets in a sokoban level.
+#pragma once
+#include "pcgrl_device.cuh"
+
+namespace pcgrl {
+
+enum { SOLVE_FOR_STEP = 0, SOLVE_FOR_RESET = 1, SOLVE_STATS_ONLY = 2 };
+enum { GAME_SOKOBAN = 0, GAME_DDAVE = 1, GAME_MDUNGEON = 2 };
+
+#define SOLVER_MAX_SLOTS 148
+#define SOLVER_NODE_WORDS 8
+#define SOLVER_PRIO_BIAS 2048
+
+struct SolverQueue {
+  int32_t* count;      // [1] number of queued items
+  int32_t* items;      // [n] env | mode << 28
+  int32_t* pass_done;  // [n] passes finished per item
+  int32_t* best_win;   // [n] earliest pass (in reference order) that has won, 4 = none
+  int32_t* results;    // [n][4][4]  {won, depth, h, counters}
+  int32_t* status;
+  int32_t capacity;
+};
+
+struct SolverLayout {
+  size_t queue_bytes, old_stats_off, heat_off, nodes_off, total;
+  int slots;
+  size_t nodes_per_pass;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static inline size_t solver_queue_bytes(int n) {
+  // count(16 B) + items + pass_done + best_win + results
+  return align_up(16 + sizeof(int32_t) * (size_t)n * (3 + 16), 256);
+}
+
+static inline SolverLayout solver_layout(const pcgrl_config* c, int n) {
+  SolverLayout L;
+  L.queue_bytes = solver_queue_bytes(n);
+  L.old_stats_off = 2 * L.queue_bytes;
+  L.heat_off = L.old_stats_off + align_up(sizeof(int32_t) * PCGRL_MAX_STATS * (size_t)n, 256);
+  L.nodes_off = L.heat_off + align_up(3 * (size_t)n, 256);
+  L.slots = n < SOLVER_MAX_SLOTS ? n : SOLVER_MAX_SLOTS;
+  L.nodes_per_pass = (size_t)4 * (size_t)c->solver_power + 8;
+  L.total = L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t);
+  return L;
+}
+
+static inline size_t solver_scratch_bytes(const pcgrl_config* c, int n) { return solver_layout(c, n).total; }
+
+static inline int solver_validate(const pcgrl_config* c) {
+  if (c->width > 14 || c->height > 14 || c->width * c->height > 128) return 1;
+  if (c->solver_power < 1 || c->solver_power > 8000) return 2;
+  return 0;
+}
+static inline const char* solver_validate_message(int rc) {
+  return rc == 1 ? "solver problems support width, height <= 14 and width*height <= 128"
+                 : "solver_power must be in [1, 8000]";
+}
+
+static inline SolverQueue solver_queue(const pcgrl_config* c, void* scratch, int n, int which, int32_t* status) {
+  SolverQueue q;
+  memset(&q, 0, sizeof(q));
+  q.status = status;
+  q.capacity = n;
+  if (!scratch || c->problem < PCGRL_PROB_SOKOBAN) return q;
+  char* base = (char*)scratch + (size_t)which * solver_queue_bytes(n);
+  q.count = (int32_t*)base;
+  q.items = (int32_t*)(base + 16);
+  q.pass_done = q.items + n;
+  q.best_win = q.pass_done + n;
+  q.results = q.best_win + n;
+  return q;
+}
+static inline int32_t* solver_old_stats(const pcgrl_config* c, void* scratch, int n) {
+  return (int32_t*)((char*)scratch + solver_layout(c, n).old_stats_off);
+}
+static inline uint8_t* solver_heat_cell(const pcgrl_config* c, void* scratch, int n) {
+  return (uint8_t*)scratch + solver_layout(c, n).heat_off;
+}
+
+__global__ void k_queue_clear(SolverQueue q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *q.count = 0;
+  if (i < q.capacity) { q.pass_done[i] = 0; q.best_win[i] = 4; }
+}
+static inline void solver_queue_clear(SolverQueue q, cudaStream_t s) {
+  if (q.count) k_queue_clear<<<(q.capacity + 255) / 256, 256, 0, s>>>(q);
+}
+
+__device__ __forceinline__ void solver_enqueue(const SolverQueue& q, int env, int mode, int lane) {
+  if (lane == 0) {
+    const int slot = atomicAdd(q.count, 1);
+    q.items[slot] = env | (mode << 28);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// level (shared memory) and state (registers)
+// ------------------------------------------------------------------------------------------------
+struct Level {
+  int W, H, bw, bh;       // map size, bordered size
+  uint32_t solid[16];     // bordered rows
+  uint32_t dead[16];      // sokoban deadlock cells (engine.py:203-246)
+  uint32_t spikes[16];    // ddave
+  uint8_t tiles[128];     // map tiles, row-major (object types for mdungeon)
+  uint8_t tx[16], ty[16]; // sokoban targets in row-major order
+  int ntargets, ncrates;
+  int doorx, doory, keyx, keyy;
+  int overflow;
+};
+
+// 5 key words (m[0..3], ks) == everything State.getKey can distinguish inside one level; payload: dh, misc.
+//   sokoban : m = 16 crate bytes (x | y<<4, index order kept, 0xFF filler); ks = px | py<<8
+//   ddave   : m = remaining-diamond bits over map cells; ks = px | py<<8 | health<<16 | key_present<<24;
+//             misc = airTime | collected diamonds<<8 | jumps<<16
+//   mdungeon: m = remaining potion/treasure/enemy bits; ks = px | py<<8 | health<<16;
+//             misc = potions | treasures<<8 | enemies<<16
+struct SState {
+  uint32_t m[4];
+  uint32_t ks;
+  uint32_t dh;    // depth | (h + SOLVER_PRIO_BIAS) << 16
+  uint32_t misc;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ int st_px(const SState& s) { return (int)(s.ks & 0xffu); }
+__device__ __forceinline__ int st_py(const SState& s) { return (int)((s.ks >> 8) & 0xffu); }
+__device__ __forceinline__ int st_health(const SState& s) { return (int)((s.ks >> 16) & 0xffu); }
+__device__ __forceinline__ void st_set_pos(SState& s, int x, int y) { s.ks = (s.ks & 0xffff0000u) | (uint32_t)x | ((uint32_t)y << 8); }
+__device__ __forceinline__ void st_set_health(SState& s, int h) { s.ks = (s.ks & 0xff00ffffu) | ((uint32_t)h << 16); }
+__device__ __forceinline__ int st_depth(const SState& s) { return (int)(s.dh & 0xffffu); }
+__device__ __forceinline__ int st_h(const SState& s) { return (int)(s.dh >> 16) - SOLVER_PRIO_BIAS; }
+
+__device__ __forceinline__ bool mask_test(const SState& s, int idx) {
+  const uint32_t w = (idx < 64) ? ((idx < 32) ? s.m[0] : s.m[1]) : ((idx < 96) ? s.m[2] : s.m[3]);
+  return (w >> (idx & 31)) & 1u;
+}
+__device__ __forceinline__ void mask_clear(SState& s, int idx) {
+  const uint32_t bit = ~(1u << (idx & 31));
+#pragma unroll
+  for (int w = 0; w < 4; w++) if ((idx >> 5) == w) s.m[w] &= bit;
+}
+__device__ __forceinline__ bool lv_solid(const Level& L, int x, int y) { return (L.solid[y] >> x) & 1u; }
+__device__ __forceinline__ bool lv_movable(const Level& L, int x, int y) {  // ddave :204-205, mdungeon :201-202
+  return !(x < 0 || y < 0 || x >= L.bw || y >= L.bh || lv_solid(L, x, y));
+}
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+
+// --- sokoban (sokoban/engine.py) ----------------------------------------------------------------
+__device__ __forceinline__ int sk_crate_at(const SState& s, int x, int y) {  // :262-266 first match in list order
+  const uint32_t vv = 0x01010101u * (uint32_t)(x | (y << 4));
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const uint32_t eq = __vcmpeq4(s.m[w], vv);
+    if (eq) return 4 * w + ((__ffs(eq) - 1) >> 3);
+  }
+  return -1;
+}
+__device__ __forceinline__ uint32_t sk_crate(const SState& s, int i) {
+  const uint32_t w = (i < 8) ? ((i < 4) ? s.m[0] : s.m[1]) : ((i < 12) ? s.m[2] : s.m[3]);
+  return (w >> (8 * (i & 3))) & 0xffu;
+}
+__device__ __forceinline__ void sk_set_crate(SState& s, int i, int x, int y) {
+  const int sh = 8 * (i & 3);
+  const uint32_t v = (uint32_t)(x | (y << 4)) << sh, keep = ~(0xffu << sh);
+#pragma unroll
+  for (int w = 0; w < 4; w++) if ((i >> 2) == w) s.m[w] = (s.m[w] & keep) | v;
+}
+__device__ __forceinline__ bool sk_movable(const Level& L, const SState& s, int x, int y) {  // :268-269
+  if (x < 0 || y < 0 || x > L.bw - 1 || y > L.bh - 1) return false;
+  return !lv_solid(L, x, y) && sk_crate_at(s, x, y) < 0;
+}
+__device__ __forceinline__ bool sk_win(const Level& L, const SState& s) {  // :271-280
+  if (L.ntargets != L.ncrates || L.ntargets == 0) return false;
+  for (int t = 0; t < L.ntargets; t++) if (sk_crate_at(s, L.tx[t], L.ty[t]) < 0) return false;
+  return true;
+}
+__device__ __forceinline__ int sk_heuristic(const Level& L, const SState& s) {  // :282-296
+  uint32_t used = 0;
+  int distance = 0;
+  for (int c = 0; c < L.ncrates; c++) {
+    const uint32_t cr = sk_crate(s, c);
+    const int cx = (int)(cr & 15u), cy = (int)(cr >> 4);
+    int best = L.bw + L.bh, match = -1, first_free = -1;
+    for (int t = 0; t < L.ntargets; t++) {
+      if ((used >> t) & 1u) continue;
+      if (first_free < 0) first_free = t;
+      const int d = iabs(cx - (int)L.tx[t]) + iabs(cy - (int)L.ty[t]);
+      if (best > d) { match = t; best = d; }
+    }
+    if (match < 0) match = first_free;  // bestMatch = 0 default (first remaining target)
+    if (match < 0) break;
+    distance += iabs((int)L.tx[match] - cx) + iabs((int)L.ty[match] - cy);
+    used |= 1u << match;
+  }
+  return distance;
+}
+__device__ __forceinline__ bool sk_update(const Level& L, SState& s, int dx, int dy) {  // :298-327 -> crateMove
+  if (sk_win(L, s)) return false;
+  const int nx = st_px(s) + dx, ny = st_py(s) + dy;
+  if (sk_movable(L, s, nx, ny)) { st_set_pos(s, nx, ny); return false; }
+  const int c = sk_crate_at(s, nx, ny);
+  if (c >= 0) {
+    const int cx = nx + dx, cy = ny + dy;
+    if (sk_movable(L, s, cx, cy)) {
+      st_set_pos(s, nx, ny);
+      sk_set_crate(s, c, cx, cy);
+      return true;
+    }
+  }
+  return false;
+}
+__device__ __forceinline__ bool sk_deadlocked(const Level& L, const SState& s) {  // :248-252
+  for (int c = 0; c < L.ncrates; c++) {
+    const uint32_t cr = sk_crate(s, c);
+    if ((L.dead[cr >> 4] >> (cr & 15u)) & 1u) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ bool sk_target_at(const Level& L, int x, int y) {
+  for (int t = 0; t < L.ntargets; t++) if (L.tx[t] == x && L.ty[t] == y) return true;
+  return false;
+}
+__device__ void sk_init_deadlocks(Level& L) {  // :203-246 (single thread)
+  for (int y = 0; y < 16; y++) L.dead[y] = 0;
+  uint32_t corner[16];
+  for (int y = 0; y < 16; y++) corner[y] = 0;
+  for (int y = 1; y < L.bh - 1; y++)
+    for (int x = 1; x < L.bw - 1; x++) {
+      if (lv_solid(L, x, y)) continue;
+      const bool up = lv_solid(L, x, y - 1), dn = lv_solid(L, x, y + 1), lf = lv_solid(L, x - 1, y), rt = lv_solid(L, x + 1, y);
+      if (((up && lf) || (up && rt) || (dn && lf) || (dn && rt)) && !sk_target_at(L, x, y)) corner[y] |= 1u << x;
+    }
+  for (int y = 0; y < 16; y++) L.dead[y] = corner[y];
+  // for every ordered pair of corners on one row / column: the open segment between them is dead if every cell
+  // is a non-target floor cell hugging a wall on at least one side
+  for (int y2 = 1; y2 < L.bh - 1; y2++)
+    for (int x2 = 1; x2 < L.bw - 1; x2++) {
+      if (!((corner[y2] >> x2) & 1u)) continue;
+      for (int x1 = x2 + 1; x1 < L.bw - 1; x1++) {  // same row (both orders give the same cell set)
+        if (!((corner[y2] >> x1) & 1u)) continue;
+        bool ok = true;
+        for (int x = x2 + 1; x < x1 && ok; x++)
+          if (sk_target_at(L, x, y2) || lv_solid(L, x, y2) || (!lv_solid(L, x, y2 - 1) && !lv_solid(L, x, y2 + 1))) ok = false;
+        if (ok) for (int x = x2 + 1; x < x1; x++) L.dead[y2] |= 1u << x;
+      }
+      for (int y1 = y2 + 1; y1 < L.bh - 1; y1++) {  // same column
+        if (!((corner[y1] >> x2) & 1u)) continue;
+        bool ok = true;
+        for (int y = y2 + 1; y < y1 && ok; y++)
+          if (sk_target_at(L, x2, y) || lv_solid(L, x2, y) || (!lv_solid(L, x2 - 1, y) && !lv_solid(L, x2 + 1, y))) ok = false;
+        if (ok) for (int y = y2 + 1; y < y1; y++) L.dead[y] |= 1u << x2;
+      }
+    }
+}
+
+// --- ddave (ddave/engine.py) --------------------------------------------------------------------
+__device__ __forceinline__ int cell_index(const Level& L, int x, int y) { return (y - 1) * L.W + (x - 1); }
+__device__ __forceinline__ bool dd_win(const Level& L, const SState& s) {  // :319-320 (key count == 1 - key_present)
+  return ((s.ks >> 24) & 1u) == 0u && st_px(s) == L.doorx && st_py(s) == L.doory;
+}
+__device__ __forceinline__ void dd_update(const Level& L, SState& s, int dx, int dy) {  // :244-280 + :225-242
+  if (dd_win(L, s) || st_health(s) <= 0) return;
+  const int px = st_px(s), py = st_py(s);
+  int air = (int)(s.misc & 0xffu), diamonds = (int)((s.misc >> 8) & 0xffu), jumps = (int)(s.misc >> 16);
+  const bool ground = lv_solid(L, px, py + 1), ceiling = lv_solid(L, px, py - 1);
+  int nx = px, ny = py;
+  if (dx != 0) {
+    if (lv_movable(L, nx + dx, ny)) nx += dx;
+  } else if (dy < 0) {
+    if (ground && !ceiling) { air = 3; jumps++; }
+  }
+  if (air > 1) {
+    air--;
+    if (lv_movable(L, nx, ny - 1)) ny--; else air = 1;
+  } else if (air > 0) {
+    air--;
+  } else {
+    if (lv_movable(L, nx, ny + 1)) ny++;
+  }
+  st_set_pos(s, nx, ny);
+  const int idx = cell_index(L, nx, ny);
+  if (idx >= 0 && idx < 128 && nx >= 1 && ny >= 1 && nx <= L.W && ny <= L.H) {
+    if (mask_test(s, idx)) { diamonds++; mask_clear(s, idx); }                   // diamond
+    else if ((L.spikes[ny] >> nx) & 1u) st_set_health(s, 0);                       // spike
+    else if (((s.ks >> 24) & 1u) && nx == L.keyx && ny == L.keyy) s.ks &= ~(1u << 24);  // key
+  }
+  s.misc = (uint32_t)air | ((uint32_t)diamonds << 8) | ((uint32_t)jumps << 16);
+}
+__device__ __forceinline__ int dd_heuristic(const Level& L, const SState& s) {  // :294-299
+  int d = iabs(st_px(s) - L.doorx) + iabs(st_py(s) - L.doory);
+  if ((s.ks >> 24) & 1u) d = iabs(st_px(s) - L.keyx) + iabs(st_py(s) - L.keyy) + (L.bw + L.bh);
+  return d - 5 * (int)((s.misc >> 8) & 0xffu);
+}
+
+// --- mdungeon (mdungeon/engine.py) ---------------------------------------------------------------
+__device__ __forceinline__ bool md_win(const Level& L, const SState& s) { return st_px(s) == L.doorx && st_py(s) == L.doory; }  // :308-309
+__device__ __forceinline__ void md_update(const Level& L, SState& s, int dx, int dy) {  // :254-270 + :222-252
+  if (md_win(L, s) || st_health(s) <= 0) return;
+  const int nx = st_px(s) + dx, ny = st_py(s) + dy;
+  if (!lv_movable(L, nx, ny)) return;
+  st_set_pos(s, nx, ny);
+  const int idx = cell_index(L, nx, ny);
+  if (nx >= 1 && ny >= 1 && nx <= L.W && ny <= L.H && mask_test(s, idx)) {
+    const int t = L.tiles[idx];
+    int health = st_health(s);
+    int potions = (int)(s.misc & 0xffu), treasures = (int)((s.misc >> 8) & 0xffu), enemies = (int)((s.misc >> 16) & 0xffu);
+    if (t == 4) { health = min(health + 2, 5); potions++; }
+    else if (t == 5) { treasures++; }
+    else { enemies++; health = max(health - (t == 6 ? 1 : 2), 0); }
+    mask_clear(s, idx);
+    st_set_health(s, health);
+    s.misc = (uint32_t)potions | ((uint32_t)treasures << 8) | ((uint32_t)enemies << 16);
+  }
+}
+__device__ __forceinline__ int md_heuristic(const Level& L, const SState& s) {  // :285-289
+  return iabs(st_px(s) - L.doorx) + iabs(st_py(s) - L.doory) + 4 * (5 - st_health(s)) - 4 * (int)((s.misc >> 8) & 0xffu);
+}
+
+template <int GAME> __device__ __forceinline__ bool g_win(const Level& L, const SState& s) {
+  return GAME == GAME_SOKOBAN ? sk_win(L, s) : GAME == GAME_DDAVE ? dd_win(L, s) : md_win(L, s);
+}
+template <int GAME> __device__ __forceinline__ int g_heuristic(const Level& L, const SState& s) {
+  return GAME == GAME_SOKOBAN ? sk_heuristic(L, s) : GAME == GAME_DDAVE ? dd_heuristic(L, s) : md_heuristic(L, s);
+}
+
+// *_prob.py _run_game level framing + engine.stringInitialize; run by lane 0 after the tiles are staged
+template <int GAME>
+__device__ void level_init(Level& L, SState& root, int W, int H) {
+  L.W = W; L.H = H; L.bw = W + 2; L.bh = H + 2;
+  L.ntargets = 0; L.ncrates = 0; L.overflow = 0;
+  L.doorx = L.doory = L.keyx = L.keyy = 0;
+  for (int y = 0; y < 16; y++) { L.solid[y] = 0; L.spikes[y] = 0; L.dead[y] = 0; }
+  root.m[0] = root.m[1] = root.m[2] = root.m[3] = (GAME == GAME_SOKOBAN) ? 0xffffffffu : 0u;
+  root.ks = 0; root.dh = 0; root.misc = 0; root.pad = 0;
+  for (int y = 0; y < L.bh; y++)
+    for (int x = 0; x < L.bw; x++) {
+      const bool border = (x == 0 || y == 0 || x == L.bw - 1 || y == L.bh - 1);
+      const int t = border ? 1 : L.tiles[(y - 1) * W + (x - 1)];
+      if (t == 1) { L.solid[y] |= 1u << x; continue; }
+      if (t == 0) continue;
+      const int idx = (y - 1) * W + (x - 1);
+      if (GAME == GAME_SOKOBAN) {
+        if (t == 2) st_set_pos(root, x, y);
+        if (t == 3) { if (L.ncrates < 16) { sk_set_crate(root, L.ncrates, x, y); L.ncrates++; } else L.overflow = 1; }
+        if (t == 4) { if (L.ntargets < 16) { L.tx[L.ntargets] = (uint8_t)x; L.ty[L.ntargets] = (uint8_t)y; L.ntargets++; } else L.overflow = 1; }
+      } else if (GAME == GAME_DDAVE) {
+        if (t == 2) { st_set_pos(root, x, y); st_set_health(root, 1); }
+        if (t == 3) { L.doorx = x; L.doory = y; }
+        if (t == 4) {
+#pragma unroll
+          for (int w = 0; w < 4; w++) if ((idx >> 5) == w) root.m[w] |= 1u << (idx & 31);
+        }
+        if (t == 5) { L.keyx = x; L.keyy = y; root.ks |= 1u << 24; }
+        if (t == 6) L.spikes[y] |= 1u << x;
+      } else {
+        if (t == 2) { st_set_pos(root, x, y); st_set_health(root, 5); }
+        if (t == 3) { L.doorx = x; L.doory = y; }
+        if (t >= 4) {
+#pragma unroll
+          for (int w = 0; w < 4; w++) if ((idx >> 5) == w) root.m[w] |= 1u << (idx & 31);
+        }
+      }
+    }
+  if (GAME == GAME_SOKOBAN) sk_init_deadlocks(L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void node_store(uint32_t* nodes, int i, const SState& s) {
+  uint4* p = reinterpret_cast<uint4*>(nodes + (size_t)i * SOLVER_NODE_WORDS);
+  p[0] = make_uint4(s.m[0], s.m[1], s.m[2], s.m[3]);
+  p[1] = make_uint4(s.ks, s.dh, s.misc, s.pad);
+}
+__device__ __forceinline__ void node_load(const uint32_t* nodes, int i, SState& s) {
+  const uint4* p = reinterpret_cast<const uint4*>(nodes + (size_t)i * SOLVER_NODE_WORDS);
+  const uint4 a = p[0], b = p[1];
+  s.m[0] = a.x; s.m[1] = a.y; s.m[2] = a.z; s.m[3] = a.w;
+  s.ks = b.x; s.dh = b.y; s.misc = b.z; s.pad = b.w;
+}
+__device__ __forceinline__ uint32_t key_hash(const SState& s) {
+  uint32_t h = 2166136261u;
+  h = (h ^ s.m[0]) * 16777619u; h = (h ^ s.m[1]) * 16777619u; h = (h ^ s.m[2]) * 16777619u;
+  h = (h ^ s.m[3]) * 16777619u; h = (h ^ s.ks) * 16777619u;
+  return h ^ (h >> 15);
+}
+
+// CPython heapq on packed entries (priority << 15 | node); comparisons use the priority only, strict <
+// (Lib/heapq.py _siftdown / _siftup; engine.py Node.__lt__ with 2*h + b*depth, b = 2*balance).
+#define HP(e) ((e) >> 15)
+__device__ __forceinline__ void heap_siftdown(uint32_t* heap, int startpos, int pos) {
+  const uint32_t item = heap[pos];
+  while (pos > startpos) {
+    const int parentpos = (pos - 1) >> 1;
+    const uint32_t parent = heap[parentpos];
+    if (HP(item) < HP(parent)) { heap[pos] = parent; pos = parentpos; continue; }
+    break;
+  }
+  heap[pos] = item;
+}
+__device__ __forceinline__ uint32_t heap_pop(uint32_t* heap, int& n) {
+  const uint32_t last = heap[--n];
+  if (n == 0) return last;
+  const uint32_t ret = heap[0];
+  int pos = 0, childpos = 1;
+  while (childpos < n) {
+    const int rightpos = childpos + 1;
+    uint32_t child = heap[childpos];
+    if (rightpos < n) {
+      const uint32_t right = heap[rightpos];
+      if (!(HP(child) < HP(right))) { childpos = rightpos; child = right; }
+    }
+    heap[pos] = child;
+    pos = childpos;
+    childpos = 2 * pos + 1;
+  }
+  heap[pos] = last;
+  heap_siftdown(heap, 0, pos);
+  return ret;
+}
+
+// One pass of _run_game: BFSAgent / AStarAgent.getSolution (b < 0: BFS).  Single lane.
+// Returns: res[0] won, res[1] depth, res[2] h, res[3] misc counters of solState; -1 in res[0] if cancelled.
+template <int GAME>
+__device__ void search_pass(const Level& L, const SState& root0, int b, int power, uint32_t* nodes, uint32_t* heap,
+                            uint32_t* table, int table_mask, const volatile int32_t* best_win, int pass_index, int* res) {
+  const bool check_lose = (GAME != GAME_SOKOBAN);
+  SState root = root0;
+  root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
+  node_store(nodes, 0, root);
+  int nn = 1, nheap = 0, head = 0, iterations = 0;
+  int best = -1, best_h = 0, best_depth = 0;
+  if (b >= 0) { heap[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
+  res[0] = 0;
+  while (iterations < power && (b >= 0 ? nheap > 0 : head < nn)) {
+    if ((iterations & 31) == 0 && *best_win < pass_index) { res[0] = -1; return; }
+    iterations++;
+    const int cur = (b >= 0) ? (int)(heap_pop(heap, nheap) & 0x7fffu) : head++;
+    SState cs;
+    node_load(nodes, cur, cs);
+    if (check_lose && st_health(cs) <= 0) continue;
+    if (g_win<GAME>(L, cs)) {
+      res[0] = 1; res[1] = st_depth(cs); res[2] = st_h(cs); res[3] = (int)cs.misc;
+      return;
+    }
+    // visited set: open addressing, entry = fingerprint << 15 | (node + 1); exact key compare on a fingerprint hit
+    const uint32_t hsh = key_hash(cs);
+    const uint32_t fp = (hsh >> 15) & 0x1ffffu;
+    uint32_t slot = hsh & (uint32_t)table_mask;
+    bool seen = false;
+    while (true) {
+      const uint32_t ent = table[slot];
+      if (ent == 0u) break;
+      if ((ent >> 15) == fp) {
+        SState o;
+        node_load(nodes, (int)(ent & 0x7fffu) - 1, o);
+        if (o.m[0] == cs.m[0] && o.m[1] == cs.m[1] && o.m[2] == cs.m[2] && o.m[3] == cs.m[3] && o.ks == cs.ks) { seen = true; break; }
+      }
+      slot = (slot + 1) & (uint32_t)table_mask;
+    }
+    if (seen) continue;
+    const int ch = st_h(cs), cd = st_depth(cs);
+    if (best < 0 || ch < best_h || (ch == best_h && cd < best_depth)) { best = cur; best_h = ch; best_depth = cd; }
+    table[slot] = (fp << 15) | (uint32_t)(cur + 1);
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) {  // Node.getChildren in `directions` order
+      SState c = cs;
+      if (GAME == GAME_SOKOBAN) {  // engine.py:3 and :14-24
+        const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
+        const bool crate_move = sk_update(L, c, dx, dy);
+        if ((c.ks & 0xffffu) == (cs.ks & 0xffffu)) continue;
+        if (crate_move && sk_deadlocked(L, c)) continue;
+      } else if (GAME == GAME_DDAVE) {  // ddave/engine.py:3  (0,0) (-1,0) (1,0) (0,-1)
+        const int dx = (d == 1) ? -1 : (d == 2) ? 1 : 0, dy = (d == 3) ? -1 : 0;
+        dd_update(L, c, dx, dy);
+      } else {  // mdungeon/engine.py:3
+        const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
+        md_update(L, c, dx, dy);
+      }
+      const int h = g_heuristic<GAME>(L, c);
+      c.dh = (uint32_t)(cd + 1) | ((uint32_t)(h + SOLVER_PRIO_BIAS) << 16);
+      node_store(nodes, nn, c);
+      if (b >= 0) {
+        heap[nheap] = ((uint32_t)(2 * h + b * (cd + 1) + 2 * SOLVER_PRIO_BIAS) << 15) | (uint32_t)nn;
+        nheap++;
+        heap_siftdown(heap, 0, nheap - 1);
+      }
+      nn++;
+    }
+  }
+  SState bs;
+  node_load(nodes, best < 0 ? 0 : best, bs);
+  res[0] = 0; res[1] = st_depth(bs); res[2] = st_h(bs); res[3] = (int)bs.misc;
+}
+
+template <int PROB> struct GameOf;
+template <> struct GameOf<PCGRL_PROB_SOKOBAN> { static constexpr int GAME = GAME_SOKOBAN; };
+template <> struct GameOf<PCGRL_PROB_DDAVE> { static constexpr int GAME = GAME_DDAVE; };
+template <> struct GameOf<PCGRL_PROB_MDUNGEON> { static constexpr int GAME = GAME_MDUNGEON; };
+template <> struct GameOf<PCGRL_PROB_BINARY> { static constexpr int GAME = -1; };
+template <> struct GameOf<PCGRL_PROB_ZELDA> { static constexpr int GAME = -1; };
+
+// grid = 4 * slots CTAs of one warp; CTA c runs pass (c & 3) of queue items (c >> 2), (c >> 2) + slots, ...
+template <int PROB>
+__global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_config cfg, int32_t* stats, int32_t* start_stats,
+                                              const uint8_t* __restrict__ maps, SolverQueue q, uint32_t* node_pool,
+                                              size_t nodes_per_pass, int slots, int table_size) {
+  constexpr int GAME = GameOf<PROB>::GAME;
+  extern __shared__ uint32_t dyn[];
+  __shared__ Level L;
+  const int lane = threadIdx.x, pass = blockIdx.x & 3, slot = blockIdx.x >> 2;
+  const int count = *q.count;
+  uint32_t* table = dyn;
+  uint32_t* heap = dyn + table_size;
+  uint32_t* nodes = node_pool + ((size_t)slot * 4 + pass) * nodes_per_pass * SOLVER_NODE_WORDS;
+  const int W = cfg.width, H = cfg.height, cells = W * H;
+  // pass order: sokoban BFS, A*(1), A*(.5), A*(0) (sokoban_prob.py:110-122); ddave / mdungeon A*(1), A*(.5), A*(0), BFS
+  const int b = (GAME == GAME_SOKOBAN) ? ((pass == 0) ? -1 : (pass == 1) ? 2 : (pass == 2) ? 1 : 0)
+                                       : ((pass == 0) ? 2 : (pass == 1) ? 1 : (pass == 2) ? 0 : -1);
+  for (int item = slot; item < count; item += slots) {
+    const int packed = q.items[item], e = packed & 0x0fffffff, mode = packed >> 28;
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) L.tiles[i] = maps[(size_t)e * cells + i];
+    for (int i = lane; i < table_size; i += 32) table[i] = 0u;
+    __syncwarp();
+    int res[4] = {0, 0, 0, 0};
+    if (lane == 0) {
+      SState root;
+      level_init<GAME>(L, root, W, H);
+      if (L.overflow) {
+        atomicExch(q.status, 1);
+        res[0] = 0; res[1] = 0; res[2] = 0; res[3] = 0;
+      } else {
+        search_pass<GAME>(L, root, b, cfg.solver_power, nodes, heap, table, table_size - 1, q.best_win + item, pass, res);
+        if (res[0] == 1) atomicMin(q.best_win + item, pass);
+      }
+      int32_t* r = q.results + ((size_t)item * 4 + pass) * 4;
+      r[0] = res[0]; r[1] = res[1]; r[2] = res[2]; r[3] = res[3];
+      __threadfence();
+      if (atomicAdd(q.pass_done + item, 1) == 3) {  // last pass to finish merges in the reference's order
+        __threadfence();
+        const volatile int32_t* rr = q.results + (size_t)item * 16;
+        int sel = 3;
+        for (int p = 0; p < 4; p++) if (rr[p * 4] == 1) { sel = p; break; }
+        const int won = (rr[sel * 4] == 1), depth = rr[sel * 4 + 1], h = rr[sel * 4 + 2];
+        const uint32_t misc = (uint32_t)rr[sel * 4 + 3];
+        int32_t* st = stats + (size_t)e * PCGRL_MAX_STATS;
+        int32_t* ss = (mode == SOLVE_FOR_RESET && start_stats) ? start_stats + (size_t)e * PCGRL_MAX_STATS : nullptr;
+        const int dist_win = won ? 0 : h, sol_len = won ? depth : 0;
+        if (GAME == GAME_SOKOBAN) {  // sokoban_prob.py:110-122,143-144
+          st[4] = dist_win; st[5] = sol_len;
+          if (ss) { ss[4] = dist_win; ss[5] = sol_len; }
+        } else if (GAME == GAME_DDAVE) {  // ddave_prob.py:122-135,164-168
+          const int jumps = (int)(misc >> 16), col = (int)((misc >> 8) & 0xffu);
+          st[9] = dist_win; st[10] = sol_len; st[7] = jumps; st[8] = col;
+          if (ss) { ss[9] = dist_win; ss[10] = sol_len; ss[7] = jumps; ss[8] = col; }
+        } else {  // mdungeon_prob.py:125-138,166-170
+          const int pot = (int)(misc & 0xffu), tre = (int)((misc >> 8) & 0xffu), ene = (int)((misc >> 16) & 0xffu);
+          st[9] = dist_win; st[10] = sol_len; st[6] = pot; st[7] = tre; st[8] = ene;
+          if (ss) { ss[9] = dist_win; ss[10] = sol_len; ss[6] = pot; ss[7] = tre; ss[8] = ene; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int PROB>
+static inline void solver_launch(const pcgrl_config* cfg, int32_t* stats, int32_t* start_stats, const uint8_t* maps,
+                                 SolverQueue q, void* scratch, int n, cudaStream_t s) {
+  if constexpr (GameOf<PROB>::GAME >= 0) {
+  if (!q.count) return;
+  const SolverLayout lay = solver_layout(cfg, n);
+  int table_size = 1024;
+  while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
+  const size_t heap_words = (size_t)4 * cfg->solver_power + 8;
+  const size_t smem = (table_size + heap_words) * sizeof(uint32_t);
+  static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
+  if (configured[PROB] < smem) {
+    cudaFuncSetAttribute(k_solve<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured[PROB] = smem;
+  }
+  uint32_t* pool = (uint32_t*)((char*)scratch + lay.nodes_off);
+  k_solve<PROB><<<4 * lay.slots, 32, smem, s>>>(*cfg, stats, start_stats, maps, q, pool, lay.nodes_per_pass, lay.slots, table_size);
+  }
+}
+
+}  // namespace pcgrl

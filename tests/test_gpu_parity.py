@@ -1,0 +1,247 @@
+"""GPU parity tests: the sm_100a path (through the C ABI / ctypes) against
+  (a) the golden vectors recorded from the unmodified reference, and
+  (b) the CPU oracle on identical seeds and action sequences.
+Integer observations / statistics / done flags must be bit-exact; rewards are compared bit-exactly too
+(fp64, same term order) which is stricter than the 1e-6 the north star asks for."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import util
+from gym_pcgrl_b200 import PROBLEMS, BatchedPcgrlEnv, HostStepIO, PcgrlEnv, _abi, _native
+
+pytestmark = pytest.mark.gpu
+
+KATS = util.kat_configs()
+REWARD_TOL = 1e-6  # tolerance stated by BASELINE.json; the asserts below are exact and this is the fallback bound
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_state_equal(env, ref, S, ctx, wide):
+    t = env._tens
+    np.testing.assert_array_equal(t2n(t["map"]), ref["map"], err_msg=ctx + " map")
+    np.testing.assert_array_equal(t2n(t["heatmap"]), ref["heatmap"], err_msg=ctx + " heatmap")
+    if not wide:
+        np.testing.assert_array_equal(t2n(t["pos"]), ref["pos"], err_msg=ctx + " pos")
+    np.testing.assert_array_equal(t2n(t["stats"])[:, :S], ref["stats"][:, :S], err_msg=ctx + " stats")
+    np.testing.assert_array_equal(t2n(t["start_stats"])[:, :S], ref["start_stats"][:, :S], err_msg=ctx + " start_stats")
+    np.testing.assert_array_equal(t2n(t["iteration"]), ref["iteration"], err_msg=ctx + " iteration")
+    np.testing.assert_array_equal(t2n(t["changes"]), ref["changes"], err_msg=ctx + " changes")
+
+
+def test_library_loads_on_gpu_box():
+    assert _native.lib().pcgrl_abi_version() == _abi.ABI_VERSION
+
+
+def test_seed_kernel_matches_numpy_randomstate():
+    env = BatchedPcgrlEnv("binary", "narrow", num_envs=5, device="cuda", seed=0)
+    seeds = [0, 1, 42, 12345, 2 ** 31 - 1]
+    env.seed_simple(seeds)
+    got = t2n(env._tens["rng"]).view(np.uint32)
+    for i, s in enumerate(seeds):
+        want = util.randomstate_words(s)
+        np.testing.assert_array_equal(got[i, 0], want)
+        np.testing.assert_array_equal(got[i, 1], want)
+
+
+@pytest.mark.parametrize("prob_name", ["binary", "zelda", "sokoban", "ddave", "mdungeon"])
+def test_get_stats_matches_reference_golden(prob_name):
+    import torch
+    for maps, stats in util.stats_groups(prob_name):
+        prob = PROBLEMS[prob_name]()
+        prob.adjust_param(width=maps.shape[2], height=maps.shape[1])
+        if prob_name in ("sokoban", "ddave", "mdungeon") and (maps.shape[1] > 14 or maps.shape[2] > 14 or maps.shape[1] * maps.shape[2] > 128):
+            continue
+        got = prob.get_stats(torch.from_numpy(maps).cuda())
+        rows = np.stack([t2n(got[k]) for k in prob.stat_names], axis=1)
+        bad = np.nonzero((rows != stats).any(axis=1))[0]
+        assert bad.size == 0, "%s %s: map %d cuda %s reference %s\n%s" % (
+            prob_name, maps.shape, bad[0], rows[bad[0]], stats[bad[0]], maps[bad[0]])
+
+
+@pytest.mark.parametrize("meta", KATS, ids=[m["name"] for m in KATS])
+def test_trajectory_matches_reference_golden(meta):
+    """Single env through the classic-gym facade, manual reset on done: the reference's own trajectory."""
+    traj, _ = util.load_traj(meta["name"])
+    prob, rep, _v = meta["env_id"].split("-")
+    env = PcgrlEnv(prob, rep, device="cuda")
+    if meta["kwargs"]:
+        env.adjust_param(**meta["kwargs"])
+        env.adjust_param(**meta["kwargs"])
+    assert env._max_changes == meta["max_changes"] and env._max_iterations == meta["max_iterations"]
+    env.set_rng(np.random.RandomState(meta["seed"]), np.random.RandomState(meta["seed"]))
+    S = util.nstats(prob)
+    wide = rep == "wide"
+    obs = env.reset()
+    np.testing.assert_array_equal(obs["map"], traj["reset_map"][0])
+    k = 0
+    total = 0.0
+    for t in range(meta["steps"]):
+        a = traj["actions"][t, :3] if wide else int(traj["actions"][t, 0])
+        obs, r, d, info = env.step(a)
+        ctx = "%s step %d" % (meta["name"], t)
+        np.testing.assert_array_equal(obs["map"], traj["map"][t], err_msg=ctx)
+        np.testing.assert_array_equal(obs["heatmap"].astype(np.int32), traj["heat"][t], err_msg=ctx)
+        if not wide:
+            np.testing.assert_array_equal(obs["pos"].astype(np.int32), traj["pos"][t], err_msg=ctx)
+        stats = t2n(env._batched._tens["stats"])[0, :S]
+        np.testing.assert_array_equal(stats, traj["stats"][t], err_msg=ctx)
+        assert abs(float(r) - traj["reward"][t]) <= REWARD_TOL and float(r) == traj["reward"][t], ctx
+        assert d == bool(traj["done"][t]), ctx
+        assert info["iterations"] == traj["iteration"][t] and info["changes"] == traj["changes"][t], ctx
+        total += float(r)
+        if d:
+            obs = env.reset()
+            k += 1
+            np.testing.assert_array_equal(obs["map"], traj["reset_map"][k], err_msg=ctx)
+            if not wide:
+                np.testing.assert_array_equal(obs["pos"].astype(np.int32), traj["reset_pos"][k], err_msg=ctx)
+            np.testing.assert_array_equal(t2n(env._batched._tens["stats"])[0, :S], traj["reset_stats"][k], err_msg=ctx)
+    assert k == meta["episodes"]
+    assert abs(total - meta["sum_reward"]) < 1e-6
+    env._batched.check_status()
+
+
+BATCH_CASES = [
+    # (env id, kwargs, n envs, steps)
+    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 512, 150),
+    ("binary-narrow-v0", dict(width=11, height=11, change_percentage=0.2), 128, 120),
+    ("binary-turtle-v0", {}, 128, 150),
+    ("binary-wide-v0", {}, 128, 100),
+    ("binary-narrow-v0", dict(width=32, height=32, change_percentage=0.05), 64, 80),
+    ("binary-wide-v0", dict(width=3, height=2), 64, 60),
+    ("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2), 256, 150),
+    ("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2, probs={
+        "empty": 0.93, "solid": 0.02, "player": 0.006, "key": 0.006, "door": 0.006, "bat": 0.01, "scorpion": 0.01, "spider": 0.012}), 256, 150),
+    ("zelda-narrow-v0", {}, 128, 100),
+    ("zelda-wide-v0", {}, 128, 100),
+    ("sokoban-wide-v0", {}, 256, 100),
+    ("sokoban-wide-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 128, 60),
+    ("sokoban-narrow-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 64, 60),
+    ("ddave-wide-v0", dict(probs={"empty": 0.85, "solid": 0.08, "player": 0.01, "exit": 0.01, "diamond": 0.02, "key": 0.01, "spike": 0.02}), 128, 60),
+    ("ddave-turtle-v0", {}, 128, 80),
+    ("mdungeon-wide-v0", dict(probs={"empty": 0.85, "solid": 0.05, "player": 0.01, "exit": 0.01, "potion": 0.02, "treasure": 0.02, "goblin": 0.02, "ogre": 0.02}), 128, 60),
+    ("mdungeon-narrow-v0", {}, 128, 80),
+]
+
+
+def random_actions(env, rng, n):
+    sp = env.action_space
+    if hasattr(sp, "nvec"):
+        return np.stack([rng.randint(int(k), size=n) for k in sp.nvec], axis=1).astype(np.int32)
+    return rng.randint(sp.n, size=n).astype(np.int32)
+
+
+@pytest.mark.parametrize("case", BATCH_CASES, ids=["%s-%d" % (c[0], i) for i, c in enumerate(BATCH_CASES)])
+def test_batched_rollout_matches_oracle(case):
+    """N lock-step envs with auto-reset (VecEnv semantics) against the oracle, every step, every buffer."""
+    import torch
+    env_id, kwargs, n, steps = case
+    env = util.host_env(env_id, kwargs, num_envs=n, auto_reset=True, device="cuda")
+    states = np.stack([util.randomstate_words(100 + i) for i in range(n)])
+    env.set_rng_states(states)
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    ref.set_rng_states(states)
+    prob = env_id.split("-")[0]
+    S, wide = util.nstats(prob), env_id.split("-")[1] == "wide"
+    env.reset()
+    ref.reset()
+    assert_state_equal(env, ref, S, "%s reset" % env_id, wide)
+    arng = np.random.RandomState(5)
+    ndone = 0
+    for t in range(steps):
+        a = random_actions(env, arng, n)
+        obs, reward, done, info = env.step(torch.from_numpy(a).cuda())
+        ref.step(a)
+        ctx = "%s step %d" % (env_id, t)
+        assert_state_equal(env, ref, S, ctx, wide)
+        np.testing.assert_array_equal(t2n(reward), ref["reward"], err_msg=ctx + " reward")
+        np.testing.assert_array_equal(t2n(done).astype(np.uint8), ref["done"], err_msg=ctx + " done")
+        np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, :S], ref["info_stats"][:, :S], err_msg=ctx + " info")
+        ndone += int(ref["done"].sum())
+    np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"], err_msg="rng state")
+    np.testing.assert_array_equal(t2n(env._tens["tile_prob"]), ref["tile_prob"], err_msg="tile_prob")
+    env.check_status()
+    assert ndone > 0, "case never finished an episode; raise steps"
+
+
+def test_rollout_api_equals_stepping():
+    import torch
+    n, T = 256, 64
+    envs = []
+    for _ in range(2):
+        env = util.host_env("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), num_envs=n, device="cuda")
+        env.set_rng_states(np.stack([util.randomstate_words(7 + i) for i in range(n)]))
+        env.reset()
+        envs.append(env)
+    acts = torch.from_numpy(np.random.RandomState(3).randint(3, size=(T, n)).astype(np.int32)).cuda()
+    rew, done = envs[0].rollout(acts)
+    for t in range(T):
+        _, r, d, _ = envs[1].step(acts[t])
+        assert torch.equal(r, rew[t]) and torch.equal(d, done[t])
+    for k in ("map", "heatmap", "pos", "stats", "start_stats", "iteration", "changes", "rng"):
+        assert torch.equal(envs[0]._tens[k], envs[1]._tens[k]), k
+
+
+def test_step_host_equals_step():
+    import torch
+    n = 128
+    envs = []
+    for _ in range(2):
+        env = util.host_env("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2), num_envs=n, device="cuda")
+        env.set_rng_states(np.stack([util.randomstate_words(50 + i) for i in range(n)]))
+        env.reset()
+        envs.append(env)
+    io = HostStepIO(envs[0], with_obs=True, with_info=True)
+    arng = np.random.RandomState(9)
+    for t in range(40):
+        a = arng.randint(12, size=n).astype(np.int32)
+        io.actions[:, 0] = torch.from_numpy(a)
+        envs[0].step_host(io)
+        obs, r, d, info = envs[1].step(torch.from_numpy(a).cuda())
+        assert torch.equal(io.map, obs["map"].cpu()) and torch.equal(io.heatmap, obs["heatmap"].cpu())
+        assert torch.equal(io.pos, obs["pos"].cpu())
+        assert torch.equal(io.reward, r.cpu()) and torch.equal(io.done.bool(), d.cpu())
+        assert torch.equal(io.info_stats, envs[1]._tens["info_stats"].cpu())
+
+
+def test_full_size_invariants_binary_narrow_4096():
+    """BASELINE config 2 at full size: env i of the batch == the same env stepped alone (shard invariance),
+    plus cheap invariants that hold for every env."""
+    import torch
+    n, T = 4096, 48
+    kw = dict(width=16, height=16, change_percentage=0.2)
+    env = util.host_env("binary-narrow-v0", kw, num_envs=n, device="cuda")
+    states = np.stack([util.randomstate_words(10_000 + i) for i in range(n)])
+    env.set_rng_states(states)
+    env.reset()
+    acts = np.random.RandomState(11).randint(3, size=(T, n)).astype(np.int32)
+    rew, done = env.rollout(torch.from_numpy(acts).cuda())
+    # a different batch shape over a slice of the same envs must give identical trajectories
+    sl = slice(1000, 1128)
+    sub = util.host_env("binary-narrow-v0", kw, num_envs=128, device="cuda")
+    sub.set_rng_states(states[sl])
+    sub.reset()
+    rew2, done2 = sub.rollout(torch.from_numpy(np.ascontiguousarray(acts[:, sl])).cuda())
+    assert torch.equal(rew[:, sl], rew2) and torch.equal(done[:, sl], done2)
+    assert torch.equal(env._tens["map"][sl], sub._tens["map"])
+    t = env._tens
+    assert int(t["map"].max()) <= 1
+    assert bool((t["heatmap"].sum(dim=(1, 2)).to(torch.int32) == t["changes"]).all())   # heat == changes of the episode
+    assert bool((t["changes"] < env._max_changes).all()) and bool((t["iteration"] < env._max_iterations).all())
+    assert bool((t["stats"][:, 0] >= 0).all()) and bool((t["stats"][:, 1] <= 255).all())
+    # and the oracle agrees on the whole batch
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    ref.set_rng_states(states)
+    ref.reset()
+    for k in range(T):
+        ref.step(acts[k])
+    np.testing.assert_array_equal(t2n(t["map"]), ref["map"])
+    np.testing.assert_array_equal(t2n(t["stats"])[:, :2], ref["stats"][:, :2])
+    np.testing.assert_array_equal(t2n(rew[-1]), ref["reward"])

@@ -34,7 +34,7 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int* src, int lane
 }
 
 template <int PROB>
-__global__ void __launch_bounds__(32 * WPB) k_rollout(const __grid_constant__ pcgrl_config cfg,
+__global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
                                                       const __grid_constant__ pcgrl_buffers b,
                                                       const int32_t* __restrict__ actions, double* reward_out,
                                                       uint8_t* done_out, int T, int n) {
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(32 * WPB) k_rollout(const __grid_constant__ pc
       bool unused;
       map_stats<PROB>(board, cfg, lane, st, unused);
     }
-    const double reward = problem_reward<PROB>(cfg, st, old);                     // :142
+    const double reward = (change > 0) ? problem_reward<PROB>(cfg, st, old) : 0.0;  // :142 (get_reward(s, s) == 0)
     const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
                       iteration >= cfg.max_iterations;                            // :143
     if (lane == 0) {

@@ -245,16 +245,21 @@ __device__ __forceinline__ uint32_t cell_bit(int row, int col, int lane) { retur
 // BFS from `seed` over `pass` (G/helper.py:222-237 run_dikjstra): returns the eccentricity of the seed inside
 // its component, the visited set and the last non-empty frontier (the cells at maximum distance).
 __device__ __forceinline__ int bfs_ecc(uint32_t seed, uint32_t pass, uint32_t& visited, uint32_t& last) {
-  uint32_t f = seed;
-  visited = seed;
+  uint32_t f = seed, vis = seed;
   int d = 0;
-  while (true) {
-    const uint32_t n = dilate(f) & pass & ~visited;
-    if (!__any_sync(FULL_MASK, n != 0u)) break;
-    visited |= n;
-    f = n;
-    d++;
+  while (true) {  // two waves per termination vote; the tail decides whether the first of the two was the last
+    const uint32_t n1 = dilate(f) & pass & ~vis;
+    const uint32_t v1 = vis | n1;
+    const uint32_t n2 = dilate(n1) & pass & ~v1;
+    if (!__any_sync(FULL_MASK, n2 != 0u)) {
+      if (__any_sync(FULL_MASK, n1 != 0u)) { vis = v1; f = n1; d += 1; }
+      break;
+    }
+    vis = v1 | n2;
+    f = n2;
+    d += 2;
   }
+  visited = vis;
   last = f;
   return d;
 }
@@ -302,12 +307,30 @@ __device__ __forceinline__ int count_regions(uint32_t pass, int lane) {
 // G/helper.py:197-207 + :250-264 fused: regions and calc_longest_path of `pass`.
 // Per component (processed in row-major order of its first cell, like the reference): BFS from the first
 // cell, np.argmax tie-break = row-major-first cell of the last frontier, BFS from there, keep the max.
-// Exact prunings: single-cell components contribute 0; a component whose first sweep has eccentricity d1
-// has diameter <= 2*d1, so its second sweep is skipped when 2*d1 <= best.
+// The result (a max over components) does not depend on the component order, so three exact shortcuts apply:
+// single-cell components contribute 0 and two-cell components contribute 1 (both found for the whole map at
+// once from neighbour-count boards); a component whose first sweep has eccentricity d1 has diameter <= 2*d1,
+// so its second sweep is skipped when 2*d1 <= best.
 __device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane, int& regions_out, int& path_out) {
-  const uint32_t iso = pass & ~neighbours(pass, lane);
-  int regions = popc_all(iso), best = 0;
-  uint32_t remaining = pass & ~iso;
+  // neighbour-presence boards: has a passable neighbour to the left / right / above / below
+  uint32_t up = __shfl_up_sync(FULL_MASK, pass, 1), dn = __shfl_down_sync(FULL_MASK, pass, 1);
+  if (lane == 0) up = 0;
+  if (lane == 31) dn = 0;
+  const uint32_t l = pass << 1, r = pass >> 1;
+  const uint32_t any_nb = l | r | up | dn;
+  const uint32_t iso = pass & ~any_nb;                       // single-cell components: path 0
+  // cells with exactly one passable neighbour; two adjacent such cells form a 2-cell component: path 1
+  const uint32_t one = pass & (l ^ r ^ up ^ dn) & ~((l & r) | (up & dn) | ((l ^ r) & (up ^ dn)));
+  const uint32_t hd = one & (one >> 1);                      // left cell of a horizontal domino
+  uint32_t below = __shfl_down_sync(FULL_MASK, one, 1);
+  if (lane == 31) below = 0;
+  const uint32_t vd = one & below;                           // top cell of a vertical domino
+  uint32_t vd_low = __shfl_up_sync(FULL_MASK, vd, 1);
+  if (lane == 0) vd_low = 0;
+  const uint32_t dominoes = hd | (hd << 1) | vd | vd_low;
+  const int ndom = popc_all(hd) + popc_all(vd);
+  int regions = popc_all(iso) + ndom, best = ndom > 0 ? 1 : 0;
+  uint32_t remaining = pass & ~iso & ~dominoes;
   int row, col;
   while (first_cell(remaining, row, col)) {
     uint32_t visited, last;

@@ -33,9 +33,35 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = dict(prob="binary", rep="narrow", width=16, height=16, change_percentage=0.2, envs_per_gpu=4096)
+ZELDA_SPARSE = {"empty": 0.93, "solid": 0.02, "player": 0.006, "key": 0.006, "door": 0.006, "bat": 0.01,
+                "scorpion": 0.01, "spider": 0.012}
+SOKOBAN_SPARSE = {"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}
+# BASELINE.json configs.  The default / headline workload is config 2.
+WORKLOADS = {
+    "binary-narrow-16x16": dict(prob="binary", rep="narrow", envs_per_gpu=4096,
+                                kwargs=dict(width=16, height=16, change_percentage=0.2)),
+    "zelda-turtle-11x16": dict(prob="zelda", rep="turtle", envs_per_gpu=4096,
+                               kwargs=dict(width=11, height=16, change_percentage=0.2)),
+    "zelda-turtle-11x16-sparse": dict(prob="zelda", rep="turtle", envs_per_gpu=4096,
+                                      kwargs=dict(width=11, height=16, change_percentage=0.2, probs=ZELDA_SPARSE)),
+    "sokoban-wide-5x5": dict(prob="sokoban", rep="wide", envs_per_gpu=2048, kwargs={}),
+    "sokoban-wide-5x5-sparse": dict(prob="sokoban", rep="wide", envs_per_gpu=2048, kwargs=dict(probs=SOKOBAN_SPARSE)),
+}
+for _p in ("binary", "ddave", "mdungeon", "zelda"):          # config 5: default-size sweep, 8192 envs/GPU
+    for _r in ("narrow", "turtle", "wide"):
+        WORKLOADS["%s-%s-default" % (_p, _r)] = dict(prob=_p, rep=_r, envs_per_gpu=8192, kwargs={})
+WORKLOAD = dict(WORKLOADS["binary-narrow-16x16"])
 WORKLOAD_NAME = "binary-narrow 16x16, 4096 envs/GPU, random-action rollout, auto-reset"
+
+
+def select_workload(name):
+    global WORKLOAD, WORKLOAD_NAME
+    WORKLOAD = dict(WORKLOADS[name])
+    WORKLOAD_NAME = "%s, %d envs/GPU, random-action rollout, auto-reset" % (name, WORKLOAD["envs_per_gpu"])
 HBM_FALLBACK_GBS = 6650.0
+
+
+KERNEL_NAMES = {"binary": "k_rollout<binary>", "zelda": "k_rollout<zelda>"}
 
 
 def algorithmic_bytes_per_env_step(w, h):
@@ -54,10 +80,23 @@ def make_env(num_envs, device, env_offset, auto_reset=True):
     from gym_pcgrl_b200 import BatchedPcgrlEnv
     env = BatchedPcgrlEnv(WORKLOAD["prob"], WORKLOAD["rep"], num_envs=num_envs, device=device, seed=0,
                           auto_reset=auto_reset, env_offset=env_offset)
-    kw = dict(width=WORKLOAD["width"], height=WORKLOAD["height"], change_percentage=WORKLOAD["change_percentage"])
-    env.adjust_param(**kw)
-    env.adjust_param(**kw)  # quirk Q3: limits follow the size only on the second call
+    kw = WORKLOAD["kwargs"]
+    if kw:
+        env.adjust_param(**kw)
+        env.adjust_param(**kw)  # quirk Q3: limits follow the size only on the second call
     return env
+
+
+def action_high(env):
+    sp = env.action_space
+    return [int(v) for v in sp.nvec] if hasattr(sp, "nvec") else [int(sp.n)]
+
+
+def host_actions(env, steps, n, seed):
+    rng = np.random.RandomState(seed)
+    hi = action_high(env)
+    a = np.stack([rng.randint(h, size=(steps, n)) for h in hi], axis=-1).astype(np.int32)
+    return a if len(hi) > 1 else a[..., 0]
 
 
 class ClockSampler:
@@ -119,8 +158,7 @@ def cpu_oracle_run(num_envs, seconds, threads, steps=None):
         states[i] = mt_state_words(rs)
     ref.set_rng_states(states)
     ref.reset()
-    arng = np.random.RandomState(1)
-    acts = arng.randint(3, size=(64, num_envs)).astype(np.int32)
+    acts = host_actions(env, 64, num_envs, 1)
     for k in range(2):
         ref.step(acts[k])
     done, t0 = 0, time.perf_counter()
@@ -155,7 +193,7 @@ def run_reference(args, rank, world):
         states[i] = mt_state_words(rs)
     ref.set_rng_states(states)
     ref.reset()
-    acts = np.random.RandomState(1).randint(3, size=(64, n)).astype(np.int32)
+    acts = host_actions(env, 64, n, 1)
     for k in range(args.warmup):
         ref.step(acts[k % 64])
     t1 = time.perf_counter()
@@ -188,7 +226,9 @@ def main():
     ap.add_argument("--no-flush-l2", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--gather", action="store_true", help="all-gather reward/done across ranks after every chunk")
+    ap.add_argument("--workload", default="binary-narrow-16x16", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    select_workload(args.workload)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,13 +249,15 @@ def main():
 
     from gym_pcgrl_b200 import HostStepIO
     n = WORKLOAD["envs_per_gpu"]
-    W, H = WORKLOAD["width"], WORKLOAD["height"]
     K, Wm, chunk = args.steps, max(args.warmup, 3), max(1, min(args.chunk, args.steps))
     env = make_env(n, dev, env_offset=rank * n)
+    W, H = env._prob._width, env._prob._height
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    acts = torch.randint(0, 3, (K + Wm, n), generator=gen, device=dev, dtype=torch.int32)
+    hi = action_high(env)
+    acts = torch.stack([torch.randint(0, h, (K + Wm, n), generator=gen, device=dev, dtype=torch.int32) for h in hi], dim=-1)
+    acts = acts.contiguous() if len(hi) > 1 else acts[..., 0].contiguous()
     reward_buf = torch.empty((chunk, n), dtype=torch.float64, device=dev)
     done_buf = torch.empty((chunk, n), dtype=torch.uint8, device=dev)
     flush = None if args.no_flush_l2 else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -260,7 +302,7 @@ def main():
 
     # ---- e2e: per-step C-ABI call with host buffers (H2D actions, D2H obs + reward + done, sync) every step
     io = HostStepIO(env, with_obs=True, with_info=False)
-    host_acts = torch.randint(0, 3, (K + 8, n), dtype=torch.int32).pin_memory()
+    host_acts = torch.from_numpy(host_actions(env, K + 8, n, 99 + rank)).pin_memory()
     for t in range(8):
         io.struct.actions = host_acts[t].data_ptr()
         env.step_host(io)
@@ -303,7 +345,7 @@ def main():
                     "api": "pcgrl_step_host (pinned host buffers; map+heatmap+pos+reward+done read back every step)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_rollout<binary>",
+                         "traffic": None, "peak_source": peak_src, "kernel": KERNEL_NAMES.get(WORKLOAD["prob"], "k_step_update/k_solve/k_step_finish"),
                          "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W, H),
                          "units_per_launch": n * chunk, "avg_launch_ms": avg_launch_s * 1e3},
             "cpu_baseline": {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -312,7 +354,8 @@ def main():
         }
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                line["roofline"]["traffic"] = json.load(f).get("k_rollout_binary_bytes_per_launch")
+                if args.workload == "binary-narrow-16x16":
+                    line["roofline"]["traffic"] = json.load(f).get("k_rollout_binary_bytes_per_launch")
         except Exception:
             pass
         print(json.dumps(line), flush=True)

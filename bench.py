@@ -297,30 +297,34 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     dev_ms = sum(a.elapsed_time(b) for a, b, _ in events)
-    clocks = sampler.stop() if rank == 0 else None
     env.check_status()
 
-    # ---- e2e: per-step C-ABI call with host buffers (H2D actions, D2H obs + reward + done, sync) every step
-    io = HostStepIO(env, with_obs=True, with_info=False)
+    # ---- e2e: per-step C-ABI call with host buffers: actions H2D from pinned memory, observation + reward + done
+    # back on the host and the stream synchronised EVERY step (the call a gym / VecEnv binding makes)
     host_acts = torch.from_numpy(host_actions(env, K + 8, n, 99 + rank)).pin_memory()
-    for t in range(8):
-        io.struct.actions = host_acts[t].data_ptr()
-        env.step_host(io)
-    barrier()
-    t0 = time.perf_counter()
-    rsum = 0.0
-    for t in range(K):
-        io.struct.actions = host_acts[8 + t].data_ptr()
-        env.step_host(io)
-    rsum = float(io.reward.sum())
-    barrier()
-    e2e_s = time.perf_counter() - t0
+
+    def run_e2e(mode):
+        io = HostStepIO(env, with_obs=True, with_info=False, mode=mode)
+        for t in range(8):
+            io.struct.actions = host_acts[t].data_ptr()
+            env.step_host(io)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(K):
+            io.struct.actions = host_acts[8 + t].data_ptr()
+            env.step_host(io)
+        barrier()
+        return time.perf_counter() - t0, io, float(io.reward.sum())
+
+    e2e_s, io, rsum = run_e2e("delta")
+    e2e_full_s, io_full, _ = run_e2e("full")
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks
-    t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, e2e_full_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t_dev[0]), float(t_dev[1])
+    dev_ms_max, e2e_ms_max, e2e_full_ms_max = float(t_dev[0]), float(t_dev[1]), float(t_dev[2])
 
     if rank == 0:
         total_envs = n * world
@@ -342,7 +346,11 @@ def main():
                        "parallelism": "env-index sharding, no data-path collective" + (" + all_gather(reward)" if gathered_r is not None else "")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": io.h2d_bytes * world,
                     "d2h_bytes_per_step": io.d2h_bytes * world, "ms_per_step": e2e_ms_max / K,
-                    "api": "pcgrl_step_host (pinned host buffers; map+heatmap+pos+reward+done read back every step)"},
+                    "api": "pcgrl_step_host mode 1 (pinned host buffers; per-env delta records + fresh maps of reset envs copied "
+                           "back and applied, so the host arrays hold the complete map+heatmap+pos+reward+done after every step)"},
+            "e2e_full_copy": {"value": total_envs * K / (e2e_full_ms_max * 1e-3), "unit": "env-steps/s",
+                              "h2d_bytes_per_step": io_full.h2d_bytes * world, "d2h_bytes_per_step": io_full.d2h_bytes * world,
+                              "ms_per_step": e2e_full_ms_max / K, "api": "pcgrl_step_host mode 0 (every array copied back in full)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": KERNEL_NAMES.get(WORKLOAD["prob"], "k_step_update/k_solve/k_step_finish"),

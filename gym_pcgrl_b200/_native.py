@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpcgrl_b200.so")
 
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
-           "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host"]
+           "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
+           "pcgrl_host_staging_bytes"]
 
 _lib = None
 
@@ -52,6 +53,8 @@ def lib():
         L.pcgrl_step_host.restype = C.c_int
         L.pcgrl_step_host.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p,
                                       C.POINTER(_abi.PcgrlHostIO), C.c_int, C.c_void_p]
+        L.pcgrl_host_staging_bytes.restype = C.c_size_t
+        L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:
             raise NativeError("libpcgrl_b200.so ABI %d != python ABI %d" % (L.pcgrl_abi_version(), _abi.ABI_VERSION))
         _lib = L

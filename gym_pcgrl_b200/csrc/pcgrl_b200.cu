@@ -37,7 +37,7 @@ template <int PROB>
 __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
                                                       const __grid_constant__ pcgrl_buffers b,
                                                       const int32_t* __restrict__ actions, double* reward_out,
-                                                      uint8_t* done_out, int T, int n) {
+                                                      uint8_t* done_out, int T, int n, Staging sg) {
   constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
   __shared__ WarpSmem smem[WPB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     int old[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];
-    int hx, hy;
-    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy);
+    int hx, hy, cell, tile;
+    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile);
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
       bool unused;
@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
       iteration = 0;
       changes = 0;
-    } else if (change > 0) {
-      heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
+      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
+    } else {
+      if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
+      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map);
     }
   }
   rng.finish(lane);
@@ -174,16 +176,16 @@ __global__ void __launch_bounds__(32 * WPB) k_step_update(const __grid_constant_
   store_row<NS>(old_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);  // old_stats = self._rep_stats (pcgrl_env.py:132)
   WarpRng rng;
   rng.init(r.rng_rep);
-  int hx, hy;
-  const int change = apply_action(cfg, actions + (size_t)e * adim, board, r.map, rng, lane, x, y, hx, hy);
+  int hx, hy, cell, tile;
+  const int change = apply_action(cfg, actions + (size_t)e * adim, board, r.map, rng, lane, x, y, hx, hy, cell, tile);
   rng.finish(lane);
   if (lane == 0) {
     if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
     b.iteration[e] += 1;
     b.changes[e] += change;
-    heat_cell[3 * e] = (uint8_t)change;  // consumed by k_step_finish
-    heat_cell[3 * e + 1] = (uint8_t)hx;
-    heat_cell[3 * e + 2] = (uint8_t)hy;
+    uint8_t* hc = heat_cell + 6 * (size_t)e;  // consumed by k_step_finish
+    hc[0] = (uint8_t)change; hc[1] = (uint8_t)hx; hc[2] = (uint8_t)hy;
+    hc[3] = (uint8_t)(cell & 0xff); hc[4] = (uint8_t)(cell >> 8); hc[5] = (uint8_t)tile;
   }
   if (change > 0) {
     bool need_solver;
@@ -199,7 +201,7 @@ template <int PROB>
 __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant__ pcgrl_config cfg,
                                                           const __grid_constant__ pcgrl_buffers b, SolverQueue q,
                                                           const int32_t* __restrict__ old_stats,
-                                                          const uint8_t* __restrict__ heat_cell, int n) {
+                                                          const uint8_t* __restrict__ heat_cell, int n, Staging sg) {
   constexpr int NS = ProblemTraits<PROB>::NSTATS;
   __shared__ WarpSmem smem[WPB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -215,7 +217,10 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
   const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes || iteration >= cfg.max_iterations;
   if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
   store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
-  const int change = heat_cell[3 * e], hx = heat_cell[3 * e + 1], hy = heat_cell[3 * e + 2];
+  const uint8_t* hc = heat_cell + 6 * (size_t)e;
+  const int change = hc[0], hx = hc[1], hy = hc[2], cell = hc[3] | (hc[4] << 8), tile = hc[5];
+  int px = 0, py = 0;
+  if (cfg.representation != PCGRL_REP_WIDE) { px = b.pos[2 * e]; py = b.pos[2 * e + 1]; }
   if (done && (cfg.flags & PCGRL_FLAG_AUTO_RESET)) {
     const EnvRefs r = env_refs(cfg, b, e);
     WarpRng rng;
@@ -233,8 +238,10 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
     store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
     store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
     if (need_solver) solver_enqueue(q, e, SOLVE_FOR_RESET, lane);
-  } else if (change > 0) {
-    heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);
+    write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
+  } else {
+    if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);
+    write_record(sg, cfg, e, lane, reward, done, px, py, change > 0, false, cell, tile, nullptr);
   }
   (void)H;
 }
@@ -339,14 +346,15 @@ extern "C" int pcgrl_reset(const pcgrl_config* cfg, const pcgrl_buffers* b, cons
 
 template <int PROB>
 static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
-                         uint8_t* done_out, int T, int n, cudaStream_t s) {
-  k_rollout<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n);
+                         uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
+  k_rollout<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg);
   return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
 }
 
 // one PcgrlEnv.step of a solver problem = update -> solver -> finish(+reset) -> solver
 template <int PROB>
-static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, cudaStream_t s) {
+static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, cudaStream_t s,
+                       Staging sg) {
   SolverQueue q1 = solver_queue(cfg, b->scratch, n, 0, b->status), q2 = solver_queue(cfg, b->scratch, n, 1, b->status);
   int32_t* old_stats = solver_old_stats(cfg, b->scratch, n);
   uint8_t* heat_cell = solver_heat_cell(cfg, b->scratch, n);
@@ -354,17 +362,17 @@ static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const in
   solver_queue_clear(q2, s);
   k_step_update<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, q1, old_stats, heat_cell, n);
   solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q1, b->scratch, n, s);
-  k_step_finish<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, q2, old_stats, heat_cell, n);
+  k_step_finish<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, q2, old_stats, heat_cell, n, sg);
   if (cfg->flags & PCGRL_FLAG_AUTO_RESET) solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q2, b->scratch, n, s);
   return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
 }
 
 template <int PROB>
 static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
-                          uint8_t* done_out, int T, int n, cudaStream_t s) {
+                          uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
   for (int t = 0; t < T; t++) {
-    int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s);
+    int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0, n});
     if (rc) return rc;
     if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n, b->reward, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
     if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n, b->done, (size_t)n, cudaMemcpyDeviceToDevice, s);
@@ -372,24 +380,29 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
   return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
 }
 
-extern "C" int pcgrl_rollout(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
-                             uint8_t* done_out, int T, int n, void* stream) {
+static int rollout_dispatch(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                            uint8_t* done_out, int T, int n, void* stream, Staging sg) {
   int rc = check_common(cfg, b, n);
   if (rc) return rc;
   if (!actions) return fail(-1, "actions is NULL");
   if (T <= 0) return fail(-1, "T must be > 0");
   cudaStream_t s = (cudaStream_t)stream;
   switch (cfg->problem) {
-    case PCGRL_PROB_BINARY: return rollout_fused<PCGRL_PROB_BINARY>(cfg, b, actions, reward_out, done_out, T, n, s);
-    case PCGRL_PROB_ZELDA: return rollout_fused<PCGRL_PROB_ZELDA>(cfg, b, actions, reward_out, done_out, T, n, s);
-    case PCGRL_PROB_SOKOBAN: return rollout_solver<PCGRL_PROB_SOKOBAN>(cfg, b, actions, reward_out, done_out, T, n, s);
-    case PCGRL_PROB_DDAVE: return rollout_solver<PCGRL_PROB_DDAVE>(cfg, b, actions, reward_out, done_out, T, n, s);
-    default: return rollout_solver<PCGRL_PROB_MDUNGEON>(cfg, b, actions, reward_out, done_out, T, n, s);
+    case PCGRL_PROB_BINARY: return rollout_fused<PCGRL_PROB_BINARY>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
+    case PCGRL_PROB_ZELDA: return rollout_fused<PCGRL_PROB_ZELDA>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
+    case PCGRL_PROB_SOKOBAN: return rollout_solver<PCGRL_PROB_SOKOBAN>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
+    case PCGRL_PROB_DDAVE: return rollout_solver<PCGRL_PROB_DDAVE>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
+    default: return rollout_solver<PCGRL_PROB_MDUNGEON>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
   }
 }
 
+extern "C" int pcgrl_rollout(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                             uint8_t* done_out, int T, int n, void* stream) {
+  return rollout_dispatch(cfg, b, actions, reward_out, done_out, T, n, stream, Staging{nullptr, 0u, 0, n});
+}
+
 extern "C" int pcgrl_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, void* stream) {
-  return pcgrl_rollout(cfg, b, actions, nullptr, nullptr, 1, n, stream);
+  return rollout_dispatch(cfg, b, actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0, n});
 }
 
 template <int PROB>
@@ -427,22 +440,78 @@ extern "C" int pcgrl_seed(const pcgrl_buffers* b, const uint32_t* seeds, int n, 
   return cuda_rc(cudaGetLastError(), "pcgrl_seed launch");
 }
 
-extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions,
-                               const pcgrl_host_io* io, int n, void* stream) {
+static int staging_slots(int n) {
+  int r = n / 64;
+  return r < 16 ? 16 : (r > 255 ? 255 : r);
+}
+
+extern "C" size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n) {
+  if (!cfg || n <= 0) return 0;
+  return PCGRL_STAGING_HEADER + sizeof(StepRecord) * (size_t)n + (size_t)staging_slots(n) * cfg->width * cfg->height;
+}
+
+extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, pcgrl_host_io* io,
+                               int n, void* stream) {
   if (!io || !io->actions || !io->reward || !io->done || !d_actions) return fail(-1, "NULL host io pointer");
   int rc = check_common(cfg, b, n);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t cells = (size_t)cfg->width * cfg->height;
   const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const bool wide = cfg->representation == PCGRL_REP_WIDE;
+  const bool delta = io->mode == 1;
+  if (delta && (!io->d_staging || !io->h_staging || io->staging_bytes < pcgrl_host_staging_bytes(cfg, n)))
+    return fail(-1, "mode 1 needs d_staging / h_staging of pcgrl_host_staging_bytes() bytes");
   cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
-  rc = pcgrl_step(cfg, b, d_actions, n, stream);
+
+  if (delta && io->synced) {
+    const int nslots = staging_slots(n);
+    Staging sg{(uint8_t*)io->d_staging, (uint32_t)io->reset_base, nslots, n};
+    rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, sg);
+    if (rc) return rc;
+    cudaMemcpyAsync(io->h_staging, io->d_staging, pcgrl_host_staging_bytes(cfg, n), cudaMemcpyDeviceToHost, s);
+    if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
+    rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
+    if (rc) return rc;
+    // apply the records to the caller's host arrays
+    const uint8_t* hs = (const uint8_t*)io->h_staging;
+    const uint32_t total = *(const uint32_t*)hs;
+    const StepRecord* rec = (const StepRecord*)(hs + PCGRL_STAGING_HEADER);
+    const uint8_t* slots = hs + PCGRL_STAGING_HEADER + sizeof(StepRecord) * (size_t)n;
+    bool overflow = false;
+    for (int e = 0; e < n; e++) {
+      const StepRecord r = rec[e];
+      io->reward[e] = r.reward;
+      io->done[e] = r.done;
+      if (io->pos && !wide) { io->pos[2 * e] = r.posx; io->pos[2 * e + 1] = r.posy; }
+      if (r.flags & PCGRL_REC_RESET) {
+        if (r.slot == 0xFF) overflow = true;
+        else if (io->map) memcpy(io->map + (size_t)e * cells, slots + (size_t)r.slot * cells, cells);
+        if (io->heatmap) memset(io->heatmap + (size_t)e * cells, 0, cells);
+      } else if (r.flags & PCGRL_REC_CHANGED) {
+        if (io->map) io->map[(size_t)e * cells + r.cell] = r.tile;
+        if (io->heatmap) io->heatmap[(size_t)e * cells + (wide ? (size_t)r.cell : (size_t)r.posy * cfg->width + r.posx)] += 1;
+      }
+    }
+    io->reset_base = (int64_t)total;
+    if (overflow && io->map) {  // more resets than staging slots in one step: fetch the whole map batch
+      cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
+      rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host (map refetch)");
+    }
+    return rc;
+  }
+
+  // full copies (mode 0, or the first / re-arming call of mode 1)
+  if (delta) cudaMemsetAsync(io->d_staging, 0, PCGRL_STAGING_HEADER, s);
+  rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0, n});
   if (rc) return rc;
   if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
   if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, cells * n, cudaMemcpyDeviceToHost, s);
-  if (io->pos && cfg->representation != PCGRL_REP_WIDE) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
+  if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->reward, b->reward, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->done, b->done, (size_t)n, cudaMemcpyDeviceToHost, s);
   if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
-  return cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
+  rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
+  if (delta && rc == 0) { io->synced = 1; io->reset_base = 0; }
+  return rc;
 }

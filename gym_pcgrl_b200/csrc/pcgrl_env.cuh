@@ -30,7 +30,8 @@ __device__ __forceinline__ EnvRefs env_refs(const pcgrl_config& cfg, const pcgrl
 // (narrow_rep.py:99-114: the cursor AFTER it moved; turtle_rep.py:101-129; wide_rep.py:67-70).
 // The changed tile is written to the uint8 map in HBM (one byte) and to the bitboards of lane y.
 __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32_t* __restrict__ act, Board& board,
-                                            uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy) {
+                                            uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy,
+                                            int& cell, int& tile) {
   const int W = cfg.width, H = cfg.height;
   int change = 0, wx = x, wy = y, newt = -1;
   if (cfg.representation == PCGRL_REP_NARROW) {
@@ -62,6 +63,8 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
       if (lane == 0) map[wy * W + wx] = (uint8_t)newt;
     }
   }
+  cell = wy * W + wx;
+  tile = newt < 0 ? 0 : newt;
   if (cfg.representation == PCGRL_REP_NARROW) {
     if (cfg.flags & PCGRL_FLAG_RANDOM_TILE) {
       x = rng.randint(W, lane);
@@ -155,6 +158,58 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
   }
   warp_fill_bytes(r.heat, cells, 0, lane);  // pcgrl_env.py:72
   __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// delta transport for pcgrl_step_host (mode 1): one 16-byte record per env + fresh maps of auto-reset envs
+// staging buffer = [uint32 running reset counter, pad to 16 B][StepRecord x n][nslots x H*W bytes]
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) StepRecord {
+  double reward;
+  uint8_t done, posx, posy, flags;  // flags: 1 = one map cell changed, 2 = env was reset (whole observation replaced)
+  uint16_t cell;                    // y*W + x of the changed cell
+  uint8_t tile, slot;               // new tile; staging slot of the fresh map (0xFF: none / overflow)
+};
+#define PCGRL_REC_CHANGED 1
+#define PCGRL_REC_RESET 2
+#define PCGRL_STAGING_HEADER 16
+
+struct Staging {
+  uint8_t* base;        // nullptr: transport disabled
+  uint32_t reset_base;  // value of the running counter at the start of this step
+  int nslots;
+  int n;
+};
+
+__device__ __forceinline__ void write_record(const Staging& sg, const pcgrl_config& cfg, int e, int lane, double reward,
+                                             bool done, int x, int y, bool changed, bool was_reset, int cell, int tile,
+                                             const uint8_t* new_map) {
+  if (!sg.base) return;
+  const int cells = cfg.width * cfg.height;
+  int slot = 0xFF;
+  if (was_reset) {
+    uint32_t s = 0;
+    if (lane == 0) s = atomicAdd(reinterpret_cast<uint32_t*>(sg.base), 1u) - sg.reset_base;
+    s = __shfl_sync(FULL_MASK, s, 0);
+    if (s < (uint32_t)sg.nslots) {
+      slot = (int)s;
+      uint8_t* dst = sg.base + PCGRL_STAGING_HEADER + (size_t)sg.n * sizeof(StepRecord) + (size_t)slot * cells;
+      __syncwarp();
+      for (int i = lane; i < cells; i += 32) dst[i] = new_map[i];
+    }
+  }
+  if (lane == 0) {
+    StepRecord r;
+    r.reward = reward;
+    r.done = done ? 1 : 0;
+    r.posx = (uint8_t)x;
+    r.posy = (uint8_t)y;
+    r.flags = (uint8_t)((changed && !was_reset ? PCGRL_REC_CHANGED : 0) | (was_reset ? PCGRL_REC_RESET : 0));
+    r.cell = (uint16_t)cell;
+    r.tile = (uint8_t)tile;
+    r.slot = (uint8_t)slot;
+    reinterpret_cast<StepRecord*>(sg.base + PCGRL_STAGING_HEADER)[e] = r;
+  }
 }
 
 }  // namespace pcgrl

@@ -56,7 +56,7 @@ static inline SolverLayout solver_layout(const pcgrl_config* c, int n) {
   L.queue_bytes = solver_queue_bytes(n);
   L.old_stats_off = 2 * L.queue_bytes;
   L.heat_off = L.old_stats_off + align_up(sizeof(int32_t) * PCGRL_MAX_STATS * (size_t)n, 256);
-  L.nodes_off = L.heat_off + align_up(3 * (size_t)n, 256);
+  L.nodes_off = L.heat_off + align_up(6 * (size_t)n, 256);
   L.slots = n < SOLVER_MAX_SLOTS ? n : SOLVER_MAX_SLOTS;
   L.nodes_per_pass = (size_t)4 * (size_t)c->solver_power + 8;
   L.total = L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t);

@@ -247,10 +247,15 @@ class BatchedPcgrlEnv:
 
 
 class HostStepIO:
-    """Pinned host buffers for ``BatchedPcgrlEnv.step_host`` (pcgrl_host_io in the header)."""
+    """Pinned host buffers for ``BatchedPcgrlEnv.step_host`` (pcgrl_host_io in the header).
 
-    def __init__(self, env, with_obs=True, with_info=False):
+    mode="delta" (default): the step kernels emit one 16-byte record per env plus the fresh maps of auto-reset
+    envs; one small D2H copy per step, the library patches these persistent host arrays so they always hold the
+    complete current observation.  mode="full": every array is copied back in full every step."""
+
+    def __init__(self, env, with_obs=True, with_info=False, mode="delta"):
         import torch
+        env._ensure_buffers()
         n, h, w = env.num_envs, env._prob._height, env._prob._width
         pin = dict(pin_memory=True)
         self.actions = torch.zeros((n, env._adim), dtype=torch.int32, **pin)
@@ -264,10 +269,25 @@ class HostStepIO:
         for name in ("actions", "map", "heatmap", "pos", "reward", "done", "info_stats"):
             t = getattr(self, name)
             setattr(s, name, None if t is None else t.data_ptr())
+        self.mode = mode
+        self.staging_bytes = 0
+        if mode == "delta":
+            nbytes = int(_native.lib().pcgrl_host_staging_bytes(C.byref(env.native_config), n))
+            self.d_staging = torch.zeros(nbytes, dtype=torch.uint8, device=env._dev)
+            self.h_staging = torch.zeros(nbytes, dtype=torch.uint8, **pin)
+            s.d_staging, s.h_staging, s.staging_bytes = self.d_staging.data_ptr(), self.h_staging.data_ptr(), nbytes
+            s.mode, s.synced, s.reset_base = 1, 0, 0
+            self.staging_bytes = nbytes
         self.struct = s
         self.h2d_bytes = self.actions.numel() * 4
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in
-                             (self.map, self.heatmap, self.pos, self.reward, self.done, self.info_stats) if t is not None)
+        self.full_bytes = sum(t.numel() * t.element_size() for t in
+                              (self.map, self.heatmap, self.pos, self.reward, self.done, self.info_stats) if t is not None)
+        info_bytes = 0 if self.info_stats is None else self.info_stats.numel() * 4
+        self.d2h_bytes = (self.staging_bytes + info_bytes) if mode == "delta" else self.full_bytes
+
+    def invalidate(self):
+        """Call after env.reset() / env.step() / env.rollout(): the next step_host re-syncs with a full copy."""
+        self.struct.synced = 0
 
 
 class PcgrlEnv:

@@ -142,10 +142,20 @@ int pcgrl_get_stats(const pcgrl_config* cfg, const uint8_t* maps, int32_t* stats
 /* Seeds both MT19937 streams of env i with numpy's RandomState(seeds[i]) (init_genrand). */
 int pcgrl_seed(const pcgrl_buffers* bufs, const uint32_t* seeds, int n, void* stream);
 
-/* End-to-end step with HOST buffers (the call a reference-side binding makes): copies h_actions
- * to the device, runs pcgrl_step, copies map / heatmap / pos / reward / done (and info_stats if
- * non-NULL) back to the host pointers, synchronises.  d_actions is a device staging buffer of
- * n*adim int32.  Host pointers should be pinned for full copy bandwidth. */
+/*
+ * End-to-end step with HOST buffers (the call a reference-side VecEnv binding makes): host actions in, host
+ * observation / reward / done out, stream synchronised on return.  Host pointers should be pinned.
+ *
+ * mode 0 (full):  H2D actions, pcgrl_step, D2H of map / heatmap / pos / reward / done (and info_stats) in full.
+ * mode 1 (delta): the step kernels additionally emit one 16-byte record per env (reward, done, cursor, the one
+ *                 map cell that changed) plus the fresh maps of the envs that were auto-reset into a small
+ *                 device staging buffer; ONE D2H copy of that buffer returns and the library applies the
+ *                 records to the caller's host arrays, which therefore always hold the complete current
+ *                 observation.  The host arrays must persist between calls; `synced` = 0 (set it after
+ *                 pcgrl_reset or any device-side step that bypassed this call) makes the next call fall back to
+ *                 a full copy and re-arm.  d_staging / h_staging: device and pinned-host scratch of
+ *                 pcgrl_host_staging_bytes(cfg, n) bytes each.
+ */
 typedef struct pcgrl_host_io {
   const int32_t* actions; /* in  [n][adim]            */
   uint8_t* map;           /* out [n][H][W] or NULL    */
@@ -154,9 +164,16 @@ typedef struct pcgrl_host_io {
   double* reward;         /* out [n]                  */
   uint8_t* done;          /* out [n]                  */
   int32_t* info_stats;    /* out [n][PCGRL_MAX_STATS] or NULL */
+  void* d_staging;        /* mode 1: device scratch   */
+  void* h_staging;        /* mode 1: pinned host scratch */
+  size_t staging_bytes;
+  int32_t mode;           /* 0 full copies, 1 delta records */
+  int32_t synced;         /* in/out, mode 1: host arrays are in sync with the device state */
+  int64_t reset_base;     /* in/out, mode 1: running count of staged resets (library-maintained) */
 } pcgrl_host_io;
+size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n);
 int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions,
-                    const pcgrl_host_io* io, int n, void* stream);
+                    pcgrl_host_io* io, int n, void* stream);
 
 #ifdef __cplusplus
 }

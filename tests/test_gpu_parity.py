@@ -190,26 +190,51 @@ def test_rollout_api_equals_stepping():
         assert torch.equal(envs[0]._tens[k], envs[1]._tens[k]), k
 
 
-def test_step_host_equals_step():
+HOST_CASES = [
+    ("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2), 128, 60),
+    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 512, 200),
+    ("binary-wide-v0", dict(width=5, height=4, change_percentage=0.3), 96, 80),     # many resets per step: staging overflow path
+    ("sokoban-wide-v0", {}, 128, 60),                                                   # solver pipeline + overflow
+    ("mdungeon-narrow-v0", {}, 64, 60),
+]
+
+
+@pytest.mark.parametrize("mode", ["full", "delta"])
+@pytest.mark.parametrize("case", HOST_CASES, ids=[c[0] for c in HOST_CASES])
+def test_step_host_equals_step(case, mode):
+    """pcgrl_step_host (host buffers in / out, full-copy and delta-record transport) == pcgrl_step on the device."""
     import torch
-    n = 128
+    env_id, kwargs, n, steps = case
     envs = []
     for _ in range(2):
-        env = util.host_env("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2), num_envs=n, device="cuda")
+        env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
         env.set_rng_states(np.stack([util.randomstate_words(50 + i) for i in range(n)]))
         env.reset()
         envs.append(env)
-    io = HostStepIO(envs[0], with_obs=True, with_info=True)
+    wide = env_id.split("-")[1] == "wide"
+    io = HostStepIO(envs[0], with_obs=True, with_info=True, mode=mode)
     arng = np.random.RandomState(9)
-    for t in range(40):
-        a = arng.randint(12, size=n).astype(np.int32)
-        io.actions[:, 0] = torch.from_numpy(a)
+    nreset = 0
+    for t in range(steps):
+        a = random_actions(envs[0], arng, n)
+        io.actions[:] = torch.from_numpy(a).reshape(io.actions.shape)
         envs[0].step_host(io)
         obs, r, d, info = envs[1].step(torch.from_numpy(a).cuda())
-        assert torch.equal(io.map, obs["map"].cpu()) and torch.equal(io.heatmap, obs["heatmap"].cpu())
-        assert torch.equal(io.pos, obs["pos"].cpu())
-        assert torch.equal(io.reward, r.cpu()) and torch.equal(io.done.bool(), d.cpu())
-        assert torch.equal(io.info_stats, envs[1]._tens["info_stats"].cpu())
+        ctx = "%s %s step %d" % (env_id, mode, t)
+        assert torch.equal(io.map, obs["map"].cpu()), ctx
+        assert torch.equal(io.heatmap, obs["heatmap"].cpu()), ctx
+        if not wide:
+            assert torch.equal(io.pos, obs["pos"].cpu()), ctx
+        assert torch.equal(io.reward, r.cpu()) and torch.equal(io.done.bool(), d.cpu()), ctx
+        assert torch.equal(io.info_stats, envs[1]._tens["info_stats"].cpu()), ctx
+        nreset += int(d.sum())
+        if t == steps // 2:          # a device-side step that bypasses the host transport, then re-sync
+            a2 = random_actions(envs[0], arng, n)
+            envs[0].step(torch.from_numpy(a2).cuda())
+            envs[1].step(torch.from_numpy(a2).cuda())
+            io.invalidate()
+    assert nreset > 0
+    envs[0].check_status()
 
 
 def test_full_size_invariants_binary_narrow_4096():

@@ -309,9 +309,10 @@ def main():
             io.struct.actions = host_acts[t].data_ptr()
             env.step_host(io)
         barrier()
+        base, stride = host_acts.data_ptr(), host_acts.stride(0) * 4
         t0 = time.perf_counter()
         for t in range(K):
-            io.struct.actions = host_acts[8 + t].data_ptr()
+            io.struct.actions = base + (8 + t) * stride
             env.step_host(io)
         barrier()
         return time.perf_counter() - t0, io, float(io.reward.sum())

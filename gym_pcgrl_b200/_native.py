@@ -51,8 +51,7 @@ def lib():
         L.pcgrl_seed.restype = C.c_int
         L.pcgrl_seed.argtypes = [C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
         L.pcgrl_step_host.restype = C.c_int
-        L.pcgrl_step_host.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p,
-                                      C.POINTER(_abi.PcgrlHostIO), C.c_int, C.c_void_p]
+        L.pcgrl_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.pcgrl_host_staging_bytes.restype = C.c_size_t
         L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:

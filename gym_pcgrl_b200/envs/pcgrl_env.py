@@ -134,6 +134,7 @@ class BatchedPcgrlEnv:
         import torch
         if self._tens is None:
             raise RuntimeError("call reset() before step()")
+        self.native_config  # re-freeze the parameters if adjust_param was called since the last step
         a = torch.as_tensor(actions)
         if a.device != self._dev or a.dtype != torch.int32 or not a.is_contiguous():
             a = a.to(device=self._dev, dtype=torch.int32).contiguous()
@@ -149,6 +150,7 @@ class BatchedPcgrlEnv:
         """T steps in one native call: actions int32 CUDA [T,N] / [T,N,3].  Returns (reward [T,N],
         done [T,N]); the final observation is available through ``observation()``."""
         import torch
+        self.native_config
         a = torch.as_tensor(actions).to(device=self._dev, dtype=torch.int32).contiguous()
         T = a.shape[0]
         if reward_out is None:
@@ -162,12 +164,19 @@ class BatchedPcgrlEnv:
         return reward_out, done_out.view(torch.bool)
 
     def step_host(self, io):
-        """End-to-end step on HOST buffers through pcgrl_step_host (see HostStepIO)."""
+        """End-to-end step on HOST buffers through pcgrl_step_host (see HostStepIO).  Hot loop: everything
+        that does not change between calls is cached, the device guard is only taken when needed."""
         import torch
-        with torch.cuda.device(self._dev):
-            _native.check(_native.lib().pcgrl_step_host(C.byref(self._cfg), C.byref(self._cbufs),
-                                                        self._d_actions.data_ptr(), C.byref(io.struct), self.num_envs,
-                                                        _native.stream_ptr(self._dev)), "pcgrl_step_host")
+        dev = self._dev
+        if torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return self.step_host(io)
+        if self._cfg is None:
+            self.native_config
+        rc = self._fn_step_host(self._cfg_ref, self._bufs_ref, self._d_actions_ptr, io.ref, self.num_envs,
+                                torch.cuda.current_stream(dev).cuda_stream)
+        if rc:
+            _native.check(rc, "pcgrl_step_host")
 
     def observation(self):
         return self._observation()
@@ -200,6 +209,7 @@ class BatchedPcgrlEnv:
     def native_config(self):
         if self._cfg is None:
             self._cfg = build_config(self._prob, self._rep, self._max_changes, self._max_iterations, self.auto_reset)
+            self._cfg_ref = C.byref(self._cfg)
         return self._cfg
 
     # ------------------------------------------------------------------ internals
@@ -224,6 +234,9 @@ class BatchedPcgrlEnv:
             self._tens, self._cbufs = _native.alloc_buffers(cfg, self.num_envs, self._dev)
             self._d_actions = torch.zeros(self.num_envs * self._adim, dtype=torch.int32, device=self._dev)
         self._bufs = self._tens
+        self._fn_step_host = _native.lib().pcgrl_step_host
+        self._bufs_ref = C.byref(self._cbufs)
+        self._d_actions_ptr = self._d_actions.data_ptr()
         self._rep.bind(self)
         if self._pending_states is not None:
             self._tens["rng"].copy_(torch.from_numpy(self._pending_states.view(np.int32)))
@@ -279,6 +292,7 @@ class HostStepIO:
             s.mode, s.synced, s.reset_base = 1, 0, 0
             self.staging_bytes = nbytes
         self.struct = s
+        self.ref = C.byref(s)
         self.h2d_bytes = self.actions.numel() * 4
         self.full_bytes = sum(t.numel() * t.element_size() for t in
                               (self.map, self.heatmap, self.pos, self.reward, self.done, self.info_stats) if t is not None)

@@ -125,6 +125,9 @@ struct Level {
   int ntargets, ncrates;
   int doorx, doory, keyx, keyy;
   int overflow;
+  // sokoban levels with bw*bh <= 64: one bit per bordered cell (bit y*bw + x)
+  int small;
+  unsigned long long solid64, dead64, target64;
 };
 
 // 5 key words (m[0..3], ks) == everything State.getKey can distinguish inside one level; payload: dh, misc.
@@ -380,7 +383,20 @@ __device__ void level_init(Level& L, SState& root, int W, int H) {
         }
       }
     }
-  if (GAME == GAME_SOKOBAN) sk_init_deadlocks(L);
+  L.small = 0; L.solid64 = 0ull; L.dead64 = 0ull; L.target64 = 0ull;
+  if (GAME == GAME_SOKOBAN) {
+    sk_init_deadlocks(L);
+    if (L.bw * L.bh <= 64) {
+      L.small = 1;
+      for (int y = 0; y < L.bh; y++)
+        for (int x = 0; x < L.bw; x++) {
+          const unsigned long long bit = 1ull << (y * L.bw + x);
+          if ((L.solid[y] >> x) & 1u) L.solid64 |= bit;
+          if ((L.dead[y] >> x) & 1u) L.dead64 |= bit;
+        }
+      for (int t = 0; t < L.ntargets; t++) L.target64 |= 1ull << ((int)L.ty[t] * L.bw + (int)L.tx[t]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,78 +454,186 @@ __device__ __forceinline__ uint32_t heap_pop(uint32_t* heap, int& n) {
   return ret;
 }
 
-// One pass of _run_game: BFSAgent / AStarAgent.getSolution (b < 0: BFS).  Single lane.
-// Returns: res[0] won, res[1] depth, res[2] h, res[3] misc counters of solState; -1 in res[0] if cancelled.
+// crate occupancy of a sokoban state as a 64-bit mask over bordered cells (small levels only)
+__device__ __forceinline__ unsigned long long sk_occupancy(const Level& L, const SState& s) {
+  unsigned long long occ = 0ull;
+  for (int c = 0; c < L.ncrates; c++) {
+    const uint32_t cr = sk_crate(s, c);
+    occ |= 1ull << ((int)(cr >> 4) * L.bw + (int)(cr & 15u));
+  }
+  return occ;
+}
+
+#define SOLVER_CACHE_NODES 128 /* shared-memory ring of the most recently created nodes */
+enum { ACT_EXPAND = 0, ACT_SKIP = 1, ACT_STOP = 2 };
+
+__device__ __forceinline__ void node_fetch(const uint32_t* nodes, const uint32_t* cache, int i, int nn, SState& s) {
+  if (i >= nn - SOLVER_CACHE_NODES) {
+    const uint4* p = reinterpret_cast<const uint4*>(cache + (size_t)(i & (SOLVER_CACHE_NODES - 1)) * SOLVER_NODE_WORDS);
+    const uint4 a = p[0], b = p[1];
+    s.m[0] = a.x; s.m[1] = a.y; s.m[2] = a.z; s.m[3] = a.w;
+    s.ks = b.x; s.dh = b.y; s.misc = b.z; s.pad = b.w;
+  } else {
+    node_load(nodes, i, s);
+  }
+}
+__device__ __forceinline__ void node_put(uint32_t* nodes, uint32_t* cache, int i, const SState& s) {
+  node_store(nodes, i, s);
+  uint4* p = reinterpret_cast<uint4*>(cache + (size_t)(i & (SOLVER_CACHE_NODES - 1)) * SOLVER_NODE_WORDS);
+  p[0] = make_uint4(s.m[0], s.m[1], s.m[2], s.m[3]);
+  p[1] = make_uint4(s.ks, s.dh, s.misc, s.pad);
+}
+
+// One pass of _run_game: BFSAgent / AStarAgent.getSolution (b < 0: BFS), executed by one warp:
+//   lane 0      pops (CPython heap order / FIFO), checks lose / win / visited, tracks the best node, pushes;
+//   lanes 0..3  generate the four children of the expanded node in parallel (Node.getChildren order = lane).
+// Returns (lane 0): res[0] won, res[1] depth, res[2] h, res[3] misc counters of solState; res[0] = -1 if cancelled.
 template <int GAME>
-__device__ void search_pass(const Level& L, const SState& root0, int b, int power, uint32_t* nodes, uint32_t* heap,
-                            uint32_t* table, int table_mask, const volatile int32_t* best_win, int pass_index, int* res) {
+__device__ void search_pass(const Level& L, const SState& root0, int b, int power, uint32_t* nodes, uint32_t* cache,
+                            uint32_t* heap, uint32_t* table, int table_mask, const volatile int32_t* best_win,
+                            int pass_index, int* res, int lane) {
   const bool check_lose = (GAME != GAME_SOKOBAN);
-  SState root = root0;
-  root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
-  node_store(nodes, 0, root);
+  const bool sk_small = (GAME == GAME_SOKOBAN) && L.small;
   int nn = 1, nheap = 0, head = 0, iterations = 0;
   int best = -1, best_h = 0, best_depth = 0;
-  if (b >= 0) { heap[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
-  res[0] = 0;
-  while (iterations < power && (b >= 0 ? nheap > 0 : head < nn)) {
-    if ((iterations & 31) == 0 && *best_win < pass_index) { res[0] = -1; return; }
-    iterations++;
-    const int cur = (b >= 0) ? (int)(heap_pop(heap, nheap) & 0x7fffu) : head++;
+  if (lane == 0) {
+    SState root = root0;
+    root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
+    node_put(nodes, cache, 0, root);
+    if (b >= 0) { heap[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
+    res[0] = 0;
+  }
+  __syncwarp();
+  while (true) {
+    int action = ACT_STOP, cur = 0;
     SState cs;
-    node_load(nodes, cur, cs);
-    if (check_lose && st_health(cs) <= 0) continue;
-    if (g_win<GAME>(L, cs)) {
-      res[0] = 1; res[1] = st_depth(cs); res[2] = st_h(cs); res[3] = (int)cs.misc;
-      return;
-    }
-    // visited set: open addressing, entry = fingerprint << 15 | (node + 1); exact key compare on a fingerprint hit
-    const uint32_t hsh = key_hash(cs);
-    const uint32_t fp = (hsh >> 15) & 0x1ffffu;
-    uint32_t slot = hsh & (uint32_t)table_mask;
-    bool seen = false;
-    while (true) {
-      const uint32_t ent = table[slot];
-      if (ent == 0u) break;
-      if ((ent >> 15) == fp) {
-        SState o;
-        node_load(nodes, (int)(ent & 0x7fffu) - 1, o);
-        if (o.m[0] == cs.m[0] && o.m[1] == cs.m[1] && o.m[2] == cs.m[2] && o.m[3] == cs.m[3] && o.ks == cs.ks) { seen = true; break; }
+    cs.m[0] = cs.m[1] = cs.m[2] = cs.m[3] = cs.ks = cs.dh = cs.misc = cs.pad = 0u;
+    if (lane == 0) {
+      if (!(iterations < power && (b >= 0 ? nheap > 0 : head < nn))) {
+        action = ACT_STOP;
+      } else if ((iterations & 31) == 0 && *best_win < pass_index) {
+        res[0] = -1;
+        action = ACT_STOP;
+      } else {
+        iterations++;
+        cur = (b >= 0) ? (int)(heap_pop(heap, nheap) & 0x7fffu) : head++;
+        node_fetch(nodes, cache, cur, nn, cs);
+        bool win;
+        if (sk_small) win = (sk_occupancy(L, cs) & L.target64) == L.target64 && L.ntargets == L.ncrates && L.ntargets > 0;
+        else win = g_win<GAME>(L, cs);
+        if (check_lose && st_health(cs) <= 0) {
+          action = ACT_SKIP;
+        } else if (win) {
+          res[0] = 1; res[1] = st_depth(cs); res[2] = st_h(cs); res[3] = (int)cs.misc;
+          action = ACT_STOP;
+        } else {
+          // visited set: open addressing, entry = fingerprint << 15 | (node + 1); exact key compare on a fingerprint hit
+          const uint32_t hsh = key_hash(cs);
+          const uint32_t fp = (hsh >> 15) & 0x1ffffu;
+          uint32_t slot = hsh & (uint32_t)table_mask;
+          bool seen = false;
+          while (true) {
+            const uint32_t ent = table[slot];
+            if (ent == 0u) break;
+            if ((ent >> 15) == fp) {
+              SState o;
+              node_fetch(nodes, cache, (int)(ent & 0x7fffu) - 1, nn, o);
+              if (o.m[0] == cs.m[0] && o.m[1] == cs.m[1] && o.m[2] == cs.m[2] && o.m[3] == cs.m[3] && o.ks == cs.ks) { seen = true; break; }
+            }
+            slot = (slot + 1) & (uint32_t)table_mask;
+          }
+          if (seen) {
+            action = ACT_SKIP;
+          } else {
+            const int ch = st_h(cs), cd = st_depth(cs);
+            if (best < 0 || ch < best_h || (ch == best_h && cd < best_depth)) { best = cur; best_h = ch; best_depth = cd; }
+            table[slot] = (fp << 15) | (uint32_t)(cur + 1);
+            action = ACT_EXPAND;
+          }
+        }
       }
-      slot = (slot + 1) & (uint32_t)table_mask;
     }
-    if (seen) continue;
-    const int ch = st_h(cs), cd = st_depth(cs);
-    if (best < 0 || ch < best_h || (ch == best_h && cd < best_depth)) { best = cur; best_h = ch; best_depth = cd; }
-    table[slot] = (fp << 15) | (uint32_t)(cur + 1);
-#pragma unroll 1
-    for (int d = 0; d < 4; d++) {  // Node.getChildren in `directions` order
-      SState c = cs;
+    action = __shfl_sync(FULL_MASK, action, 0);
+    if (action == ACT_STOP) break;
+    if (action == ACT_SKIP) continue;
+    // broadcast the expanded node; lanes 0..3 build one child each (Node.getChildren, `directions` order)
+    cs.m[0] = __shfl_sync(FULL_MASK, cs.m[0], 0); cs.m[1] = __shfl_sync(FULL_MASK, cs.m[1], 0);
+    cs.m[2] = __shfl_sync(FULL_MASK, cs.m[2], 0); cs.m[3] = __shfl_sync(FULL_MASK, cs.m[3], 0);
+    cs.ks = __shfl_sync(FULL_MASK, cs.ks, 0); cs.dh = __shfl_sync(FULL_MASK, cs.dh, 0);
+    cs.misc = __shfl_sync(FULL_MASK, cs.misc, 0);
+    const int nn_base = __shfl_sync(FULL_MASK, nn, 0);
+    const int cd = st_depth(cs);
+    bool valid = false;
+    SState c = cs;
+    int h = 0;
+    if (lane < 4) {
+      const int d = lane;
       if (GAME == GAME_SOKOBAN) {  // engine.py:3 and :14-24
         const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
-        const bool crate_move = sk_update(L, c, dx, dy);
-        if ((c.ks & 0xffffu) == (cs.ks & 0xffffu)) continue;
-        if (crate_move && sk_deadlocked(L, c)) continue;
+        if (sk_small) {
+          // bit-mask form of State.update (:298-327): the expanded node is never a winning state
+          const unsigned long long occ = sk_occupancy(L, cs);
+          const int nx = st_px(cs) + dx, ny = st_py(cs) + dy;
+          const unsigned long long nbit = 1ull << (ny * L.bw + nx);  // inside: the border ring is solid
+          h = st_h(cs);
+          if (!((L.solid64 | occ) & nbit)) {
+            st_set_pos(c, nx, ny);
+            valid = true;
+          } else if (occ & nbit) {
+            const int cx = nx + dx, cy = ny + dy;
+            if (cx >= 0 && cy >= 0 && cx < L.bw && cy < L.bh) {
+              const unsigned long long cbit = 1ull << (cy * L.bw + cx);
+              if (!((L.solid64 | occ) & cbit)) {
+                st_set_pos(c, nx, ny);
+                sk_set_crate(c, sk_crate_at(cs, nx, ny), cx, cy);
+                valid = (((occ ^ nbit ^ cbit) & L.dead64) == 0ull);  // a crate moved: prune deadlocks (any crate)
+                h = sk_heuristic(L, c);
+              }
+            }
+          }
+        } else {
+          const bool crate_move = sk_update(L, c, dx, dy);
+          valid = (c.ks & 0xffffu) != (cs.ks & 0xffffu) && !(crate_move && sk_deadlocked(L, c));
+          h = sk_heuristic(L, c);
+        }
       } else if (GAME == GAME_DDAVE) {  // ddave/engine.py:3  (0,0) (-1,0) (1,0) (0,-1)
         const int dx = (d == 1) ? -1 : (d == 2) ? 1 : 0, dy = (d == 3) ? -1 : 0;
         dd_update(L, c, dx, dy);
+        valid = true;
+        h = dd_heuristic(L, c);
       } else {  // mdungeon/engine.py:3
         const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
         md_update(L, c, dx, dy);
+        valid = true;
+        h = md_heuristic(L, c);
       }
-      const int h = g_heuristic<GAME>(L, c);
       c.dh = (uint32_t)(cd + 1) | ((uint32_t)(h + SOLVER_PRIO_BIAS) << 16);
-      node_store(nodes, nn, c);
-      if (b >= 0) {
-        heap[nheap] = ((uint32_t)(2 * h + b * (cd + 1) + 2 * SOLVER_PRIO_BIAS) << 15) | (uint32_t)nn;
-        nheap++;
-        heap_siftdown(heap, 0, nheap - 1);
-      }
-      nn++;
     }
+    const uint32_t vmask = __ballot_sync(FULL_MASK, valid) & 0xFu;
+    if (valid) node_put(nodes, cache, nn_base + __popc(vmask & ((1u << lane) - 1u)), c);
+    const int prio = 2 * h + b * (cd + 1) + 2 * SOLVER_PRIO_BIAS;
+    int idx = nn_base;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      const int pd = __shfl_sync(FULL_MASK, prio, d);
+      if ((vmask >> d) & 1u) {
+        if (lane == 0 && b >= 0) {
+          heap[nheap] = ((uint32_t)pd << 15) | (uint32_t)idx;
+          nheap++;
+          heap_siftdown(heap, 0, nheap - 1);
+        }
+        idx++;
+      }
+    }
+    nn = idx;
+    __syncwarp();
   }
-  SState bs;
-  node_load(nodes, best < 0 ? 0 : best, bs);
-  res[0] = 0; res[1] = st_depth(bs); res[2] = st_h(bs); res[3] = (int)bs.misc;
+  if (lane == 0 && res[0] == 0) {
+    SState bs;
+    node_fetch(nodes, cache, best < 0 ? 0 : best, nn, bs);
+    res[1] = st_depth(bs); res[2] = st_h(bs); res[3] = (int)bs.misc;
+  }
+  __syncwarp();
 }
 
 template <int PROB> struct GameOf;
@@ -530,7 +654,9 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
   const int lane = threadIdx.x, pass = blockIdx.x & 3, slot = blockIdx.x >> 2;
   const int count = *q.count;
   uint32_t* table = dyn;
-  uint32_t* heap = dyn + table_size;
+  uint32_t* cache = dyn + table_size;
+  uint32_t* heap = cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;
+  __shared__ SState root_s;
   uint32_t* nodes = node_pool + ((size_t)slot * 4 + pass) * nodes_per_pass * SOLVER_NODE_WORDS;
   const int W = cfg.width, H = cfg.height, cells = W * H;
   // pass order: sokoban BFS, A*(1), A*(.5), A*(0) (sokoban_prob.py:110-122); ddave / mdungeon A*(1), A*(.5), A*(0), BFS
@@ -542,17 +668,23 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
     for (int i = lane; i < cells; i += 32) L.tiles[i] = maps[(size_t)e * cells + i];
     for (int i = lane; i < table_size; i += 32) table[i] = 0u;
     __syncwarp();
-    int res[4] = {0, 0, 0, 0};
+    __shared__ int res_s[4];
+    int* res = res_s;
     if (lane == 0) {
       SState root;
       level_init<GAME>(L, root, W, H);
-      if (L.overflow) {
-        atomicExch(q.status, 1);
-        res[0] = 0; res[1] = 0; res[2] = 0; res[3] = 0;
-      } else {
-        search_pass<GAME>(L, root, b, cfg.solver_power, nodes, heap, table, table_size - 1, q.best_win + item, pass, res);
-        if (res[0] == 1) atomicMin(q.best_win + item, pass);
-      }
+      root_s = root;
+      res[0] = 0; res[1] = 0; res[2] = 0; res[3] = 0;
+      if (L.overflow) atomicExch(q.status, 1);
+    }
+    __syncwarp();
+    if (!L.overflow) {
+      const SState root = root_s;
+      search_pass<GAME>(L, root, b, cfg.solver_power, nodes, cache, heap, table, table_size - 1, q.best_win + item, pass, res, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (res[0] == 1) atomicMin(q.best_win + item, pass);
       int32_t* r = q.results + ((size_t)item * 4 + pass) * 4;
       r[0] = res[0]; r[1] = res[1]; r[2] = res[2]; r[3] = res[3];
       __threadfence();
@@ -593,7 +725,7 @@ static inline void solver_launch(const pcgrl_config* cfg, int32_t* stats, int32_
   int table_size = 1024;
   while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
   const size_t heap_words = (size_t)4 * cfg->solver_power + 8;
-  const size_t smem = (table_size + heap_words) * sizeof(uint32_t);
+  const size_t smem = (table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words) * sizeof(uint32_t);
   static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
   if (configured[PROB] < smem) {
     cudaFuncSetAttribute(k_solve<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

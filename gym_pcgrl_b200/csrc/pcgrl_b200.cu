@@ -49,15 +49,16 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
   const EnvRefs r = env_refs(cfg, b, e);
 
-  Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
+  // all prologue loads are independent: issue them before the ballots of load_board serialise the warp
+  WarpRng rng;
+  rng.init(r.rng_rep, (cfg.representation == PCGRL_REP_NARROW) ? lane : -1);
   int x = 0, y = 0;
   if (cfg.representation != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
   int iteration = b.iteration[e], changes = b.changes[e];
   int st[NS], start[NS];
   load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
   load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
-  WarpRng rng;
-  rng.init(r.rng_rep);
+  Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
 
   for (int t = 0; t < T; t++) {
     const int32_t* act = actions + ((size_t)t * n + e) * adim;

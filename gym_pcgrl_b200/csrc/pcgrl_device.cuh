@@ -22,7 +22,8 @@ namespace pcgrl {
 // ------------------------------------------------------------------------------------------------
 struct WarpSmem {
   uint32_t bits[3 * PCGRL_SBITS_STRIDE];  // ballot words of the three tile bit-planes (row-major bit stream)
-  uint32_t draws[64];                     // tempered MT19937 outputs for one 32-cell chunk of gen_random_map
+  uint32_t draws[512];                    // tempered MT19937 outputs for one 256-cell segment of gen_random_map
+  uint32_t mt[624];                       // MT19937 key staged here for the duration of a reset (twist + ~2*H*W draws)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -67,12 +68,17 @@ struct WarpRng {
   uint32_t cache;  // tempered st[base + lane]
   bool dirty;
 
-  __device__ __forceinline__ void init(uint32_t* s) {
+  __device__ __forceinline__ void init(uint32_t* s, int lane = -1) {
     st = s;
     pos = (int)s[624];
     base = -1000;
     cache = 0;
     dirty = false;
+    if (lane >= 0 && pos < 624) {  // prefetch: the dependent second round trip starts now, not at the first draw
+      base = pos;
+      const int i = pos + lane;
+      cache = mt_temper((i < 624) ? s[i] : 0u);
+    }
   }
   __device__ __forceinline__ uint32_t next(int lane) {
     if (pos >= 624) {
@@ -93,7 +99,7 @@ struct WarpRng {
   // RandomState.random_sample(): two draws -> 53-bit double
   __device__ __forceinline__ double next_double(int lane) {
     const uint32_t a = next(lane) >> 5, b = next(lane) >> 6;
-    return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);  // exact: power-of-two scaling
   }
   // RandomState.randint(n): masked rejection sampling, one 32-bit draw per attempt, none if n == 1
   __device__ __forceinline__ int randint(int n, int lane) {
@@ -105,7 +111,7 @@ struct WarpRng {
     do { v = next(lane) & mask; } while (v > rng);
     return (int)v;
   }
-  // `count` (<= 64) consecutive tempered draws into shared memory
+  // `count` (<= 512) consecutive tempered draws into shared memory
   __device__ __forceinline__ void fill(uint32_t* buf, int count, int lane) {
     int filled = 0;
     while (filled < count) {
@@ -124,6 +130,26 @@ struct WarpRng {
   }
   __device__ __forceinline__ void finish(int lane) {
     if (dirty && lane == 0) st[624] = (uint32_t)pos;
+  }
+  // Stage the 624 key words in shared memory (one coalesced round trip instead of one per twist batch / refill);
+  // `pos` stays in the register.  unstage() writes the key back and returns to the HBM copy.
+  __device__ __forceinline__ uint32_t* stage(uint32_t* smem_key, int lane) {
+    uint32_t* g = st;
+    uint32_t v[20];
+#pragma unroll
+    for (int k = 0; k < 20; k++) v[k] = (k * 32 + lane < 624) ? g[k * 32 + lane] : 0u;  // 20 loads in flight
+#pragma unroll
+    for (int k = 0; k < 20; k++) if (k * 32 + lane < 624) smem_key[k * 32 + lane] = v[k];
+    __syncwarp();
+    st = smem_key;
+    base = -1000;
+    return g;
+  }
+  __device__ __forceinline__ void unstage(uint32_t* g, int lane) {
+    __syncwarp();
+    for (int i = lane; i < 624; i += 32) g[i] = st[i];
+    st = g;
+    base = -1000;
     __syncwarp();
   }
 };
@@ -204,10 +230,16 @@ __device__ __forceinline__ Board bits_to_board(uint32_t* sbits, int nchunks, int
 template <int NPLANES>
 __device__ __forceinline__ Board load_board(const uint8_t* __restrict__ g, int W, int H, int lane, uint32_t* sbits) {
   const int cells = W * H, nchunks = (cells + 31) >> 5;
-  for (int c = 0; c < nchunks; c++) {
-    const int i = c * 32 + lane;
-    const uint32_t t = (i < cells) ? (uint32_t)g[i] : 0u;
-    chunk_to_bits<NPLANES>(t, c, lane, sbits);
+  for (int c0 = 0; c0 < nchunks; c0 += 8) {  // 8 independent loads in flight per round trip (16x16 = one trip)
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = (c0 + k) * 32 + lane;
+      t[k] = (i < cells) ? (uint32_t)g[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (c0 + k < nchunks) chunk_to_bits<NPLANES>(t[k], c0 + k, lane, sbits);
   }
   return bits_to_board<NPLANES>(sbits, nchunks, W, H, lane);
 }

@@ -109,7 +109,12 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
   const EnvRefs r = env_refs(cfg, b, e);
   const bool generate = (cfg.flags & PCGRL_FLAG_RANDOM_START) || (b.start_valid[e] == 0);
   __syncwarp();
+  uint32_t* rng_home = nullptr;
+  WarpRng pr;  // problem stream (binary_prob.py:68-72): start its two dependent loads now, consume at the end
+  const bool redraw_probs = (PROB == PCGRL_PROB_BINARY) && (cfg.flags & PCGRL_FLAG_RANDOM_PROBS);
+  if (redraw_probs) pr.init(r.rng_prob, lane);
   if (generate) {  // representation.py:41-43 -> helper.py:310-312 gen_random_map
+    rng_home = rng.stage(sm.mt, lane);  // the reset consumes 2*H*W (+2) draws and usually crosses a twist
     // helper.py:343-352 get_int_prob, then RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]
     double cdf[PCGRL_MAX_TILES];
     double total = 0.0, acc = 0.0;
@@ -123,20 +128,24 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
 #pragma unroll
     for (int t = 0; t < PCGRL_MAX_TILES; t++) if (t < T) cdf[t] /= acc;
     const int nchunks = (cells + 31) >> 5;
-    for (int c = 0; c < nchunks; c++) {
-      const int nin = min(32, cells - c * 32);
-      rng.fill(sm.draws, 2 * nin, lane);  // H*W random_sample() doubles in row-major order
-      uint32_t tile = 0;
-      if (lane < nin) {
-        const uint32_t a = sm.draws[2 * lane] >> 5, bb = sm.draws[2 * lane + 1] >> 6;
-        const double u = ((double)a * 67108864.0 + (double)bb) / 9007199254740992.0;
+    for (int s0 = 0; s0 < cells; s0 += 256) {  // segments of 256 cells: 512 draws staged at once, 8 cells per lane
+      const int nseg = min(256, cells - s0);
+      rng.fill(sm.draws, 2 * nseg, lane);  // H*W random_sample() doubles in row-major order
 #pragma unroll
-        for (int t = 0; t < PCGRL_MAX_TILES; t++) tile += (cdf[t] <= u) ? 1u : 0u;  // searchsorted(side='right')
-        r.map[c * 32 + lane] = (uint8_t)tile;
-        r.start_map[c * 32 + lane] = (uint8_t)tile;  // _old_map = _map.copy()
+      for (int k = 0; k < 8; k++) {
+        const int j = k * 32 + lane;  // cell inside the segment
+        uint32_t tile = 0;
+        if (j < nseg) {
+          const uint32_t a = sm.draws[2 * j] >> 5, bb = sm.draws[2 * j + 1] >> 6;
+          const double u = ((double)a * 67108864.0 + (double)bb) * (1.0 / 9007199254740992.0);  // exact scaling by 2^-53
+#pragma unroll
+          for (int t = 0; t < PCGRL_MAX_TILES; t++) tile += (cdf[t] <= u) ? 1u : 0u;  // searchsorted(side='right')
+          r.map[s0 + j] = (uint8_t)tile;
+          r.start_map[s0 + j] = (uint8_t)tile;  // _old_map = _map.copy()
+        }
+        if (k * 32 < nseg) chunk_to_bits<NP>(tile, (s0 >> 5) + k, lane, sm.bits);
       }
       __syncwarp();
-      chunk_to_bits<NP>(tile, c, lane, sm.bits);
     }
     board = bits_to_board<NP>(sm.bits, nchunks, W, H, lane);
     if (lane == 0) b.start_valid[e] = 1;
@@ -148,10 +157,9 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
     x = rng.randint(W, lane);
     y = rng.randint(H, lane);
   }
+  if (rng_home) rng.unstage(rng_home, lane);
   map_stats<PROB>(board, cfg, lane, st, need_solver);
-  if (PROB == PCGRL_PROB_BINARY && (cfg.flags & PCGRL_FLAG_RANDOM_PROBS)) {  // binary_prob.py:68-72 (problem stream)
-    WarpRng pr;
-    pr.init(r.rng_prob);
+  if (redraw_probs) {  // binary_prob.py:68-72 (problem stream)
     const double p_empty = pr.next_double(lane);
     pr.finish(lane);
     if (lane == 0) { r.tile_prob[0] = p_empty; r.tile_prob[1] = 1 - p_empty; }

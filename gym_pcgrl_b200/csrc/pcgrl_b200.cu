@@ -355,28 +355,87 @@ static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
 // one PcgrlEnv.step of a solver problem = update -> solver -> finish(+reset) -> solver
 template <int PROB>
 static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, cudaStream_t s,
-                       Staging sg) {
+                       Staging sg, int max_slots = SOLVER_MAX_SLOTS) {
   SolverQueue q1 = solver_queue(cfg, b->scratch, n, 0, b->status), q2 = solver_queue(cfg, b->scratch, n, 1, b->status);
   int32_t* old_stats = solver_old_stats(cfg, b->scratch, n);
   uint8_t* heat_cell = solver_heat_cell(cfg, b->scratch, n);
   solver_queue_clear(q1, s);
   solver_queue_clear(q2, s);
   k_step_update<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, q1, old_stats, heat_cell, n);
-  solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q1, b->scratch, n, s);
+  solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q1, b->scratch, n, s, max_slots);
   k_step_finish<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, q2, old_stats, heat_cell, n, sg);
-  if (cfg->flags & PCGRL_FLAG_AUTO_RESET) solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q2, b->scratch, n, s);
+  if (cfg->flags & PCGRL_FLAG_AUTO_RESET) solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q2, b->scratch, n, s, max_slots);
   return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
 }
 
+// pcgrl_buffers of the env range [off, off + m) with its own scratch region
+static pcgrl_buffers shard_buffers(const pcgrl_config* cfg, const pcgrl_buffers* b, int off, void* scratch, size_t scratch_bytes) {
+  const size_t cells = (size_t)cfg->width * cfg->height, o = (size_t)off;
+  pcgrl_buffers g = *b;
+  g.map += o * cells; g.heatmap += o * cells; g.pos += 2 * o; g.iteration += o; g.changes += o;
+  g.stats += o * PCGRL_MAX_STATS; g.start_stats += o * PCGRL_MAX_STATS; g.info_stats += o * PCGRL_MAX_STATS;
+  g.reward += o; g.done += o; g.rng += o * 2 * PCGRL_MT_WORDS; g.tile_prob += o * PCGRL_MAX_TILES;
+  g.start_map += o * cells; g.start_valid += o;
+  g.scratch = scratch; g.scratch_bytes = scratch_bytes;
+  return g;
+}
+
+struct GroupStreams {
+  int device = -1;
+  cudaStream_t streams[SOLVER_MAX_GROUPS];
+  cudaEvent_t fork, join[SOLVER_MAX_GROUPS];
+};
+
+static GroupStreams* group_streams() {
+  static thread_local GroupStreams gs;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (gs.device != dev) {  // (re)create for the calling thread's current device
+    for (int i = 0; i < SOLVER_MAX_GROUPS; i++) {
+      cudaStreamCreateWithFlags(&gs.streams[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&gs.join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&gs.fork, cudaEventDisableTiming);
+    gs.device = dev;
+  }
+  return &gs;
+}
+
+// T consecutive PcgrlEnv.step calls of a solver problem.  T == 1 (and the host transport) is one lock-step batch.
+// For T > 1 the actions of all steps are known, so the batch is split into independent env groups, each advancing
+// through its own T steps on its own stream: a search that runs to the iteration cap stalls one group, not the batch.
 template <int PROB>
 static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                           uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
-  for (int t = 0; t < T; t++) {
-    int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0, n});
-    if (rc) return rc;
-    if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n, b->reward, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
-    if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n, b->done, (size_t)n, cudaMemcpyDeviceToDevice, s);
+  const GroupPlan plan = solver_group_plan(cfg, n);
+  if (T == 1 || plan.groups == 1) {
+    for (int t = 0; t < T; t++) {
+      int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0, n});
+      if (rc) return rc;
+      if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n, b->reward, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
+      if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n, b->done, (size_t)n, cudaMemcpyDeviceToDevice, s);
+    }
+    return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
+  }
+  GroupStreams* gs = group_streams();
+  cudaEventRecord(gs->fork, s);
+  for (int g = 0; g < plan.groups; g++) cudaStreamWaitEvent(gs->streams[g], gs->fork, 0);
+  for (int t = 0; t < T; t++) {  // round-robin over groups keeps every stream fed while the host is still enqueueing
+    for (int g = 0; g < plan.groups; g++) {
+      const int off = g * plan.envs_per_group, m = (off + plan.envs_per_group <= n) ? plan.envs_per_group : n - off;
+      if (m <= 0) continue;
+      const pcgrl_buffers bg = shard_buffers(cfg, b, off, (char*)b->scratch + (size_t)g * plan.bytes_per_group, plan.bytes_per_group);
+      cudaStream_t sgp = gs->streams[g];
+      int rc = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, sgp, Staging{nullptr, 0u, 0, m}, plan.slots_per_group);
+      if (rc) return rc;
+      if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n + off, bg.reward, sizeof(double) * m, cudaMemcpyDeviceToDevice, sgp);
+      if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n + off, bg.done, (size_t)m, cudaMemcpyDeviceToDevice, sgp);
+    }
+  }
+  for (int g = 0; g < plan.groups; g++) {
+    cudaEventRecord(gs->join[g], gs->streams[g]);
+    cudaStreamWaitEvent(s, gs->join[g], 0);
   }
   return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
 }

@@ -51,19 +51,39 @@ static inline size_t solver_queue_bytes(int n) {
   return align_up(16 + sizeof(int32_t) * (size_t)n * (3 + 16), 256);
 }
 
-static inline SolverLayout solver_layout(const pcgrl_config* c, int n) {
+static inline SolverLayout solver_layout(const pcgrl_config* c, int n, int max_slots = SOLVER_MAX_SLOTS) {
   SolverLayout L;
   L.queue_bytes = solver_queue_bytes(n);
   L.old_stats_off = 2 * L.queue_bytes;
   L.heat_off = L.old_stats_off + align_up(sizeof(int32_t) * PCGRL_MAX_STATS * (size_t)n, 256);
   L.nodes_off = L.heat_off + align_up(6 * (size_t)n, 256);
-  L.slots = n < SOLVER_MAX_SLOTS ? n : SOLVER_MAX_SLOTS;
+  L.slots = n < max_slots ? n : max_slots;
   L.nodes_per_pass = (size_t)4 * (size_t)c->solver_power + 8;
   L.total = L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t);
   return L;
 }
 
-static inline size_t solver_scratch_bytes(const pcgrl_config* c, int n) { return solver_layout(c, n).total; }
+// Rollouts (T > 1) of the solver problems split the batch into independent env groups, one CUDA stream each,
+// so that a slow search only stalls its own group (see rollout_solver).  Each group owns a scratch region.
+#define SOLVER_MAX_GROUPS 16
+#define SOLVER_GROUP_MIN_ENVS 64
+struct GroupPlan { int groups, envs_per_group, slots_per_group; size_t bytes_per_group; };
+static inline GroupPlan solver_group_plan(const pcgrl_config* c, int n) {
+  GroupPlan g;
+  g.groups = n / SOLVER_GROUP_MIN_ENVS;
+  if (g.groups > SOLVER_MAX_GROUPS) g.groups = SOLVER_MAX_GROUPS;
+  if (g.groups < 1) g.groups = 1;
+  g.envs_per_group = ((n + g.groups - 1) / g.groups + 3) & ~3;  // multiple of 4: heat-map word atomics stay aligned
+  g.slots_per_group = 2 * SOLVER_MAX_SLOTS / g.groups;
+  if (g.slots_per_group < 8) g.slots_per_group = 8;
+  g.bytes_per_group = align_up(solver_layout(c, g.envs_per_group, g.slots_per_group).total, 256);
+  return g;
+}
+static inline size_t solver_scratch_bytes(const pcgrl_config* c, int n) {
+  const GroupPlan g = solver_group_plan(c, n);
+  const size_t single = solver_layout(c, n).total, grouped = (size_t)g.groups * g.bytes_per_group;
+  return single > grouped ? single : grouped;
+}
 
 static inline int solver_validate(const pcgrl_config* c) {
   if (c->width > 14 || c->height > 14 || c->width * c->height > 128) return 1;
@@ -90,7 +110,7 @@ static inline SolverQueue solver_queue(const pcgrl_config* c, void* scratch, int
   return q;
 }
 static inline int32_t* solver_old_stats(const pcgrl_config* c, void* scratch, int n) {
-  return (int32_t*)((char*)scratch + solver_layout(c, n).old_stats_off);
+  return (int32_t*)((char*)scratch + solver_layout(c, n).old_stats_off);  // offsets do not depend on the slot count
 }
 static inline uint8_t* solver_heat_cell(const pcgrl_config* c, void* scratch, int n) {
   return (uint8_t*)scratch + solver_layout(c, n).heat_off;
@@ -718,10 +738,10 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
 
 template <int PROB>
 static inline void solver_launch(const pcgrl_config* cfg, int32_t* stats, int32_t* start_stats, const uint8_t* maps,
-                                 SolverQueue q, void* scratch, int n, cudaStream_t s) {
+                                 SolverQueue q, void* scratch, int n, cudaStream_t s, int max_slots = SOLVER_MAX_SLOTS) {
   if constexpr (GameOf<PROB>::GAME >= 0) {
   if (!q.count) return;
-  const SolverLayout lay = solver_layout(cfg, n);
+  const SolverLayout lay = solver_layout(cfg, n, max_slots);
   int table_size = 1024;
   while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
   const size_t heap_words = (size_t)4 * cfg->solver_power + 8;

@@ -172,22 +172,38 @@ def test_batched_rollout_matches_oracle(case):
         assert ndone > 0, "case never finished an episode; raise steps"
 
 
-def test_rollout_api_equals_stepping():
+ROLLOUT_CASES = [
+    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 256, 64),
+    ("zelda-wide-v0", {}, 200, 48),
+    # solver problems: T > 1 runs the batch as independent env groups on separate streams
+    ("sokoban-wide-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 260, 40),
+    ("mdungeon-turtle-v0", {}, 192, 40),
+    ("ddave-narrow-v0", {}, 130, 40),
+]
+
+
+@pytest.mark.parametrize("case", ROLLOUT_CASES, ids=[c[0] for c in ROLLOUT_CASES])
+def test_rollout_api_equals_stepping(case):
     import torch
-    n, T = 256, 64
+    env_id, kwargs, n, T = case
     envs = []
     for _ in range(2):
-        env = util.host_env("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), num_envs=n, device="cuda")
+        env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
         env.set_rng_states(np.stack([util.randomstate_words(7 + i) for i in range(n)]))
         env.reset()
         envs.append(env)
-    acts = torch.from_numpy(np.random.RandomState(3).randint(3, size=(T, n)).astype(np.int32)).cuda()
+    arng = np.random.RandomState(3)
+    acts = torch.from_numpy(np.stack([random_actions(envs[0], arng, n) for _ in range(T)])).cuda()
     rew, done = envs[0].rollout(acts)
     for t in range(T):
         _, r, d, _ = envs[1].step(acts[t])
-        assert torch.equal(r, rew[t]) and torch.equal(d, done[t])
-    for k in ("map", "heatmap", "pos", "stats", "start_stats", "iteration", "changes", "rng"):
+        assert torch.equal(r, rew[t]) and torch.equal(d, done[t]), "%s step %d" % (env_id, t)
+    keys = ["map", "heatmap", "stats", "start_stats", "iteration", "changes", "rng", "info_stats"]
+    if env_id.split("-")[1] != "wide":
+        keys.append("pos")
+    for k in keys:
         assert torch.equal(envs[0]._tens[k], envs[1]._tens[k]), k
+    envs[0].check_status()
 
 
 HOST_CASES = [

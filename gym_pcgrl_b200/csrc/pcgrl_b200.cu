@@ -202,7 +202,8 @@ template <int PROB>
 __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant__ pcgrl_config cfg,
                                                           const __grid_constant__ pcgrl_buffers b, SolverQueue q,
                                                           const int32_t* __restrict__ old_stats,
-                                                          const uint8_t* __restrict__ heat_cell, int n, Staging sg) {
+                                                          const uint8_t* __restrict__ heat_cell, int n, Staging sg,
+                                                          double* reward_out, uint8_t* done_out) {
   constexpr int NS = ProblemTraits<PROB>::NSTATS;
   __shared__ WarpSmem smem[WPB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -216,7 +217,12 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
   const int iteration = b.iteration[e], changes = b.changes[e];
   const double reward = problem_reward<PROB>(cfg, st, old);
   const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes || iteration >= cfg.max_iterations;
-  if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
+  if (lane == 0) {
+    b.reward[e] = reward;
+    b.done[e] = done ? 1 : 0;
+    if (reward_out) reward_out[e] = reward;  // row t of the rollout outputs
+    if (done_out) done_out[e] = done ? 1 : 0;
+  }
   store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   const uint8_t* hc = heat_cell + 6 * (size_t)e;
   const int change = hc[0], hx = hc[1], hy = hc[2], cell = hc[3] | (hc[4] << 8), tile = hc[5];
@@ -355,15 +361,14 @@ static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
 // one PcgrlEnv.step of a solver problem = update -> solver -> finish(+reset) -> solver
 template <int PROB>
 static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, cudaStream_t s,
-                       Staging sg, int max_slots = SOLVER_MAX_SLOTS) {
+                       Staging sg, int max_slots = SOLVER_MAX_SLOTS, double* reward_out = nullptr, uint8_t* done_out = nullptr) {
   SolverQueue q1 = solver_queue(cfg, b->scratch, n, 0, b->status), q2 = solver_queue(cfg, b->scratch, n, 1, b->status);
   int32_t* old_stats = solver_old_stats(cfg, b->scratch, n);
   uint8_t* heat_cell = solver_heat_cell(cfg, b->scratch, n);
-  solver_queue_clear(q1, s);
-  solver_queue_clear(q2, s);
+  solver_queue_clear2(q1, q2, s);
   k_step_update<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, q1, old_stats, heat_cell, n);
   solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q1, b->scratch, n, s, max_slots);
-  k_step_finish<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, q2, old_stats, heat_cell, n, sg);
+  k_step_finish<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, q2, old_stats, heat_cell, n, sg, reward_out, done_out);
   if (cfg->flags & PCGRL_FLAG_AUTO_RESET) solver_launch<PROB>(cfg, b->stats, b->start_stats, b->map, q2, b->scratch, n, s, max_slots);
   return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
 }
@@ -411,10 +416,10 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
   const GroupPlan plan = solver_group_plan(cfg, n);
   if (T == 1 || plan.groups == 1) {
     for (int t = 0; t < T; t++) {
-      int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0, n});
+      int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0, n},
+                                 SOLVER_MAX_SLOTS, reward_out ? reward_out + (size_t)t * n : nullptr,
+                                 done_out ? done_out + (size_t)t * n : nullptr);
       if (rc) return rc;
-      if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n, b->reward, sizeof(double) * n, cudaMemcpyDeviceToDevice, s);
-      if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n, b->done, (size_t)n, cudaMemcpyDeviceToDevice, s);
     }
     return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
   }
@@ -427,10 +432,10 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
       if (m <= 0) continue;
       const pcgrl_buffers bg = shard_buffers(cfg, b, off, (char*)b->scratch + (size_t)g * plan.bytes_per_group, plan.bytes_per_group);
       cudaStream_t sgp = gs->streams[g];
-      int rc = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, sgp, Staging{nullptr, 0u, 0, m}, plan.slots_per_group);
+      int rc = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, sgp, Staging{nullptr, 0u, 0, m},
+                                 plan.slots_per_group, reward_out ? reward_out + (size_t)t * n + off : nullptr,
+                                 done_out ? done_out + (size_t)t * n + off : nullptr);
       if (rc) return rc;
-      if (reward_out) cudaMemcpyAsync(reward_out + (size_t)t * n + off, bg.reward, sizeof(double) * m, cudaMemcpyDeviceToDevice, sgp);
-      if (done_out) cudaMemcpyAsync(done_out + (size_t)t * n + off, bg.done, (size_t)m, cudaMemcpyDeviceToDevice, sgp);
     }
   }
   for (int g = 0; g < plan.groups; g++) {

@@ -116,13 +116,21 @@ static inline uint8_t* solver_heat_cell(const pcgrl_config* c, void* scratch, in
   return (uint8_t*)scratch + solver_layout(c, n).heat_off;
 }
 
-__global__ void k_queue_clear(SolverQueue q) {
+__global__ void k_queue_clear(SolverQueue q, SolverQueue q2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *q.count = 0;
-  if (i < q.capacity) { q.pass_done[i] = 0; q.best_win[i] = 4; }
+  if (i == 0) { *q.count = 0; if (q2.count) *q2.count = 0; }
+  if (i < q.capacity) {
+    q.pass_done[i] = 0; q.best_win[i] = 4;
+    if (q2.count) { q2.pass_done[i] = 0; q2.best_win[i] = 4; }
+  }
 }
 static inline void solver_queue_clear(SolverQueue q, cudaStream_t s) {
-  if (q.count) k_queue_clear<<<(q.capacity + 255) / 256, 256, 0, s>>>(q);
+  SolverQueue none;
+  memset(&none, 0, sizeof(none));
+  if (q.count) k_queue_clear<<<(q.capacity + 255) / 256, 256, 0, s>>>(q, none);
+}
+static inline void solver_queue_clear2(SolverQueue q, SolverQueue q2, cudaStream_t s) {  // both queues, one launch
+  if (q.count) k_queue_clear<<<(q.capacity + 255) / 256, 256, 0, s>>>(q, q2);
 }
 
 __device__ __forceinline__ void solver_enqueue(const SolverQueue& q, int env, int mode, int lane) {
@@ -518,6 +526,11 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
   int best = -1, best_h = 0, best_depth = 0;
   if (lane == 0) {
     SState root = root0;
+    if (sk_small) {
+      const unsigned long long occ = sk_occupancy(L, root);
+      root.misc = (uint32_t)occ;
+      root.pad = (uint32_t)(occ >> 32);
+    }
     root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
     node_put(nodes, cache, 0, root);
     if (b >= 0) { heap[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
@@ -539,8 +552,12 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
         cur = (b >= 0) ? (int)(heap_pop(heap, nheap) & 0x7fffu) : head++;
         node_fetch(nodes, cache, cur, nn, cs);
         bool win;
-        if (sk_small) win = (sk_occupancy(L, cs) & L.target64) == L.target64 && L.ntargets == L.ncrates && L.ntargets > 0;
-        else win = g_win<GAME>(L, cs);
+        if (sk_small) {  // small sokoban levels carry their crate-occupancy mask in (misc, pad)
+          const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
+          win = (occ & L.target64) == L.target64 && L.ntargets == L.ncrates && L.ntargets > 0;
+        } else {
+          win = g_win<GAME>(L, cs);
+        }
         if (check_lose && st_health(cs) <= 0) {
           action = ACT_SKIP;
         } else if (win) {
@@ -581,6 +598,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     cs.m[2] = __shfl_sync(FULL_MASK, cs.m[2], 0); cs.m[3] = __shfl_sync(FULL_MASK, cs.m[3], 0);
     cs.ks = __shfl_sync(FULL_MASK, cs.ks, 0); cs.dh = __shfl_sync(FULL_MASK, cs.dh, 0);
     cs.misc = __shfl_sync(FULL_MASK, cs.misc, 0);
+    cs.pad = __shfl_sync(FULL_MASK, cs.pad, 0);
     const int nn_base = __shfl_sync(FULL_MASK, nn, 0);
     const int cd = st_depth(cs);
     bool valid = false;
@@ -592,7 +610,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
         const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
         if (sk_small) {
           // bit-mask form of State.update (:298-327): the expanded node is never a winning state
-          const unsigned long long occ = sk_occupancy(L, cs);
+          const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
           const int nx = st_px(cs) + dx, ny = st_py(cs) + dy;
           const unsigned long long nbit = 1ull << (ny * L.bw + nx);  // inside: the border ring is solid
           h = st_h(cs);
@@ -606,7 +624,10 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
               if (!((L.solid64 | occ) & cbit)) {
                 st_set_pos(c, nx, ny);
                 sk_set_crate(c, sk_crate_at(cs, nx, ny), cx, cy);
-                valid = (((occ ^ nbit ^ cbit) & L.dead64) == 0ull);  // a crate moved: prune deadlocks (any crate)
+                const unsigned long long occ2 = occ ^ nbit ^ cbit;
+                c.misc = (uint32_t)occ2;
+                c.pad = (uint32_t)(occ2 >> 32);
+                valid = ((occ2 & L.dead64) == 0ull);  // a crate moved: prune deadlocks (any crate)
                 h = sk_heuristic(L, c);
               }
             }

@@ -8,7 +8,7 @@ MAX_STATS = 12
 MT_WORDS = 625
 
 PROB_BINARY, PROB_ZELDA, PROB_SOKOBAN, PROB_DDAVE, PROB_MDUNGEON = range(5)
-REP_NARROW, REP_TURTLE, REP_WIDE = range(3)
+REP_NARROW, REP_TURTLE, REP_WIDE, REP_NARROWCAST, REP_NARROWMULTI, REP_TURTLECAST = range(6)
 
 FLAG_RANDOM_TILE = 1
 FLAG_WARP = 2
@@ -18,7 +18,9 @@ FLAG_AUTO_RESET = 16
 
 PROBLEM_IDS = {"binary": PROB_BINARY, "zelda": PROB_ZELDA, "sokoban": PROB_SOKOBAN,
                "ddave": PROB_DDAVE, "mdungeon": PROB_MDUNGEON}
-REP_IDS = {"narrow": REP_NARROW, "turtle": REP_TURTLE, "wide": REP_WIDE}
+REP_IDS = {"narrow": REP_NARROW, "turtle": REP_TURTLE, "wide": REP_WIDE, "narrowcast": REP_NARROWCAST,
+           "narrowmulti": REP_NARROWMULTI, "turtlecast": REP_TURTLECAST}
+ACTION_DIMS = {REP_NARROW: 1, REP_TURTLE: 1, REP_WIDE: 3, REP_NARROWCAST: 2, REP_NARROWMULTI: 9, REP_TURTLECAST: 2}
 
 # key order of each Problem.get_stats dict == column order of every stats row
 STAT_NAMES = {
@@ -96,4 +98,6 @@ BUFFER_SPECS = [
 
 
 def action_dim(representation):
-    return 3 if representation in (REP_WIDE, "wide") else 1
+    if isinstance(representation, str):
+        representation = REP_IDS[representation]
+    return ACTION_DIMS[int(representation)]

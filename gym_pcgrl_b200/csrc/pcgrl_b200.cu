@@ -45,13 +45,13 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   if (e >= n) return;
   WarpSmem& sm = smem[wib];
   const int W = cfg.width, H = cfg.height, cells = W * H;
-  const int adim = (cfg.representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const int adim = action_dim(cfg.representation);
   const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
   const EnvRefs r = env_refs(cfg, b, e);
 
   // all prologue loads are independent: issue them before the ballots of load_board serialise the warp
   WarpRng rng;
-  rng.init(r.rng_rep, (cfg.representation == PCGRL_REP_NARROW) ? lane : -1);
+  rng.init(r.rng_rep, (cfg.representation == PCGRL_REP_NARROW || cfg.representation >= PCGRL_REP_NARROWCAST) ? lane : -1);
   int x = 0, y = 0;
   if (cfg.representation != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
   int iteration = b.iteration[e], changes = b.changes[e];
@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];
     int hx, hy, cell, tile;
-    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile);
+    bool multi;
+    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi);
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
       bool unused;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
     } else {
       if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
-      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map);
+      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map, multi);
     }
   }
   rng.finish(lane);
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(32 * WPB) k_step_update(const __grid_constant_
   const int e = blockIdx.x * WPB + wib;
   if (e >= n) return;
   const int W = cfg.width, H = cfg.height;
-  const int adim = (cfg.representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const int adim = action_dim(cfg.representation);
   const EnvRefs r = env_refs(cfg, b, e);
   Board board = load_board<NP>(r.map, W, H, lane, smem[wib].bits);
   int x = 0, y = 0;
@@ -178,7 +179,8 @@ __global__ void __launch_bounds__(32 * WPB) k_step_update(const __grid_constant_
   WarpRng rng;
   rng.init(r.rng_rep);
   int hx, hy, cell, tile;
-  const int change = apply_action(cfg, actions + (size_t)e * adim, board, r.map, rng, lane, x, y, hx, hy, cell, tile);
+  bool multi;
+  const int change = apply_action(cfg, actions + (size_t)e * adim, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi);
   rng.finish(lane);
   if (lane == 0) {
     if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(32 * WPB) k_step_update(const __grid_constant_
     b.changes[e] += change;
     uint8_t* hc = heat_cell + 6 * (size_t)e;  // consumed by k_step_finish
     hc[0] = (uint8_t)change; hc[1] = (uint8_t)hx; hc[2] = (uint8_t)hy;
-    hc[3] = (uint8_t)(cell & 0xff); hc[4] = (uint8_t)(cell >> 8); hc[5] = (uint8_t)tile;
+    hc[3] = (uint8_t)(cell & 0xff); hc[4] = (uint8_t)(cell >> 8); hc[5] = (uint8_t)(tile | (multi ? 0x80 : 0));
   }
   if (change > 0) {
     bool need_solver;
@@ -225,7 +227,8 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
   }
   store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   const uint8_t* hc = heat_cell + 6 * (size_t)e;
-  const int change = hc[0], hx = hc[1], hy = hc[2], cell = hc[3] | (hc[4] << 8), tile = hc[5];
+  const int change = hc[0], hx = hc[1], hy = hc[2], cell = hc[3] | (hc[4] << 8), tile = hc[5] & 0x7f;
+  const bool multi = (hc[5] & 0x80) != 0;
   int px = 0, py = 0;
   if (cfg.representation != PCGRL_REP_WIDE) { px = b.pos[2 * e]; py = b.pos[2 * e + 1]; }
   if (done && (cfg.flags & PCGRL_FLAG_AUTO_RESET)) {
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
     write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
   } else {
     if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);
-    write_record(sg, cfg, e, lane, reward, done, px, py, change > 0, false, cell, tile, nullptr);
+    write_record(sg, cfg, e, lane, reward, done, px, py, change > 0, false, cell, tile, b.map + (size_t)e * cells, multi);
   }
   (void)H;
 }
@@ -325,6 +328,11 @@ static int check_common(const pcgrl_config* cfg, const pcgrl_buffers* b, int n) 
   if (cfg->problem >= PCGRL_PROB_SOKOBAN && (!b->scratch || b->scratch_bytes < pcgrl_scratch_bytes(cfg, n)))
     return fail(-1, "scratch buffer too small: see pcgrl_scratch_bytes()");
   return 0;
+}
+
+static inline int action_dim_host(int rep) {
+  return rep == PCGRL_REP_WIDE ? 3 : (rep == PCGRL_REP_NARROWCAST || rep == PCGRL_REP_TURTLECAST) ? 2
+       : rep == PCGRL_REP_NARROWMULTI ? 9 : 1;
 }
 
 static inline dim3 env_grid(int n) { return dim3((unsigned)((n + WPB - 1) / WPB)); }
@@ -412,7 +420,7 @@ static GroupStreams* group_streams() {
 template <int PROB>
 static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                           uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
-  const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const int adim = action_dim_host(cfg->representation);
   const GroupPlan plan = solver_group_plan(cfg, n);
   if (T == 1 || plan.groups == 1) {
     for (int t = 0; t < T; t++) {
@@ -522,7 +530,7 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t cells = (size_t)cfg->width * cfg->height;
-  const int adim = (cfg->representation == PCGRL_REP_WIDE) ? 3 : 1;
+  const int adim = action_dim_host(cfg->representation);
   const bool wide = cfg->representation == PCGRL_REP_WIDE;
   const bool delta = io->mode == 1;
   if (delta && (!io->d_staging || !io->h_staging || io->staging_bytes < pcgrl_host_staging_bytes(cfg, n)))
@@ -554,7 +562,12 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
         else if (io->map) memcpy(io->map + (size_t)e * cells, slots + (size_t)r.slot * cells, cells);
         if (io->heatmap) memset(io->heatmap + (size_t)e * cells, 0, cells);
       } else if (r.flags & PCGRL_REC_CHANGED) {
-        if (io->map) io->map[(size_t)e * cells + r.cell] = r.tile;
+        if (r.flags & PCGRL_REC_MULTI) {
+          if (r.slot == 0xFF) overflow = true;
+          else if (io->map) memcpy(io->map + (size_t)e * cells, slots + (size_t)r.slot * cells, cells);
+        } else if (io->map) {
+          io->map[(size_t)e * cells + r.cell] = r.tile;
+        }
         if (io->heatmap) io->heatmap[(size_t)e * cells + (wide ? (size_t)r.cell : (size_t)r.posy * cfg->width + r.posx)] += 1;
       }
     }

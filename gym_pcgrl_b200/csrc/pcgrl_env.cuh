@@ -26,34 +26,96 @@ __device__ __forceinline__ EnvRefs env_refs(const pcgrl_config& cfg, const pcgrl
   return r;
 }
 
+__device__ __forceinline__ int action_dim(int representation) {
+  return representation == PCGRL_REP_WIDE ? 3
+       : (representation == PCGRL_REP_NARROWCAST || representation == PCGRL_REP_TURTLECAST) ? 2
+       : representation == PCGRL_REP_NARROWMULTI ? 9 : 1;
+}
+
+// turtle_rep.py:101-125 / turtle_cast_rep.py:41-61: move the cursor, clamp or wrap
+__device__ __forceinline__ void turtle_move(const pcgrl_config& cfg, int a, int& x, int& y) {
+  const int W = cfg.width, H = cfg.height;
+  const bool warp = (cfg.flags & PCGRL_FLAG_WARP) != 0;
+  const int dx = (a == 0) ? -1 : (a == 1) ? 1 : 0, dy = (a == 2) ? -1 : (a == 3) ? 1 : 0;
+  x += dx;
+  if (x < 0) x = warp ? x + W : 0;
+  if (x >= W) x = warp ? x - W : W - 1;
+  y += dy;
+  if (y < 0) y = warp ? y + H : 0;
+  if (y >= H) y = warp ? y - H : H - 1;
+}
+
+// Write up to nine tiles of the 3x3 block centred on (x, y): t9[(dy+1)*3 + dx+1] >= 0 is the new tile, -1 keeps
+// the cell; cells outside the map are skipped (narrow_cast_rep.py:43-48, narrow_multi_rep.py:41-47,
+// turtle_cast_rep.py:69-75).  Lane y+dy edits its own bitboard row and the uint8 map; returns the number of
+// cells whose tile changed.
+__device__ __forceinline__ int apply_stamp(const pcgrl_config& cfg, Board& board, uint8_t* map, int lane, int x, int y,
+                                           const int (&t9)[9]) {
+  const int W = cfg.width, H = cfg.height;
+  int cnt = 0;
+  const int row = lane - y;  // -1, 0, 1 for the three lanes that own a stamped row
+  if (row >= -1 && row <= 1 && lane < H) {
+#pragma unroll
+    for (int dx = -1; dx <= 1; dx++) {
+      const int cx = x + dx;
+      const int newt = (row < 0) ? t9[dx + 1] : (row == 0) ? t9[3 + dx + 1] : t9[6 + dx + 1];
+      if (cx >= 0 && cx < W && newt >= 0) {
+        if (tile_at(board, cx) != newt) {
+          cnt++;
+          set_tile(board, cx, newt);
+          map[lane * W + cx] = (uint8_t)newt;
+        }
+      }
+    }
+  }
+  return (int)__reduce_add_sync(FULL_MASK, (unsigned)cnt);
+}
+
 // Representation.update(action) -> (change, x, y) where (hx, hy) is the heat-map cell
-// (narrow_rep.py:99-114: the cursor AFTER it moved; turtle_rep.py:101-129; wide_rep.py:67-70).
-// The changed tile is written to the uint8 map in HBM (one byte) and to the bitboards of lane y.
+// (narrow_rep.py:99-114: the cursor AFTER it moved; turtle_rep.py:101-129; wide_rep.py:67-70; the cast / multi
+// variants stamp a 3x3 block).  Changed tiles are written to the uint8 map in HBM and to the bitboards.
+// cell/tile describe a single-cell edit (delta transport); multi is set when more than one cell may have changed.
 __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32_t* __restrict__ act, Board& board,
                                             uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy,
-                                            int& cell, int& tile) {
-  const int W = cfg.width, H = cfg.height;
+                                            int& cell, int& tile, bool& multi) {
+  const int W = cfg.width, H = cfg.height, rep = cfg.representation;
   int change = 0, wx = x, wy = y, newt = -1;
-  if (cfg.representation == PCGRL_REP_NARROW) {
+  multi = false;
+  if (rep == PCGRL_REP_NARROW) {
     const int a = act[0];
     if (a > 0) newt = (a - 1) & 7;
-  } else if (cfg.representation == PCGRL_REP_TURTLE) {
+  } else if (rep == PCGRL_REP_TURTLE) {
     const int a = act[0];
     if (a >= 4) newt = (a - 4) & 7;
-    else if (a >= 0) {
-      const bool warp = (cfg.flags & PCGRL_FLAG_WARP) != 0;
-      const int dx = (a == 0) ? -1 : (a == 1) ? 1 : 0, dy = (a == 2) ? -1 : (a == 3) ? 1 : 0;
-      x += dx;
-      if (x < 0) x = warp ? x + W : 0;
-      if (x >= W) x = warp ? x - W : W - 1;
-      y += dy;
-      if (y < 0) y = warp ? y + H : 0;
-      if (y >= H) y = warp ? y - H : H - 1;
-    }
-  } else {
+    else if (a >= 0) turtle_move(cfg, a, x, y);
+  } else if (rep == PCGRL_REP_WIDE) {
     wx = min(max(act[0], 0), W - 1);
     wy = min(max(act[1], 0), H - 1);
     newt = act[2] & 7;
+  } else if (rep == PCGRL_REP_NARROWCAST) {
+    const int type = act[0], value = act[1] & 7;
+    if (type == 1) newt = value;
+    else if (type == 2) {
+      const int t9[9] = {value, value, value, value, value, value, value, value, value};
+      change = apply_stamp(cfg, board, map, lane, x, y, t9);
+      multi = true;
+    }
+  } else if (rep == PCGRL_REP_NARROWMULTI) {
+    int t9[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { const int a = act[k]; t9[k] = (a > 0) ? ((a - 1) & 7) : -1; }
+    change = apply_stamp(cfg, board, map, lane, x, y, t9);
+    multi = true;
+  } else {  // PCGRL_REP_TURTLECAST
+    const int type = act[0], value = act[1] & 7;
+    if (type >= 0 && type < 4) turtle_move(cfg, type, x, y);
+    else if (type == 4) newt = value;
+    else if (type == 5) {
+      const int t9[9] = {value, value, value, value, value, value, value, value, value};
+      change = apply_stamp(cfg, board, map, lane, x, y, t9);
+      multi = true;
+    }
+    wx = x; wy = y;
   }
   if (newt >= 0) {
     const int oldt = __shfl_sync(FULL_MASK, tile_at(board, wx), wy);
@@ -65,7 +127,7 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
   }
   cell = wy * W + wx;
   tile = newt < 0 ? 0 : newt;
-  if (cfg.representation == PCGRL_REP_NARROW) {
+  if (rep == PCGRL_REP_NARROW || rep == PCGRL_REP_NARROWCAST || rep == PCGRL_REP_NARROWMULTI) {
     if (cfg.flags & PCGRL_FLAG_RANDOM_TILE) {
       x = rng.randint(W, lane);
       y = rng.randint(H, lane);
@@ -74,10 +136,10 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
       if (x >= W) { x = 0; y += 1; if (y >= H) y = 0; }
     }
     hx = x; hy = y;
-  } else if (cfg.representation == PCGRL_REP_TURTLE) {
-    hx = x; hy = y;
-  } else {
+  } else if (rep == PCGRL_REP_WIDE) {
     hx = wx; hy = wy;
+  } else {
+    hx = x; hy = y;
   }
   return change;
 }
@@ -180,6 +242,7 @@ struct __align__(16) StepRecord {
 };
 #define PCGRL_REC_CHANGED 1
 #define PCGRL_REC_RESET 2
+#define PCGRL_REC_MULTI 4 /* several cells changed: the whole map is staged, the heat map is kept */
 #define PCGRL_STAGING_HEADER 16
 
 struct Staging {
@@ -191,11 +254,12 @@ struct Staging {
 
 __device__ __forceinline__ void write_record(const Staging& sg, const pcgrl_config& cfg, int e, int lane, double reward,
                                              bool done, int x, int y, bool changed, bool was_reset, int cell, int tile,
-                                             const uint8_t* new_map) {
+                                             const uint8_t* new_map, bool multi = false) {
   if (!sg.base) return;
   const int cells = cfg.width * cfg.height;
   int slot = 0xFF;
-  if (was_reset) {
+  multi = multi && changed && !was_reset;
+  if (was_reset || multi) {
     uint32_t s = 0;
     if (lane == 0) s = atomicAdd(reinterpret_cast<uint32_t*>(sg.base), 1u) - sg.reset_base;
     s = __shfl_sync(FULL_MASK, s, 0);
@@ -212,7 +276,8 @@ __device__ __forceinline__ void write_record(const Staging& sg, const pcgrl_conf
     r.done = done ? 1 : 0;
     r.posx = (uint8_t)x;
     r.posy = (uint8_t)y;
-    r.flags = (uint8_t)((changed && !was_reset ? PCGRL_REC_CHANGED : 0) | (was_reset ? PCGRL_REC_RESET : 0));
+    r.flags = (uint8_t)((changed && !was_reset ? PCGRL_REC_CHANGED : 0) | (was_reset ? PCGRL_REC_RESET : 0) |
+                        (multi ? PCGRL_REC_MULTI : 0));
     r.cell = (uint16_t)cell;
     r.tile = (uint8_t)tile;
     r.slot = (uint8_t)slot;

@@ -139,7 +139,7 @@ class BatchedPcgrlEnv:
         if a.device != self._dev or a.dtype != torch.int32 or not a.is_contiguous():
             a = a.to(device=self._dev, dtype=torch.int32).contiguous()
         assert a.numel() == self.num_envs * self._adim, "actions must have shape [%d%s]" % (
-            self.num_envs, ",3" if self._adim == 3 else "")
+            self.num_envs, ",%d" % self._adim if self._adim > 1 else "")
         with torch.cuda.device(self._dev):
             _native.check(_native.lib().pcgrl_step(C.byref(self._cfg), C.byref(self._cbufs), a.data_ptr(),
                                                    self.num_envs, _native.stream_ptr(self._dev)), "pcgrl_step")
@@ -353,7 +353,7 @@ class PcgrlEnv:
 
     def step(self, action):
         a = np.asarray(action, dtype=np.int32).reshape(1, -1)
-        obs, reward, done, info = self._batched.step(a if self._batched._adim == 3 else a.reshape(1))
+        obs, reward, done, info = self._batched.step(a if self._batched._adim > 1 else a.reshape(1))
         r = float(reward[0].item())
         info = {k: (int(v[0].item()) if hasattr(v, "dim") else v) for k, v in info.items()}
         return self._obs(obs), (int(r) if r == int(r) and self._prob.name in ("binary", "zelda") else r), \

@@ -33,8 +33,16 @@ extern "C" {
 /* PROBLEMS registry order (reference: gym_pcgrl/envs/probs/__init__.py:9-16; smb is out of scope) */
 enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_DDAVE = 3,
        PCGRL_PROB_MDUNGEON = 4, PCGRL_NUM_PROBLEMS = 5 };
-/* REPRESENTATIONS (reference: gym_pcgrl/envs/reps/__init__.py:9-16; cast/multi variants are "next") */
-enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_NUM_REPS = 3 };
+/* REPRESENTATIONS (reference: gym_pcgrl/envs/reps/__init__.py:9-16).  Action layout (int32 per env):
+ *   narrow      [1]  0 = keep, a>0 writes tile a-1 at the cursor                  (narrow_rep.py:99-114)
+ *   turtle      [1]  0..3 move, a>=4 writes tile a-4                               (turtle_rep.py:101-129)
+ *   wide        [3]  x, y, tile                                                    (wide_rep.py:67-70)
+ *   narrowcast  [2]  type (0 keep, 1 cursor cell, 2 3x3 block), tile               (narrow_cast_rep.py:36-59)
+ *   narrowmulti [9]  one entry per cell of the 3x3 block, 0 = keep, a>0 tile a-1   (narrow_multi_rep.py:39-59)
+ *   turtlecast  [2]  type (0..3 move, 4 cursor cell, 5 3x3 block), tile            (turtle_cast_rep.py:38-76) */
+enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP_NARROWCAST = 3,
+       PCGRL_REP_NARROWMULTI = 4, PCGRL_REP_TURTLECAST = 5, PCGRL_NUM_REPS = 6 };
+#define PCGRL_MAX_ACTION_DIM 9
 
 #define PCGRL_MAX_DIM 32     /* width, height <= 32: one bitboard row per warp lane          */
 #define PCGRL_MAX_TILES 8    /* zelda / mdungeon alphabets                                    */
@@ -125,8 +133,8 @@ size_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int n_envs);
 int pcgrl_reset(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const uint8_t* mask_or_null,
                 int n, void* stream);
 
-/* PcgrlEnv.step(action) for n envs.  actions: int32 [n] (narrow/turtle) or [n][3] = (x,y,tile)
- * (wide).  pcgrl_env.py:129-150 */
+/* PcgrlEnv.step(action) for n envs.  actions: int32 [n][adim], adim per representation as listed at
+ * the PCGRL_REP_* enum (1 narrow/turtle, 3 wide, 2 narrowcast/turtlecast, 9 narrowmulti).  pcgrl_env.py:129-150 */
 int pcgrl_step(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* actions, int n,
                void* stream);
 

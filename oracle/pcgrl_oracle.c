@@ -806,11 +806,67 @@ static int env_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32
       change = (map[y * W + x] != a - 4);
       map[y * W + x] = (uint8_t)(a - 4);
     }
-  } else { /* wide_rep.py:67-70 */
+  } else if (cfg->representation == PCGRL_REP_WIDE) { /* wide_rep.py:67-70 */
     x = actions[3 * i]; y = actions[3 * i + 1];
     int v = actions[3 * i + 2];
     change = (map[y * W + x] != v);
     map[y * W + x] = (uint8_t)v;
+  } else if (cfg->representation == PCGRL_REP_NARROWCAST || cfg->representation == PCGRL_REP_NARROWMULTI) {
+    if (cfg->representation == PCGRL_REP_NARROWCAST) { /* narrow_cast_rep.py:36-59 */
+      int type = actions[2 * i], value = actions[2 * i + 1];
+      if (type == 1) {
+        change += (map[y * W + x] != value);
+        map[y * W + x] = (uint8_t)value;
+      } else if (type == 2) {
+        int low_y = y - 1 > 0 ? y - 1 : 0, high_y = y + 2 < H ? y + 2 : H;
+        int low_x = x - 1 > 0 ? x - 1 : 0, high_x = x + 2 < W ? x + 2 : W;
+        for (int yy = low_y; yy < high_y; yy++)
+          for (int xx = low_x; xx < high_x; xx++) {
+            change += (map[yy * W + xx] != value);
+            map[yy * W + xx] = (uint8_t)value;
+          }
+      }
+    } else { /* narrow_multi_rep.py:39-59 */
+      const int32_t* a = actions + 9 * i;
+      int low_y = y - 1 > 0 ? y - 1 : 0, high_y = y + 2 < H ? y + 2 : H;
+      int low_x = x - 1 > 0 ? x - 1 : 0, high_x = x + 2 < W ? x + 2 : W;
+      for (int k = 0; k < 9; k++) {
+        int xx = x + (k % 3) - 1, yy = y + (k / 3) - 1;
+        if (xx >= low_x && xx < high_x && yy >= low_y && yy < high_y && a[k] > 0) {
+          change += (map[yy * W + xx] != a[k] - 1);
+          map[yy * W + xx] = (uint8_t)(a[k] - 1);
+        }
+      }
+    }
+    if (cfg->flags & PCGRL_FLAG_RANDOM_TILE) { /* narrow_rep.py cursor advance, inherited */
+      x = mt_randint(rng_rep, W);
+      y = mt_randint(rng_rep, H);
+    } else {
+      x += 1;
+      if (x >= W) { x = 0; y += 1; if (y >= H) y = 0; }
+    }
+  } else { /* turtle_cast_rep.py:38-76 */
+    static const int TDX[4] = {-1, 1, 0, 0}, TDY[4] = {0, 0, -1, 1};
+    int type = actions[2 * i], value = actions[2 * i + 1], warp = (cfg->flags & PCGRL_FLAG_WARP) != 0;
+    if (type < 4) {
+      x += TDX[type];
+      if (x < 0) x = warp ? x + W : 0;
+      if (x >= W) x = warp ? x - W : W - 1;
+      y += TDY[type];
+      if (y < 0) y = warp ? y + H : 0;
+      if (y >= H) y = warp ? y - H : H - 1;
+    } else if (type == 4) {
+      change = (map[y * W + x] != value);
+      map[y * W + x] = (uint8_t)value;
+    } else if (type == 5) {
+      int low_y = y - 1 > 0 ? y - 1 : 0, high_y = y + 2 < H ? y + 2 : H;
+      int low_x = x - 1 > 0 ? x - 1 : 0, high_x = x + 2 < W ? x + 2 : W;
+      for (int yy = low_y; yy < high_y; yy++)
+        for (int xx = low_x; xx < high_x; xx++) {
+          change += (map[yy * W + xx] != value);
+          map[yy * W + xx] = (uint8_t)value;
+        }
+    }
   }
   if (cfg->representation != PCGRL_REP_WIDE) { b->pos[2 * i] = (uint8_t)x; b->pos[2 * i + 1] = (uint8_t)y; }
   if (change > 0) {

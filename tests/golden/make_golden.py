@@ -79,6 +79,13 @@ KAT_CONFIGS = [
     ("sokoban_narrow_sparse", "sokoban-narrow-v0", dict(probs=SOKOBAN_SPARSE)),
     ("sokoban_turtle_sparse", "sokoban-turtle-v0", dict(probs=SOKOBAN_SPARSE)),
     ("binary_wide_fixedprob", "binary-wide-v0", dict(random_probs=False, change_percentage=0.6)),
+    # the 3x3-stamp representations
+    ("binary_narrowcast", "binary-narrowcast-v0", {}),
+    ("zelda_narrowmulti", "zelda-narrowmulti-v0", {}),
+    ("sokoban_turtlecast_sparse", "sokoban-turtlecast-v0", dict(probs=SOKOBAN_SPARSE)),
+    ("binary_turtlecast_warp", "binary-turtlecast-v0", dict(warp=True, width=9, height=12, change_percentage=0.5)),
+    ("ddave_narrowcast_raster", "ddave-narrowcast-v0", dict(random_tile=False)),
+    ("mdungeon_narrowmulti", "mdungeon-narrowmulti-v0", {}),
 ]
 
 
@@ -127,7 +134,7 @@ def run_kat(args):
     S = len(STAT_NAMES[prob_name])
     wide = "pos" not in env.observation_space.spaces
     rec = dict(
-        actions=np.zeros((T, 3), np.int32), map=np.zeros((T, h, w), np.uint8), heat=np.zeros((T, h, w), np.int32),
+        actions=np.zeros((T, 9), np.int32), map=np.zeros((T, h, w), np.uint8), heat=np.zeros((T, h, w), np.int32),
         pos=np.zeros((T, 2), np.int32), reward=np.zeros(T, np.float64), done=np.zeros(T, np.uint8),
         stats=np.zeros((T, S), np.int32), iteration=np.zeros(T, np.int32), changes=np.zeros(T, np.int32))
     rmap, rpos, rstats, rstep = [], [], [], []

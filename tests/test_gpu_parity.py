@@ -83,7 +83,8 @@ def test_trajectory_matches_reference_golden(meta):
     k = 0
     total = 0.0
     for t in range(meta["steps"]):
-        a = traj["actions"][t, :3] if wide else int(traj["actions"][t, 0])
+        adim = _abi.action_dim(rep)
+        a = traj["actions"][t, :adim] if adim > 1 else int(traj["actions"][t, 0])
         obs, r, d, info = env.step(a)
         ctx = "%s step %d" % (meta["name"], t)
         np.testing.assert_array_equal(obs["map"], traj["map"][t], err_msg=ctx)
@@ -128,6 +129,12 @@ BATCH_CASES = [
     ("ddave-turtle-v0", {}, 128, 80),
     ("mdungeon-wide-v0", dict(probs={"empty": 0.85, "solid": 0.05, "player": 0.01, "exit": 0.01, "potion": 0.02, "treasure": 0.02, "goblin": 0.02, "ogre": 0.02}), 128, 60),
     ("mdungeon-narrow-v0", {}, 128, 80),
+    # 3x3-stamp representations
+    ("binary-narrowcast-v0", dict(width=16, height=16, change_percentage=0.2), 256, 100),
+    ("zelda-narrowmulti-v0", {}, 128, 80),
+    ("binary-turtlecast-v0", dict(warp=True, width=9, height=12, change_percentage=0.5), 128, 150),
+    ("sokoban-turtlecast-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 64, 60),
+    ("mdungeon-narrowmulti-v0", {}, 64, 60),
 ]
 
 
@@ -212,6 +219,8 @@ HOST_CASES = [
     ("binary-wide-v0", dict(width=5, height=4, change_percentage=0.3), 96, 80),     # many resets per step: staging overflow path
     ("sokoban-wide-v0", {}, 128, 60),                                                   # solver pipeline + overflow
     ("mdungeon-narrow-v0", {}, 64, 60),
+    ("zelda-narrowmulti-v0", {}, 96, 60),          # multi-cell edits: whole-map records
+    ("binary-turtlecast-v0", dict(width=10, height=10, change_percentage=0.4), 96, 120),
 ]
 
 

@@ -16,8 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_registry_and_spaces():
     assert set(PROBLEMS) == {"binary", "ddave", "mdungeon", "sokoban", "zelda"}
-    assert set(REPRESENTATIONS) == {"narrow", "turtle", "wide"}
-    assert len(pkg.REGISTRY) == 15 and "zelda-turtle-v0" in pkg.REGISTRY
+    assert set(REPRESENTATIONS) == {"narrow", "turtle", "wide", "narrowcast", "narrowmulti", "turtlecast"}
+    assert len(pkg.REGISTRY) == 30 and "zelda-turtle-v0" in pkg.REGISTRY and "sokoban-narrowmulti-v0" in pkg.REGISTRY
+    assert BatchedPcgrlEnv("zelda", "narrowmulti").action_space.nvec.tolist() == [9] * 9
+    assert BatchedPcgrlEnv("binary", "narrowcast").action_space.nvec.tolist() == [3, 2]
+    assert BatchedPcgrlEnv("ddave", "turtlecast").action_space.nvec.tolist() == [6, 7]
     env = BatchedPcgrlEnv("zelda", "turtle", num_envs=3)
     assert env.action_space.n == 4 + 8 and env.get_num_tiles() == 8 and env.get_border_tile() == 1
     assert env.observation_space["map"].shape == (7, 11) and set(env.observation_space.spaces) == {"pos", "map", "heatmap"}

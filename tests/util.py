@@ -37,7 +37,7 @@ def randomstate_words(seed):
 
 def golden_actions(meta, traj, adim):
     a = traj["actions"]
-    return a[:, :adim] if adim == 3 else a[:, 0]
+    return a[:, :adim] if adim > 1 else a[:, 0]
 
 
 def stats_groups(prob_name):

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpcgrl_b200.so")
 
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
-           "pcgrl_host_staging_bytes"]
+           "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map"]
 
 _lib = None
 
@@ -52,6 +52,12 @@ def lib():
         L.pcgrl_seed.argtypes = [C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
         L.pcgrl_step_host.restype = C.c_int
         L.pcgrl_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_obs_image.restype = C.c_int
+        L.pcgrl_obs_image.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.pcgrl_action_map.restype = C.c_int
+        L.pcgrl_action_map.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p]
         L.pcgrl_host_staging_bytes.restype = C.c_size_t
         L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:

@@ -14,6 +14,7 @@
 
 #include "pcgrl_env.cuh"
 #include "pcgrl_solver.cuh"
+#include "pcgrl_wrappers.cuh"
 
 using namespace pcgrl;
 
@@ -592,4 +593,38 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
   if (delta && rc == 0) { io->synced = 1; io->reset_base = 0; }
   return rc;
+}
+
+extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, const uint8_t* pos, void* out, int n,
+                               int crop_size, int pad_value, int one_hot, int out_dtype, void* stream) {
+  if (!cfg || !maps || !out) return fail(-1, "NULL argument");
+  if (n <= 0) return fail(-1, "n must be > 0");
+  if (crop_size < 0 || crop_size > 64) return fail(-1, "crop_size must be in [0, 64]");
+  if (crop_size > 0 && !pos) return fail(-1, "Cropped needs the cursor positions");
+  if (out_dtype != 0 && out_dtype != 1) return fail(-1, "out_dtype must be 0 (uint8) or 1 (float32)");
+  int rc = pcgrl_config_validate(cfg);
+  if (rc) return rc;
+  const int S_h = crop_size ? crop_size : cfg->height, S_w = crop_size ? crop_size : cfg->width;
+  const int channels = one_hot ? cfg->num_tiles : 1;
+  const size_t pixels = (size_t)n * S_h * S_w;
+  const unsigned blocks = (unsigned)((pixels + 255) / 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == 0)
+    k_obs_image<uint8_t><<<blocks, 256, 0, s>>>(maps, pos, (uint8_t*)out, n, cfg->height, cfg->width, S_h, S_w, crop_size, pad_value, channels);
+  else
+    k_obs_image<float><<<blocks, 256, 0, s>>>(maps, pos, (float*)out, n, cfg->height, cfg->width, S_h, S_w, crop_size, pad_value, channels);
+  return cuda_rc(cudaGetLastError(), "pcgrl_obs_image launch");
+}
+
+extern "C" int pcgrl_action_map(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* flat_actions,
+                                int32_t* actions_out, int n, void* stream) {
+  if (!cfg || !b || !flat_actions || !actions_out) return fail(-1, "NULL argument");
+  if (n <= 0) return fail(-1, "n must be > 0");
+  int rc = pcgrl_config_validate(cfg);
+  if (rc) return rc;
+  if (cfg->representation != PCGRL_REP_WIDE && cfg->representation != PCGRL_REP_NARROW && cfg->representation != PCGRL_REP_TURTLE)
+    return fail(-1, "ActionMap supports the narrow, turtle and wide representations");
+  k_action_map<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat_actions, b->map, b->pos, actions_out, n, cfg->height,
+                                                              cfg->width, cfg->num_tiles, cfg->representation == PCGRL_REP_WIDE);
+  return cuda_rc(cudaGetLastError(), "pcgrl_action_map launch");
 }

@@ -183,6 +183,21 @@ size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n);
 int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions,
                     pcgrl_host_io* io, int n, void* stream);
 
+/*
+ * Batched observation / action wrappers (reference: gym_pcgrl/wrappers.py -- "next" row f1 of the scope table).
+ *
+ * pcgrl_obs_image: Cropped (:163-206) + OneHotEncoding (:67-104) + ToImage (:18-60) in one pass.
+ *   maps [n][H][W] u8, pos [n][2] (needed when crop_size > 0) -> out [n][S][S][C], S = crop_size (or H x W when
+ *   crop_size == 0), C = num_tiles when one_hot else 1.  pad_value = border tile (Cropped pads with it).
+ *   out_dtype: 0 = uint8, 1 = float32 (values are 0/1 or small tile indices: equal in any dtype).
+ * pcgrl_action_map: ActionMap.step (:139-154): flat [n] indices over (H, W, num_tiles) -> actions_out in the
+ *   layout the wrapped representation expects ([n][3] for wide, [n] for narrow / turtle).
+ */
+int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, const uint8_t* pos, void* out, int n,
+                    int crop_size, int pad_value, int one_hot, int out_dtype, void* stream);
+int pcgrl_action_map(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* flat_actions,
+                     int32_t* actions_out, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

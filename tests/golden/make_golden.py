@@ -313,6 +313,63 @@ def run_rng():
     np.savez_compressed(os.path.join(HERE, "rng.npz"), **out)
 
 
+# ----------------------------------------------------------------------------- wrappers (gym_pcgrl/wrappers.py)
+WRAPPER_CONFIGS = [
+    # (name, kind, env id, crop size, kwargs)
+    ("cropped_binary_narrow", "cropped", "binary-narrow-v0", 28, {}),
+    ("cropped_zelda_narrow", "cropped", "zelda-narrow-v0", 22, {}),
+    ("cropped_sokoban_turtle", "cropped", "sokoban-turtle-v0", 10, {}),
+    ("cropped_ddave_turtle_odd", "cropped", "ddave-turtle-v0", 7, {}),
+    ("actionmap_binary_wide", "actionmap", "binary-wide-v0", 0, {}),
+    ("actionmap_zelda_wide", "actionmap", "zelda-wide-v0", 0, {}),
+    ("actionmap_sokoban_narrow", "actionmap_pos", "sokoban-narrow-v0", 0, {}),
+    ("actionmap_mdungeon_turtle", "actionmap_pos", "mdungeon-turtle-v0", 0, {}),
+]
+
+
+def run_wrapper(args):
+    name, kind, env_id, crop, kwargs, seed, steps = args
+    ref_shim.install()
+    from gym_pcgrl import wrappers as W
+    import gym
+    if kind == "cropped":
+        env = W.CroppedImagePCGRLWrapper(env_id, crop, **kwargs)
+        pcgrl = env.pcgrl_env
+    elif kind == "actionmap":
+        env = W.ActionMapImagePCGRLWrapper(env_id, **kwargs)
+        pcgrl = env.pcgrl_env
+    else:  # ActionMap over a cursor representation.  It has to sit OUTSIDE OneHotEncoding here: the one-hot
+        # transform mutates the observation dict that an inner ActionMap keeps as old_obs (wrappers.py:101-104,137)
+        pcgrl = gym.make(env_id)
+        e = W.OneHotEncoding(pcgrl, 'map')
+        e = W.ActionMap(e)
+        env = W.ToImage(e, ['map'])
+    pcgrl._rep._random = np.random.RandomState(seed)
+    pcgrl._prob._random = np.random.RandomState(seed)
+    arng = np.random.RandomState(seed + 1)
+    obs = env.reset()
+    obs0 = [np.asarray(obs).astype(np.uint8)]
+    space = env.action_space
+    acts, imgs, rews, dones, resets = [], [], [], [], []
+    for t in range(steps):
+        a = sample_action(space, arng)
+        obs, r, d, info = env.step(a)
+        acts.append(np.atleast_1d(a))
+        imgs.append(np.asarray(obs).astype(np.uint8))
+        rews.append(float(r))
+        dones.append(bool(d))
+        if d:
+            obs = env.reset()
+            resets.append(t)
+            obs0.append(np.asarray(obs).astype(np.uint8))
+    np.savez_compressed(os.path.join(HERE, "wrap_%s.npz" % name), actions=np.asarray(acts, np.int32), obs=np.stack(imgs),
+                        reward=np.asarray(rews), done=np.asarray(dones, np.uint8), reset_obs=np.stack(obs0),
+                        reset_step=np.asarray(resets, np.int32),
+                        meta=json.dumps(dict(name=name, kind=kind, env_id=env_id, crop=crop, kwargs=kwargs, seed=seed, steps=steps,
+                                             obs_shape=list(imgs[0].shape), obs_dtype=str(np.asarray(obs).dtype))))
+    return name, imgs[0].shape, str(np.asarray(obs).dtype), int(np.sum(dones))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -332,6 +389,9 @@ def main():
                 m["ref_steps_per_s"]), flush=True)
     if a.only in ("", "stats"):
         run_stats(pool, a.jobs)
+    if a.only in ("", "wrappers"):
+        for r in pool.map(run_wrapper, [(n, k, i, c, kw, 0, 300) for (n, k, i, c, kw) in WRAPPER_CONFIGS], chunksize=1):
+            print("wrapper", r, flush=True)
 
 
 if __name__ == "__main__":

@@ -49,8 +49,8 @@ class Box(_Space):
             shape = np.asarray(low).shape
         self.shape = tuple(shape)
         self.dtype = np.dtype(dtype)
-        self.low = np.broadcast_to(np.asarray(low), self.shape).astype(np.float64)
-        self.high = np.broadcast_to(np.asarray(high), self.shape).astype(np.float64)
+        self.low = np.broadcast_to(np.asarray(low), self.shape).astype(self.dtype)   # gym keeps the Box dtype
+        self.high = np.broadcast_to(np.asarray(high), self.shape).astype(self.dtype)
 
 
 class Dict(_Space):
@@ -146,13 +146,25 @@ def install():
     return gym_pcgrl
 
 
+class PyInt(int):
+    """int whose != / == against numpy scalars give Python bools (so ``[0, 1][tile != action]`` indexes)."""
+
+    def __ne__(self, other):
+        return bool(int(self) != int(other))
+
+    def __eq__(self, other):
+        return bool(int(self) == int(other))
+
+    __hash__ = int.__hash__
+
+
 class PyScalarMap(np.ndarray):
     """ndarray view whose scalar reads are Python ints (numpy-2 workaround)."""
 
     def __getitem__(self, idx):
         r = np.ndarray.__getitem__(self, idx)
         if isinstance(r, np.generic):
-            return int(r)
+            return PyInt(r)
         return r
 
 

@@ -606,13 +606,18 @@ extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, con
   if (rc) return rc;
   const int S_h = crop_size ? crop_size : cfg->height, S_w = crop_size ? crop_size : cfg->width;
   const int channels = one_hot ? cfg->num_tiles : 1;
-  const size_t pixels = (size_t)n * S_h * S_w;
-  const unsigned blocks = (unsigned)((pixels + 255) / 256);
+  const size_t total = (size_t)n * S_h * S_w * channels;
+  if (total >= (1ull << 32)) return fail(-1, "observation tensor too large (>= 2^32 elements): split the batch");
   cudaStream_t s = (cudaStream_t)stream;
-  if (out_dtype == 0)
-    k_obs_image<uint8_t><<<blocks, 256, 0, s>>>(maps, pos, (uint8_t*)out, n, cfg->height, cfg->width, S_h, S_w, crop_size, pad_value, channels);
-  else
-    k_obs_image<float><<<blocks, 256, 0, s>>>(maps, pos, (float*)out, n, cfg->height, cfg->width, S_h, S_w, crop_size, pad_value, channels);
+  if (out_dtype == 0) {
+    const unsigned blocks = (unsigned)((total + OBS_THREADS * 64 - 1) / (OBS_THREADS * 64));
+    k_obs_image<uint8_t><<<blocks, OBS_THREADS, 0, s>>>(maps, pos, (uint8_t*)out, (uint32_t)total, n, cfg->height, cfg->width,
+                                                        S_h, S_w, crop_size, pad_value, channels);
+  } else {
+    const unsigned blocks = (unsigned)((total + OBS_THREADS * 16 - 1) / (OBS_THREADS * 16));
+    k_obs_image<float><<<blocks, OBS_THREADS, 0, s>>>(maps, pos, (float*)out, (uint32_t)total, n, cfg->height, cfg->width,
+                                                      S_h, S_w, crop_size, pad_value, channels);
+  }
   return cuda_rc(cudaGetLastError(), "pcgrl_obs_image launch");
 }
 

@@ -11,27 +11,78 @@
 namespace pcgrl {
 
 // out[n][i][j][c]; crop: padded = np.pad(map, pad, constant_values=pad_value); cropped = padded[y:y+S, x:x+S]
+//
+// HBM-write bound, so the kernel is organised around the output stream: every thread produces 64 contiguous
+// output bytes (decoding its start (env, i, j, channel) once and then stepping channel -> column -> row -> env
+// incrementally), parks them in shared memory, and the CTA then streams its 16 KB tile out with fully coalesced
+// 16-byte stores (a warp store covers 512 contiguous bytes).  The uint8 map batch is read through L1/L2.
+#define OBS_THREADS 256
 template <typename OutT>
-__global__ void __launch_bounds__(256) k_obs_image(const uint8_t* __restrict__ maps, const uint8_t* __restrict__ pos,
-                                                   OutT* __restrict__ out, int n, int H, int W, int S_h, int S_w,
-                                                   int crop, int pad_value, int channels) {
-  const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t per_env = (size_t)S_h * S_w;
-  if (pix >= (size_t)n * per_env) return;
-  const int e = (int)(pix / per_env), rem = (int)(pix % per_env), i = rem / S_w, j = rem % S_w;
-  int t;
-  if (crop) {
+__global__ void __launch_bounds__(OBS_THREADS) k_obs_image(const uint8_t* __restrict__ maps,
+                                                           const uint8_t* __restrict__ pos, OutT* __restrict__ out,
+                                                           uint32_t total, int n, int H, int W, int S_h, int S_w,
+                                                           int crop, int pad_value, int C) {
+  constexpr int EPT = 64 / (int)sizeof(OutT);  // elements per thread
+  __shared__ uint4 tile_s[OBS_THREADS * 4];
+  const int tid = threadIdx.x;
+  const uint32_t block_elem0 = blockIdx.x * (uint32_t)(OBS_THREADS * EPT);
+  const uint32_t k0 = block_elem0 + (uint32_t)tid * EPT;
+  union { OutT v[EPT]; uint4 q[4]; } u;
+#pragma unroll
+  for (int r = 0; r < 4; r++) u.q[r] = make_uint4(0u, 0u, 0u, 0u);
+  if (k0 < total) {
+    const uint32_t per_env = (uint32_t)S_h * S_w;
+    uint32_t p = k0 / (uint32_t)C;
+    int c = (int)(k0 - p * (uint32_t)C);
+    int e = (int)(p / per_env);
+    const uint32_t rem = p - (uint32_t)e * per_env;
+    int i = (int)(rem / (uint32_t)S_w), j = (int)(rem - (uint32_t)i * S_w);
     const int pad = crop / 2;
-    const int my = (int)pos[2 * e + 1] + i - pad, mx = (int)pos[2 * e] + j - pad;
-    t = (my >= 0 && my < H && mx >= 0 && mx < W) ? (int)maps[((size_t)e * H + my) * W + mx] : pad_value;
-  } else {
-    t = (int)maps[((size_t)e * H + i) * W + j];
+    int oy = 0, ox = 0;
+    if (crop) { ox = (int)pos[2 * e] - pad; oy = (int)pos[2 * e + 1] - pad; }
+    const uint8_t* m = maps + (size_t)e * H * W;
+    auto fetch = [&]() -> int {
+      const int my = oy + i, mx = ox + j;
+      return (my >= 0 && my < H && mx >= 0 && mx < W) ? (int)m[my * W + mx] : pad_value;
+    };
+    int t = fetch();
+#pragma unroll
+    for (int q = 0; q < EPT; q++) {
+      u.v[q] = (C == 1) ? (OutT)t : (OutT)(c == t ? 1 : 0);  // np.eye(dim)[map]
+      if (++c == C) {
+        c = 0;
+        if (++j == S_w) {
+          j = 0;
+          if (++i == S_h) {
+            i = 0;
+            if (++e < n) {
+              m += (size_t)H * W;
+              if (crop) { ox = (int)pos[2 * e] - pad; oy = (int)pos[2 * e + 1] - pad; }
+            }
+          }
+        }
+        if (e < n) t = fetch();
+      }
+    }
   }
-  OutT* o = out + pix * channels;
-  if (channels == 1) {
-    o[0] = (OutT)t;
-  } else {
-    for (int c = 0; c < channels; c++) o[c] = (OutT)(c == t ? 1 : 0);  // np.eye(dim)[map]
+  // park (swizzled inside each thread's group of four to spread the banks), then stream out coalesced
+#pragma unroll
+  for (int r = 0; r < 4; r++) tile_s[tid * 4 + (r ^ (tid & 3))] = u.q[r];
+  __syncthreads();
+  const size_t total_bytes = (size_t)total * sizeof(OutT);
+  const size_t block_byte0 = (size_t)block_elem0 * sizeof(OutT);
+  uint8_t* ob = reinterpret_cast<uint8_t*>(out);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int L = r * OBS_THREADS + tid;  // linear 16-byte chunk inside the CTA tile
+    const size_t off = block_byte0 + (size_t)L * 16;
+    const uint4 val = tile_s[(L & ~3) | ((L & 3) ^ ((L >> 2) & 3))];
+    if (off + 16 <= total_bytes) {
+      *reinterpret_cast<uint4*>(ob + off) = val;
+    } else if (off < total_bytes) {  // ragged tail of the whole tensor
+      const uint8_t* vb = reinterpret_cast<const uint8_t*>(&val);
+      for (int b = 0; off + b < total_bytes; b++) ob[off + b] = vb[b];
+    }
   }
 }
 

@@ -65,6 +65,48 @@ def test_get_stats_matches_reference_golden(prob_name):
             prob_name, maps.shape, bad[0], rows[bad[0]], stats[bad[0]], maps[bad[0]])
 
 
+RANDOM_SIZE_CASES = [("binary", 32, 40), ("zelda", 32, 40), ("sokoban", 10, 12), ("ddave", 11, 10), ("mdungeon", 11, 10)]
+
+
+@pytest.mark.parametrize("case", RANDOM_SIZE_CASES, ids=[c[0] for c in RANDOM_SIZE_CASES])
+def test_get_stats_random_sizes_match_oracle(case):
+    """Problem.get_stats on random maps of random (ragged) sizes, including 1-wide / 1-high and the 32-lane maximum:
+    the bitboard transposition, row masks and BFS borders must hold for every width and height."""
+    import torch
+    from gym_pcgrl_b200._config import build_config
+    from gym_pcgrl_b200 import REPRESENTATIONS
+    prob_name, max_dim, nsizes = case
+    rng = np.random.RandomState(17)
+    sizes = [(1, 1), (1, max_dim), (max_dim, 1), (max_dim, max_dim), (2, 3), (max_dim - 1, max_dim)]
+    while len(sizes) < nsizes:
+        sizes.append((int(rng.randint(1, max_dim + 1)), int(rng.randint(1, max_dim + 1))))
+    for (w, h) in sizes:
+        if prob_name in ("sokoban", "ddave", "mdungeon") and w * h > 128:
+            continue
+        prob = PROBLEMS[prob_name]()
+        prob.adjust_param(width=w, height=h)
+        T = len(prob.tile_types)
+        maps = []
+        for k in range(48):
+            dens = rng.random_sample()
+            if prob_name == "binary":
+                m = (rng.random_sample((h, w)) < dens).astype(np.uint8)
+            else:
+                p = np.full(T, (1 - dens) * 0.4 / (T - 2)); p[0] = dens; p[1] = (1 - dens) * 0.6
+                m = rng.choice(T, size=(h, w), p=p / p.sum()).astype(np.uint8)
+                if w * h >= 3 and k % 2 == 0:      # make the BFS / solver preconditions likely
+                    flat = m.reshape(-1)
+                    flat[flat == 2] = 0
+                    flat[rng.randint(flat.size)] = 2
+            maps.append(m)
+        maps = np.stack(maps)
+        cfg = build_config(prob, REPRESENTATIONS["wide"](), 1, 1, auto_reset=False)
+        want = oracle.get_stats(cfg, maps, threads=8)
+        got = t2n(_native.get_stats(prob, torch.from_numpy(maps).cuda()))
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, "%s %dx%d: map %d cuda %s oracle %s\n%s" % (prob_name, w, h, bad[0], got[bad[0]], want[bad[0]], maps[bad[0]])
+
+
 @pytest.mark.parametrize("meta", KATS, ids=[m["name"] for m in KATS])
 def test_trajectory_matches_reference_golden(meta):
     """Single env through the classic-gym facade, manual reset on done: the reference's own trajectory."""

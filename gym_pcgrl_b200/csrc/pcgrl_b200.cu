@@ -84,7 +84,11 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       if (reward_out) reward_out[(size_t)t * n + e] = reward;
       if (done_out) done_out[(size_t)t * n + e] = done ? 1 : 0;
     }
-    if (t == T - 1) store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+    if (t == T - 1) {
+      store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+      if (PROB == PCGRL_PROB_BINARY && lane == NS)  // info["path-imp"] (binary_prob.py:137), before any auto-reset
+        b.info_stats[(size_t)e * PCGRL_MAX_STATS + NS] = st[1] - start[1];
+    }
     if (done && auto_reset) {
       bool unused;
       env_reset<PROB>(cfg, b, e, lane, sm, rng, board, x, y, st, unused);
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(32 * WPB) k_reset(const __grid_constant__ pcgr
   store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  if (PROB == PCGRL_PROB_BINARY && lane == NS) b.info_stats[(size_t)e * PCGRL_MAX_STATS + NS] = 0;
   if constexpr (ProblemTraits<PROB>::SOLVER) if (need_solver) solver_enqueue(q, e, SOLVE_FOR_RESET, lane);
 }
 

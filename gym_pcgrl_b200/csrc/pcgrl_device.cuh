@@ -105,8 +105,7 @@ struct WarpRng {
   __device__ __forceinline__ int randint(int n, int lane) {
     const uint32_t rng = (uint32_t)(n - 1);
     if (rng == 0) return 0;
-    uint32_t mask = rng;
-    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    const uint32_t mask = 0xffffffffu >> __clz(rng);  // smallest 2^k - 1 >= rng
     uint32_t v;
     do { v = next(lane) & mask; } while (v > rng);
     return (int)v;

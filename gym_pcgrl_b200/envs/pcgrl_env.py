@@ -120,31 +120,38 @@ class BatchedPcgrlEnv:
         m = None
         if mask is not None:
             m = torch.as_tensor(mask, device=self._dev).to(torch.uint8).contiguous()
+        self.native_config
         with torch.cuda.device(self._dev):
-            _native.check(_native.lib().pcgrl_reset(C.byref(self._cfg), C.byref(self._cbufs),
+            _native.check(_native.lib().pcgrl_reset(self._cfg_ref, C.byref(self._cbufs),
                                                     None if m is None else m.data_ptr(), self.num_envs,
                                                     _native.stream_ptr(self._dev)), "pcgrl_reset")
         self._prob.reset(self._prob.stats_from_rows(self._tens["start_stats"]))
-        return self._observation()
+        self._info_cache["max_iterations"], self._info_cache["max_changes"] = self._max_iterations, self._max_changes
+        return self._obs_cache
 
     def step(self, actions):
-        """PcgrlEnv.step for the whole batch.  actions: int tensor/array [N] (narrow, turtle) or
-        [N,3] = (x, y, tile) (wide).  Returns (obs, reward f64[N], done bool[N], info).
-        pcgrl_env.py:129-150."""
+        """PcgrlEnv.step for the whole batch.  actions: int32 tensor/array [N] (narrow, turtle), [N,3] = (x, y, tile)
+        (wide), [N,2] / [N,9] (cast / multi).  Returns (obs, reward f64[N], done bool[N], info) -- all live views
+        of the env's buffers (the dicts are built once, not per call).  pcgrl_env.py:129-150."""
         import torch
         if self._tens is None:
             raise RuntimeError("call reset() before step()")
-        self.native_config  # re-freeze the parameters if adjust_param was called since the last step
-        a = torch.as_tensor(actions)
-        if a.device != self._dev or a.dtype != torch.int32 or not a.is_contiguous():
-            a = a.to(device=self._dev, dtype=torch.int32).contiguous()
-        assert a.numel() == self.num_envs * self._adim, "actions must have shape [%d%s]" % (
-            self.num_envs, ",%d" % self._adim if self._adim > 1 else "")
-        with torch.cuda.device(self._dev):
-            _native.check(_native.lib().pcgrl_step(C.byref(self._cfg), C.byref(self._cbufs), a.data_ptr(),
-                                                   self.num_envs, _native.stream_ptr(self._dev)), "pcgrl_step")
-        t = self._tens
-        return self._observation(), t["reward"], t["done"].view(torch.bool), self._info()
+        if self._cfg is None:
+            self.native_config  # re-freeze the parameters if adjust_param was called since the last step
+        dev = self._dev
+        a = actions
+        if not (isinstance(a, torch.Tensor) and a.dtype == torch.int32 and a.device == dev and a.is_contiguous()):
+            a = torch.as_tensor(actions).to(device=dev, dtype=torch.int32).contiguous()
+        if a.numel() != self.num_envs * self._adim:
+            raise ValueError("actions must have shape [%d%s]" % (self.num_envs, ",%d" % self._adim if self._adim > 1 else ""))
+        if torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return self.step(a)
+        rc = self._fn_step(self._cfg_ref, self._bufs_ref, a.data_ptr(), self.num_envs,
+                           torch.cuda.current_stream(dev).cuda_stream)
+        if rc:
+            _native.check(rc, "pcgrl_step")
+        return self._obs_cache, self._reward_view, self._done_view, self._info_cache
 
     def rollout(self, actions, reward_out=None, done_out=None):
         """T steps in one native call: actions int32 CUDA [T,N] / [T,N,3].  Returns (reward [T,N],
@@ -235,6 +242,11 @@ class BatchedPcgrlEnv:
             self._d_actions = torch.zeros(self.num_envs * self._adim, dtype=torch.int32, device=self._dev)
         self._bufs = self._tens
         self._fn_step_host = _native.lib().pcgrl_step_host
+        self._fn_step = _native.lib().pcgrl_step
+        self._obs_cache = self._build_observation()
+        self._info_cache = self._build_info()
+        self._reward_view = self._tens["reward"]
+        self._done_view = self._tens["done"].view(torch.bool)
         self._bufs_ref = C.byref(self._cbufs)
         self._d_actions_ptr = self._d_actions.data_ptr()
         self._rep.bind(self)
@@ -243,15 +255,23 @@ class BatchedPcgrlEnv:
             self._pending_states = None
 
     def _observation(self):
+        return self._obs_cache
+
+    def _build_observation(self):
         t = self._tens
         obs = {"map": t["map"], "heatmap": t["heatmap"]}
         if self._rep.name != "wide":
             obs["pos"] = t["pos"]
         return obs
 
-    def _info(self):
+    def _build_info(self):
+        """Problem.get_debug_info + the env counters (pcgrl_env.py:144-148) as views of ``info_stats`` (the
+        statistics at the end of the step, written by the kernel BEFORE any auto-reset)."""
         t = self._tens
-        info = self._prob.get_debug_info(self._prob.stats_from_rows(t["info_stats"]), None)
+        rows = t["info_stats"]
+        info = {k: rows[:, i] for i, k in enumerate(self._prob.stat_names) if k in self._prob.debug_info_names}
+        for j, k in enumerate(self._prob.extra_info_names):   # derived entries the kernel appends after the stats
+            info[k] = rows[:, len(self._prob.stat_names) + j]
         info["iterations"] = t["iteration"]
         info["changes"] = t["changes"]
         info["max_iterations"] = self._max_iterations

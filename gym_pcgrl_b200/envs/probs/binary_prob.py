@@ -7,6 +7,7 @@ class BinaryProblem(Problem):
     name = "binary"
     tile_types = ("empty", "solid")
     stat_names = ("regions", "path-length")
+    extra_info_names = ("path-imp",)   # binary_prob.py:137: path-length - start path-length, info_stats column 2
 
     def __init__(self):
         super().__init__()

@@ -52,6 +52,10 @@ class DDaveProblem(Problem):
         return (new_stats["sol-length"] >= self._target_solution) & \
             (new_stats["num-jumps"] > self._target_jumps)
 
+    @property
+    def debug_info_names(self):
+        return tuple(k for k in self.stat_names if k != "dist-floor")
+
     def get_debug_info(self, new_stats, old_stats):  # ddave_prob.py:233-245 (no dist-floor)
         return {k: new_stats[k] for k in ("player", "exit", "diamonds", "key", "spikes", "regions",
                                           "col-diamonds", "num-jumps", "dist-win", "sol-length")}

@@ -48,6 +48,12 @@ class Problem:
     name = None            # key in PROBLEMS
     tile_types = ()        # get_tile_types()
     stat_names = ()        # == _abi.STAT_NAMES[name]
+    extra_info_names = ()  # info entries derived in the kernel and appended to info_stats after the stats columns
+
+    @property
+    def debug_info_names(self):
+        """Keys of Problem.get_debug_info that are plain statistics (default: all of them)."""
+        return self.stat_names
 
     def __init__(self):
         # problem.py:11-22 defaults

@@ -879,6 +879,8 @@ static int env_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32
              b->iteration[i] >= cfg->max_iterations;
   b->done[i] = (uint8_t)done;
   memcpy(b->info_stats + (size_t)i * S, stats, sizeof(int32_t) * S);
+  if (cfg->problem == PCGRL_PROB_BINARY) /* binary_prob.py:137 "path-imp" */
+    b->info_stats[(size_t)i * S + 2] = stats[1] - b->start_stats[(size_t)i * S + 1];
   if (done && (cfg->flags & PCGRL_FLAG_AUTO_RESET)) return env_reset(cfg, b, i);
   return 0;
 }

@@ -138,6 +138,9 @@ def test_trajectory_matches_reference_golden(meta):
         assert abs(float(r) - traj["reward"][t]) <= REWARD_TOL and float(r) == traj["reward"][t], ctx
         assert d == bool(traj["done"][t]), ctx
         assert info["iterations"] == traj["iteration"][t] and info["changes"] == traj["changes"][t], ctx
+        if prob == "binary":   # binary_prob.py:133-138 debug info
+            assert info["path-imp"] == traj["stats"][t][1] - traj["reset_stats"][k][1], ctx
+            assert info["regions"] == traj["stats"][t][0] and info["path-length"] == traj["stats"][t][1], ctx
         total += float(r)
         if d:
             obs = env.reset()
@@ -212,7 +215,8 @@ def test_batched_rollout_matches_oracle(case):
         assert_state_equal(env, ref, S, ctx, wide)
         np.testing.assert_array_equal(t2n(reward), ref["reward"], err_msg=ctx + " reward")
         np.testing.assert_array_equal(t2n(done).astype(np.uint8), ref["done"], err_msg=ctx + " done")
-        np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, :S], ref["info_stats"][:, :S], err_msg=ctx + " info")
+        Si = S + (1 if prob == "binary" else 0)   # binary appends path-imp
+        np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, :Si], ref["info_stats"][:, :Si], err_msg=ctx + " info")
         ndone += int(ref["done"].sum())
     np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"], err_msg="rng state")
     np.testing.assert_array_equal(t2n(env._tens["tile_prob"]), ref["tile_prob"], err_msg="tile_prob")

@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // In-place twist by one warp.  Batches of 32 consecutive indices: new[i] depends on old[i], old[i+1] and
 // (i < 227 ? old[i+397] : new[i-227]); the dependency distance (227) exceeds the batch width, and every
 // lane reads its inputs before any lane of the batch writes, so the result equals the sequential loop.
-__device__ __noinline__ void mt_twist_warp(uint32_t* k, int lane) {
+__device__ __forceinline__ void mt_twist_warp(uint32_t* k, int lane) {
   __syncwarp();
   for (int base = 0; base < 624; base += 32) {
     const int i = base + lane;

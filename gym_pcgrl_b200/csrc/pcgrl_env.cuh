@@ -164,19 +164,27 @@ __device__ __forceinline__ void warp_fill_bytes(uint8_t* dst, int nbytes, uint8_
 // PcgrlEnv.reset for one env, up to (and including) the map part of get_stats.  The caller finishes
 // Problem.reset (start_stats) -- after the solver for the solver problems.
 template <int PROB>
-__device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buffers& b, int e, int lane, WarpSmem& sm,
+__device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buffers& b, int e, int lane, WarpSmem& sm,
                                        WarpRng& rng, Board& board, int& x, int& y, int* st, bool& need_solver) {
   constexpr int NP = ProblemTraits<PROB>::NPLANES;
   const int W = cfg.width, H = cfg.height, cells = W * H, T = cfg.num_tiles;
   const EnvRefs r = env_refs(cfg, b, e);
   const bool generate = (cfg.flags & PCGRL_FLAG_RANDOM_START) || (b.start_valid[e] == 0);
   __syncwarp();
+#ifdef PCGRL_PROFILE
+  long long tp[8]; int ntp = 0;
+#define TP() do { __syncwarp(); tp[ntp++] = clock64(); } while (0)
+#else
+#define TP() do {} while (0)
+#endif
+  TP();
   uint32_t* rng_home = nullptr;
   WarpRng pr;  // problem stream (binary_prob.py:68-72): start its two dependent loads now, consume at the end
   const bool redraw_probs = (PROB == PCGRL_PROB_BINARY) && (cfg.flags & PCGRL_FLAG_RANDOM_PROBS);
   if (redraw_probs) pr.init(r.rng_prob, lane);
   if (generate) {  // representation.py:41-43 -> helper.py:310-312 gen_random_map
     rng_home = rng.stage(sm.mt, lane);  // the reset consumes 2*H*W (+2) draws and usually crosses a twist
+    TP();
     // helper.py:343-352 get_int_prob, then RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]
     double cdf[PCGRL_MAX_TILES];
     double total = 0.0, acc = 0.0;
@@ -187,8 +195,20 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
       if (t < T) { acc += r.tile_prob[t] / total; cdf[t] = acc; }
       else cdf[t] = __longlong_as_double(0x7ff0000000000000LL);
     }
+    // searchsorted(cdf, u, side='right') == #{t : cdf[t] <= u}.  u = k * 2^-53 with the 53-bit integer
+    // k = (a << 26) | b, and cdf[t] * 2^53 is exact, so cdf[t] <= u  <=>  ceil(cdf[t] * 2^53) <= k: the per-cell
+    // comparisons are done on integers, bit-identical to numpy's double comparison.
+    unsigned long long thr[PCGRL_MAX_TILES];
 #pragma unroll
-    for (int t = 0; t < PCGRL_MAX_TILES; t++) if (t < T) cdf[t] /= acc;
+    for (int t = 0; t < PCGRL_MAX_TILES; t++) {
+      if (t < T) {
+        cdf[t] /= acc;
+        const double scaled = ceil(cdf[t] * 9007199254740992.0);
+        thr[t] = (scaled >= 18446744073709551615.0) ? 0xffffffffffffffffull : (unsigned long long)scaled;
+      } else {
+        thr[t] = 0xffffffffffffffffull;
+      }
+    }
     const int nchunks = (cells + 31) >> 5;
     for (int s0 = 0; s0 < cells; s0 += 256) {  // segments of 256 cells: 512 draws staged at once, 8 cells per lane
       const int nseg = min(256, cells - s0);
@@ -198,10 +218,10 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
         const int j = k * 32 + lane;  // cell inside the segment
         uint32_t tile = 0;
         if (j < nseg) {
-          const uint32_t a = sm.draws[2 * j] >> 5, bb = sm.draws[2 * j + 1] >> 6;
-          const double u = ((double)a * 67108864.0 + (double)bb) * (1.0 / 9007199254740992.0);  // exact scaling by 2^-53
+          const uint32_t a = sm.draws[2 * j] >> 5, bb = sm.draws[2 * j + 1] >> 6;  // random_sample(): (a*2^26 + b) / 2^53
+          const unsigned long long k53 = ((unsigned long long)a << 26) | (unsigned long long)bb;
 #pragma unroll
-          for (int t = 0; t < PCGRL_MAX_TILES; t++) tile += (cdf[t] <= u) ? 1u : 0u;  // searchsorted(side='right')
+          for (int t = 0; t < PCGRL_MAX_TILES; t++) tile += (thr[t] <= k53) ? 1u : 0u;  // searchsorted(side='right')
           r.map[s0 + j] = (uint8_t)tile;
           r.start_map[s0 + j] = (uint8_t)tile;  // _old_map = _map.copy()
         }
@@ -211,6 +231,7 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
     }
     board = bits_to_board<NP>(sm.bits, nchunks, W, H, lane);
     if (lane == 0) b.start_valid[e] = 1;
+    TP();
   } else {  // representation.py:44-45
     for (int i = lane; i < cells; i += 32) r.map[i] = r.start_map[i];
     board = load_board<NP>(r.start_map, W, H, lane, sm.bits);
@@ -220,7 +241,9 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
     y = rng.randint(H, lane);
   }
   if (rng_home) rng.unstage(rng_home, lane);
+  TP();
   map_stats<PROB>(board, cfg, lane, st, need_solver);
+  TP();
   if (redraw_probs) {  // binary_prob.py:68-72 (problem stream)
     const double p_empty = pr.next_double(lane);
     pr.finish(lane);
@@ -228,6 +251,14 @@ __device__ __noinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_buff
   }
   warp_fill_bytes(r.heat, cells, 0, lane);  // pcgrl_env.py:72
   __syncwarp();
+  TP();
+#ifdef PCGRL_PROFILE
+  if (lane == 0 && b.status) {  // accumulate phase cycles: status[8 + k]
+    long long* acc = reinterpret_cast<long long*>(b.status) + 4;
+    for (int k = 1; k < ntp; k++) atomicAdd(reinterpret_cast<unsigned long long*>(acc + k), (unsigned long long)(tp[k] - tp[k - 1]));
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc), 1ull);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

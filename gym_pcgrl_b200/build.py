@@ -14,7 +14,7 @@ LIB = os.path.join(CSRC, "libpcgrl_b200.so")
 SOURCES = ["pcgrl_b200.cu"]
 HEADERS = ["pcgrl_device.cuh", "pcgrl_problems.cuh", "pcgrl_env.cuh", "pcgrl_solver.cuh", "pcgrl_wrappers.cuh"]
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 def _stale():

@@ -12,6 +12,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <thread>
+#include <vector>
+
 #include "pcgrl_env.cuh"
 #include "pcgrl_solver.cuh"
 #include "pcgrl_wrappers.cuh"
@@ -438,24 +441,36 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
     return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
   }
   GroupStreams* gs = group_streams();
+  solver_prepare<PROB>(cfg);
   cudaEventRecord(gs->fork, s);
   for (int g = 0; g < plan.groups; g++) cudaStreamWaitEvent(gs->streams[g], gs->fork, 0);
-  for (int t = 0; t < T; t++) {  // round-robin over groups keeps every stream fed while the host is still enqueueing
-    for (int g = 0; g < plan.groups; g++) {
+  // the enqueue itself (groups x T x 5 launches) is spread over a few host threads, one set of groups each
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int nthreads = plan.groups < 8 ? plan.groups : 8;
+  std::vector<int> rcs(nthreads, 0);
+  auto enqueue = [&](int tid) {
+    cudaSetDevice(dev);
+    for (int g = tid; g < plan.groups; g += nthreads) {
       const int off = g * plan.envs_per_group, m = (off + plan.envs_per_group <= n) ? plan.envs_per_group : n - off;
       if (m <= 0) continue;
       const pcgrl_buffers bg = shard_buffers(cfg, b, off, (char*)b->scratch + (size_t)g * plan.bytes_per_group, plan.bytes_per_group);
-      cudaStream_t sgp = gs->streams[g];
-      int rc = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, sgp, Staging{nullptr, 0u, 0, m},
-                                 plan.slots_per_group, reward_out ? reward_out + (size_t)t * n + off : nullptr,
-                                 done_out ? done_out + (size_t)t * n + off : nullptr);
-      if (rc) return rc;
+      for (int t = 0; t < T && rcs[tid] == 0; t++)
+        rcs[tid] = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, gs->streams[g], Staging{nullptr, 0u, 0, m},
+                                     plan.slots_per_group, reward_out ? reward_out + (size_t)t * n + off : nullptr,
+                                     done_out ? done_out + (size_t)t * n + off : nullptr);
     }
-  }
+  };
+  std::vector<std::thread> workers;
+  for (int tid = 1; tid < nthreads; tid++) workers.emplace_back(enqueue, tid);
+  enqueue(0);
+  for (auto& w : workers) w.join();
   for (int g = 0; g < plan.groups; g++) {
     cudaEventRecord(gs->join[g], gs->streams[g]);
     cudaStreamWaitEvent(s, gs->join[g], 0);
   }
+  for (int tid = 0; tid < nthreads; tid++)
+    if (rcs[tid]) return fail(rcs[tid], "pcgrl_rollout: a group launch failed");
   return cuda_rc(cudaGetLastError(), "pcgrl_rollout");
 }
 

@@ -65,8 +65,8 @@ static inline SolverLayout solver_layout(const pcgrl_config* c, int n, int max_s
 
 // Rollouts (T > 1) of the solver problems split the batch into independent env groups, one CUDA stream each,
 // so that a slow search only stalls its own group (see rollout_solver).  Each group owns a scratch region.
-#define SOLVER_MAX_GROUPS 16
-#define SOLVER_GROUP_MIN_ENVS 64
+#define SOLVER_MAX_GROUPS 64
+#define SOLVER_GROUP_MIN_ENVS 32
 struct GroupPlan { int groups, envs_per_group, slots_per_group; size_t bytes_per_group; };
 static inline GroupPlan solver_group_plan(const pcgrl_config* c, int n) {
   GroupPlan g;
@@ -757,6 +757,22 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
   }
 }
 
+// opt in to the large dynamic shared memory of k_solve (once per power setting; call before multi-threaded enqueue)
+template <int PROB>
+static inline void solver_prepare(const pcgrl_config* cfg) {
+  if constexpr (GameOf<PROB>::GAME >= 0) {
+    int table_size = 1024;
+    while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
+    const size_t heap_words = (size_t)4 * cfg->solver_power + 8;
+    const size_t smem = (table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words) * sizeof(uint32_t);
+    static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
+    if (configured[PROB] < smem) {
+      cudaFuncSetAttribute(k_solve<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured[PROB] = smem;
+    }
+  }
+}
+
 template <int PROB>
 static inline void solver_launch(const pcgrl_config* cfg, int32_t* stats, int32_t* start_stats, const uint8_t* maps,
                                  SolverQueue q, void* scratch, int n, cudaStream_t s, int max_slots = SOLVER_MAX_SLOTS) {
@@ -767,11 +783,7 @@ static inline void solver_launch(const pcgrl_config* cfg, int32_t* stats, int32_
   while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
   const size_t heap_words = (size_t)4 * cfg->solver_power + 8;
   const size_t smem = (table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words) * sizeof(uint32_t);
-  static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
-  if (configured[PROB] < smem) {
-    cudaFuncSetAttribute(k_solve<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured[PROB] = smem;
-  }
+  solver_prepare<PROB>(cfg);
   uint32_t* pool = (uint32_t*)((char*)scratch + lay.nodes_off);
   k_solve<PROB><<<4 * lay.slots, 32, smem, s>>>(*cfg, stats, start_stats, maps, q, pool, lay.nodes_per_pass, lay.slots, table_size);
   }

@@ -447,7 +447,9 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
   // the enqueue itself (groups x T x 5 launches) is spread over a few host threads, one set of groups each
   int dev = 0;
   cudaGetDevice(&dev);
-  const int nthreads = plan.groups < 8 ? plan.groups : 8;
+  int nthreads = 1;  // PCGRL_ENQUEUE_THREADS: host threads sharing the enqueue (default 1: the device front end is the limit)
+  if (const char* env = getenv("PCGRL_ENQUEUE_THREADS")) { const int v = atoi(env); if (v >= 1 && v <= 16) nthreads = v; }
+  if (nthreads > plan.groups) nthreads = plan.groups;
   std::vector<int> rcs(nthreads, 0);
   auto enqueue = [&](int tid) {
     cudaSetDevice(dev);

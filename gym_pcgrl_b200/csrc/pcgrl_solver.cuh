@@ -17,6 +17,8 @@
 // Limits (checked by pcgrl_config_validate / reported through status[0]): width, height <= 14,
 // width*height <= 128, solver_power in [1, 8000], at most 16 crates/targets in a sokoban level.
 #pragma once
+#include <stdlib.h>
+
 #include "pcgrl_device.cuh"
 
 namespace pcgrl {
@@ -66,12 +68,18 @@ static inline SolverLayout solver_layout(const pcgrl_config* c, int n, int max_s
 // Rollouts (T > 1) of the solver problems split the batch into independent env groups, one CUDA stream each,
 // so that a slow search only stalls its own group (see rollout_solver).  Each group owns a scratch region.
 #define SOLVER_MAX_GROUPS 64
+#define SOLVER_DEFAULT_GROUPS 8
 #define SOLVER_GROUP_MIN_ENVS 32
 struct GroupPlan { int groups, envs_per_group, slots_per_group; size_t bytes_per_group; };
 static inline GroupPlan solver_group_plan(const pcgrl_config* c, int n) {
   GroupPlan g;
+  int max_groups = SOLVER_DEFAULT_GROUPS;  // tuning knob: PCGRL_SOLVER_GROUPS=1..64 (1 = plain lock-step batches)
+  if (const char* env = getenv("PCGRL_SOLVER_GROUPS")) {
+    const int v = atoi(env);
+    if (v >= 1 && v <= SOLVER_MAX_GROUPS) max_groups = v;
+  }
   g.groups = n / SOLVER_GROUP_MIN_ENVS;
-  if (g.groups > SOLVER_MAX_GROUPS) g.groups = SOLVER_MAX_GROUPS;
+  if (g.groups > max_groups) g.groups = max_groups;
   if (g.groups < 1) g.groups = 1;
   g.envs_per_group = ((n + g.groups - 1) / g.groups + 3) & ~3;  // multiple of 4: heat-map word atomics stay aligned
   g.slots_per_group = 2 * SOLVER_MAX_SLOTS / g.groups;
@@ -82,7 +90,7 @@ static inline GroupPlan solver_group_plan(const pcgrl_config* c, int n) {
 static inline size_t solver_scratch_bytes(const pcgrl_config* c, int n) {
   const GroupPlan g = solver_group_plan(c, n);
   const size_t single = solver_layout(c, n).total, grouped = (size_t)g.groups * g.bytes_per_group;
-  return single > grouped ? single : grouped;
+  return single > grouped ? single : grouped;  // evaluated with the same PCGRL_SOLVER_GROUPS the rollout will see
 }
 
 static inline int solver_validate(const pcgrl_config* c) {

@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
   const EnvRefs r = env_refs(cfg, b, e);
 
+#ifdef PCGRL_PROFILE
+  long long kp[6]; int nkp = 0;
+#define KP() do { __syncwarp(); kp[nkp++] = clock64(); } while (0)
+#else
+#define KP() do {} while (0)
+#endif
+  KP();
   // all prologue loads are independent: issue them before the ballots of load_board serialise the warp
   WarpRng rng;
   rng.init(r.rng_rep, (cfg.representation == PCGRL_REP_NARROW || cfg.representation >= PCGRL_REP_NARROWCAST) ? lane : -1);
@@ -63,6 +70,10 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
   load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
   Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
+  KP();
+#ifdef PCGRL_PROFILE
+  bool prof_reset = false, prof_changed = false;
+#endif
 
   for (int t = 0; t < T; t++) {
     const int32_t* act = actions + ((size_t)t * n + e) * adim;
@@ -73,11 +84,17 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     int hx, hy, cell, tile;
     bool multi;
     const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi);
+    KP();
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
       bool unused;
       map_stats<PROB>(board, cfg, lane, st, unused);
     }
+    KP();
+#ifdef PCGRL_PROFILE
+    prof_changed = change > 0;
+    prof_reset = false;
+#endif
     const double reward = (change > 0) ? problem_reward<PROB>(cfg, st, old) : 0.0;  // :142 (get_reward(s, s) == 0)
     const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
                       iteration >= cfg.max_iterations;                            // :143
@@ -99,6 +116,9 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
       iteration = 0;
       changes = 0;
+#ifdef PCGRL_PROFILE
+      prof_reset = true;
+#endif
       if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
     } else {
       if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
@@ -113,6 +133,16 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   }
   store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start, lane);
+#ifdef PCGRL_PROFILE
+  KP();
+  if (T == 1 && lane == 0 && nkp == 5) {  // status int64[16 + 8*cls + k]: cls 0 = no change, 1 = changed, 2 = reset
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(b.status) + 16 + 8 * (prof_reset ? 2 : prof_changed ? 1 : 0);
+    atomicAdd(acc, 1ull);
+    for (int k = 1; k < 5; k++) { atomicAdd(acc + k, (unsigned long long)(kp[k] - kp[k - 1])); }
+    atomicMax(acc + 5, (unsigned long long)(kp[4] - kp[0]));
+    atomicMax(acc + 6, (unsigned long long)(kp[3] - kp[2]));
+  }
+#endif
 }
 
 template <int PROB>

@@ -13,7 +13,7 @@ n = 4096
 env = bench.make_env(n, "cuda:0", 0)
 # status buffer needs room for the phase accumulators (4 int32 + 8 int64)
 env._ensure_buffers()
-env._tens["status"] = torch.zeros(4 + 2 * 10, dtype=torch.int32, device="cuda")
+env._tens["status"] = torch.zeros(2 * 48, dtype=torch.int32, device="cuda")
 env._cbufs.status = env._tens["status"].data_ptr()
 env.reset()
 acts = torch.from_numpy(bench.host_actions(env, 600, n, 5)).cuda()
@@ -27,3 +27,10 @@ print("resets", cnt)
 for k, nm in enumerate(names):
     print("%-18s %8.0f cycles" % (nm, acc[k + 1] / max(cnt, 1)))
 print("total              %8.0f cycles" % (acc[1:6].sum() / max(cnt, 1)))
+
+print("-- single-step launch phases per warp (cycles): prologue | apply_action | map_stats | outputs+reset+epilogue")
+full = env._tens["status"].cpu().numpy().view(np.int64)
+for cls, nm in enumerate(["no change", "changed", "reset"]):
+    a = full[16 + 8 * cls: 16 + 8 * cls + 8]
+    c = max(a[0], 1)
+    print("%-10s n=%-8d mean %7.0f %7.0f %7.0f %7.0f | max warp total %d, max map_stats %d" % (nm, a[0], a[1] / c, a[2] / c, a[3] / c, a[4] / c, a[5], a[6]))

@@ -86,6 +86,9 @@ KAT_CONFIGS = [
     ("binary_turtlecast_warp", "binary-turtlecast-v0", dict(warp=True, width=9, height=12, change_percentage=0.5)),
     ("ddave_narrowcast_raster", "ddave-narrowcast-v0", dict(random_tile=False)),
     ("mdungeon_narrowmulti", "mdungeon-narrowmulti-v0", {}),
+    # random_start=False: every reset restores the first map (representation.py:41-45)
+    ("zelda_wide_fixedstart", "zelda-wide-v0", dict(random_start=False)),
+    ("binary_narrow_fixedstart_raster", "binary-narrow-v0", dict(random_start=False, random_tile=False, width=10, height=6, change_percentage=0.3)),
 ]
 
 

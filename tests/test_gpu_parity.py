@@ -225,6 +225,64 @@ def test_batched_rollout_matches_oracle(case):
         assert ndone > 0, "case never finished an episode; raise steps"
 
 
+def test_partial_reset_mask_and_fixed_start_match_oracle():
+    """reset(mask) resets exactly the masked envs; random_start=False restores each env's first map
+    (representation.py:41-45) while still drawing a fresh cursor."""
+    import torch
+    n = 96
+    for env_id, kwargs in (("zelda-narrow-v0", dict(random_start=False)), ("binary-turtle-v0", {}), ("sokoban-wide-v0", dict(random_start=False))):
+        env = util.host_env(env_id, kwargs, num_envs=n, auto_reset=False, device="cuda")
+        states = np.stack([util.randomstate_words(300 + i) for i in range(n)])
+        env.set_rng_states(states)
+        ref = oracle.OracleEnv(env.native_config, n)
+        ref.set_rng_states(states)
+        prob, rep = env_id.split("-")[:2]
+        S, wide = util.nstats(prob), rep == "wide"
+        env.reset()
+        ref.reset()
+        first_maps = ref["map"].copy()
+        arng = np.random.RandomState(4)
+        for rnd in range(4):
+            for t in range(15):
+                a = random_actions(env, arng, n)
+                env.step(torch.from_numpy(a).cuda())
+                ref.step(a)
+            mask = (arng.random_sample(n) < 0.4).astype(np.uint8)
+            env.reset(torch.from_numpy(mask))
+            ref.reset(mask)
+            assert_state_equal(env, ref, S, "%s partial reset %d" % (env_id, rnd), wide)
+            if kwargs.get("random_start") is False:
+                np.testing.assert_array_equal(ref["map"][mask == 1], first_maps[mask == 1])
+
+
+def test_state_dict_roundtrip_and_resize():
+    import torch
+    n = 64
+    env = util.host_env("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), num_envs=n, device="cuda")
+    env.set_rng_states(np.stack([util.randomstate_words(i) for i in range(n)]))
+    env.reset()
+    acts = torch.from_numpy(np.random.RandomState(0).randint(3, size=(40, n)).astype(np.int32)).cuda()
+    for t in range(20):
+        env.step(acts[t])
+    snap = env.state_dict()
+    outs = []
+    for rep_ in range(2):
+        env.load_state_dict(snap)
+        rew = [env.step(acts[t])[1].clone() for t in range(20, 40)]
+        outs.append((torch.stack(rew), env._tens["map"].clone(), env._tens["rng"].clone()))
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+    # adjust_param after the buffers exist: a new map size re-allocates the state but keeps the RNG streams
+    rng_before = env._tens["rng"].clone()
+    env.adjust_param(width=9, height=7, change_percentage=0.5)
+    obs = env.reset()
+    assert tuple(obs["map"].shape) == (n, 7, 9) and env._max_changes == int(0.5 * 16 * 16)   # quirk Q3: old size
+    ref = oracle.OracleEnv(env.native_config, n)
+    ref.arrs["rng"][:] = rng_before.cpu().numpy().view(np.uint32)
+    ref.reset()
+    np.testing.assert_array_equal(t2n(obs["map"]), ref["map"])
+    np.testing.assert_array_equal(t2n(env._tens["stats"])[:, :2], ref["stats"][:, :2])
+
+
 ROLLOUT_CASES = [
     ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 256, 64),
     ("zelda-wide-v0", {}, 200, 48),

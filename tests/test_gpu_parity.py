@@ -400,3 +400,44 @@ def test_full_size_invariants_binary_narrow_4096():
     np.testing.assert_array_equal(t2n(t["map"]), ref["map"])
     np.testing.assert_array_equal(t2n(t["stats"])[:, :2], ref["stats"][:, :2])
     np.testing.assert_array_equal(t2n(rew[-1]), ref["reward"])
+
+
+FULL_SIZE_CASES = [
+    # BASELINE.json configs 3-5 at their full batch sizes (config 2 is test_full_size_invariants_binary_narrow_4096)
+    ("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2), 4096, 40),
+    ("sokoban-wide-v0", {}, 2048, 30),
+    ("mdungeon-wide-v0", {}, 8192, 16),
+    ("ddave-narrow-v0", {}, 8192, 16),
+    ("binary-turtle-v0", {}, 8192, 40),
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE_CASES, ids=["%s-%d" % (c[0], c[2]) for c in FULL_SIZE_CASES])
+def test_full_size_batches_match_oracle(case):
+    """Full BASELINE batch sizes: fused / grouped rollout on the GPU vs the oracle on every env, plus the
+    size-independent invariants (heat == changes of the running episode, limits respected, tiles in range)."""
+    import torch
+    env_id, kwargs, n, T = case
+    env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
+    states = np.stack([util.randomstate_words(20_000 + i) for i in range(n)])
+    env.set_rng_states(states)
+    env.reset()
+    arng = np.random.RandomState(12)
+    acts = np.stack([random_actions(env, arng, n) for _ in range(T)])
+    rew, done = env.rollout(torch.from_numpy(acts).cuda())
+    env.check_status()
+    t = env._tens
+    assert int(t["map"].max()) < env.get_num_tiles()
+    assert bool((t["heatmap"].sum(dim=(1, 2)).to(torch.int32) == t["changes"]).all())
+    assert bool((t["changes"] < env._max_changes).all()) and bool((t["iteration"] < env._max_iterations).all())
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    ref.set_rng_states(states)
+    ref.reset()
+    S = util.nstats(env_id.split("-")[0])
+    for k in range(T):
+        ref.step(acts[k])
+        np.testing.assert_array_equal(t2n(rew[k]), ref["reward"], err_msg="%s step %d reward" % (env_id, k))
+        np.testing.assert_array_equal(t2n(done[k]).astype(np.uint8), ref["done"], err_msg="%s step %d done" % (env_id, k))
+    np.testing.assert_array_equal(t2n(t["map"]), ref["map"])
+    np.testing.assert_array_equal(t2n(t["stats"])[:, :S], ref["stats"][:, :S])
+    np.testing.assert_array_equal(t2n(t["rng"]).view(np.uint32), ref["rng"])

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   int st[NS], start[NS];
   load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
   load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
+  // first step's action: pull its line into L1 now so the load in apply_action does not add a round trip
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)e * adim));
   Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
   KP();
 #ifdef PCGRL_PROFILE

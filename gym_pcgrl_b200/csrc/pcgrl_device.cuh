@@ -39,26 +39,42 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// In-place twist by one warp.  Batches of 32 consecutive indices: new[i] depends on old[i], old[i+1] and
-// (i < 227 ? old[i+397] : new[i-227]); the dependency distance (227) exceeds the batch width, and every
-// lane reads its inputs before any lane of the batch writes, so the result equals the sequential loop.
+// In-place twist by one warp in three wide phases + one scalar step.  new[i] depends on old[i], old[i+1] and
+// (i < 227 ? old[i+397] : new[i-227]); inside [0,227), [227,454) and [454,623) every input is either untouched by the
+// phase or produced by an earlier phase, so each phase reads all its inputs (24 loads in flight per lane), syncs, and
+// writes -- identical to numpy's sequential mt19937_gen loop (checked against RandomState in tests/test_host_cpu.py).
+template <int LO, int HI, int SRC_OFF>
+__device__ __forceinline__ void mt_twist_phase(uint32_t* k, int lane) {
+  uint32_t out[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = LO + j * 32 + lane;
+    out[j] = 0;
+    if (i < HI) {
+      const uint32_t a = k[i], b = k[i + 1], c = k[i + SRC_OFF];
+      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      out[j] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int i = LO + j * 32 + lane;
+    if (i < HI) k[i] = out[j];
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void mt_twist_warp(uint32_t* k, int lane) {
   __syncwarp();
-  for (int base = 0; base < 624; base += 32) {
-    const int i = base + lane;
-    uint32_t a = 0, b = 0, c = 0;
-    if (i < 624) {
-      a = k[i];
-      b = k[(i + 1 == 624) ? 0 : i + 1];
-      c = k[(i < 227) ? i + 397 : i - 227];
-    }
-    __syncwarp();
-    if (i < 624) {
-      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-      k[i] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
-    __syncwarp();
+  mt_twist_phase<0, 227, 397>(k, lane);
+  mt_twist_phase<227, 454, -227>(k, lane);
+  mt_twist_phase<454, 623, -227>(k, lane);
+  if (lane == 0) {
+    const uint32_t y = (k[623] & 0x80000000u) | (k[0] & 0x7fffffffu);
+    k[623] = k[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
   }
+  __syncwarp();
 }
 
 struct WarpRng {
@@ -119,7 +135,13 @@ struct WarpRng {
         pos = 0;
       }
       const int m = min(count - filled, 624 - pos);
-      for (int i = lane; i < m; i += 32) buf[filled + i] = mt_temper(st[pos + i]);
+      for (int i0 = 0; i0 < m; i0 += 128) {  // four key words in flight per lane
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = i0 + u * 32 + lane; v[u] = (i < m) ? st[pos + i] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int i = i0 + u * 32 + lane; if (i < m) buf[filled + i] = mt_temper(v[u]); }
+      }
       pos += m;
       filled += m;
     }

@@ -126,3 +126,30 @@ def test_env_offset_gives_shard_invariant_seeds():
     a = BatchedPcgrlEnv("binary", "narrow", num_envs=8, seed=5)
     b = BatchedPcgrlEnv("binary", "narrow", num_envs=4, seed=5, env_offset=4)
     np.testing.assert_array_equal(a._pending_states[4:], b._pending_states)
+
+
+def test_phase_parallel_twist_equals_numpy():
+    """The CUDA twist (csrc/pcgrl_device.cuh mt_twist_warp) runs numpy's mt19937_gen as three wide phases plus one
+    scalar step; this is the same schedule in numpy, checked against RandomState's own twist."""
+    def twist_phases(k):
+        k = k.copy()
+        UP, LO, A = np.uint32(0x80000000), np.uint32(0x7fffffff), np.uint32(0x9908b0df)
+
+        def phase(lo, hi, off):
+            idx = np.arange(lo, hi)
+            a, b, c = k[idx], k[idx + 1], k[idx + off]          # all reads of the phase before any write
+            y = (a & UP) | (b & LO)
+            k[idx] = c ^ (y >> np.uint32(1)) ^ np.where(y & np.uint32(1), A, np.uint32(0))
+
+        phase(0, 227, 397)
+        phase(227, 454, -227)
+        phase(454, 623, -227)
+        y = (k[623] & UP) | (k[0] & LO)
+        k[623] = k[396] ^ (y >> np.uint32(1)) ^ (A if y & np.uint32(1) else np.uint32(0))
+        return k
+
+    for seed in (0, 1, 123, 2 ** 31 - 1):
+        r = np.random.RandomState(seed)
+        before = r.get_state()[1].astype(np.uint32)
+        r.random_sample(1)
+        np.testing.assert_array_equal(twist_phases(before), r.get_state()[1].astype(np.uint32))

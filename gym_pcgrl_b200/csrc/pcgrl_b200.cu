@@ -465,7 +465,7 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
   const GroupPlan plan = solver_group_plan(cfg, n);
   if (T == 1 || plan.groups == 1) {
     for (int t = 0; t < T; t++) {
-      int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0, n},
+      int rc = step_solver<PROB>(cfg, b, actions + (size_t)t * n * adim, n, s, (t == T - 1) ? sg : Staging{nullptr, 0u, 0u, 0, n},
                                  SOLVER_MAX_SLOTS, reward_out ? reward_out + (size_t)t * n : nullptr,
                                  done_out ? done_out + (size_t)t * n : nullptr);
       if (rc) return rc;
@@ -490,7 +490,7 @@ static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const
       if (m <= 0) continue;
       const pcgrl_buffers bg = shard_buffers(cfg, b, off, (char*)b->scratch + (size_t)g * plan.bytes_per_group, plan.bytes_per_group);
       for (int t = 0; t < T && rcs[tid] == 0; t++)
-        rcs[tid] = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, gs->streams[g], Staging{nullptr, 0u, 0, m},
+        rcs[tid] = step_solver<PROB>(cfg, &bg, actions + ((size_t)t * n + off) * adim, m, gs->streams[g], Staging{nullptr, 0u, 0u, 0, m},
                                      plan.slots_per_group, reward_out ? reward_out + (size_t)t * n + off : nullptr,
                                      done_out ? done_out + (size_t)t * n + off : nullptr);
     }
@@ -526,11 +526,11 @@ static int rollout_dispatch(const pcgrl_config* cfg, const pcgrl_buffers* b, con
 
 extern "C" int pcgrl_rollout(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                              uint8_t* done_out, int T, int n, void* stream) {
-  return rollout_dispatch(cfg, b, actions, reward_out, done_out, T, n, stream, Staging{nullptr, 0u, 0, n});
+  return rollout_dispatch(cfg, b, actions, reward_out, done_out, T, n, stream, Staging{nullptr, 0u, 0u, 0, n});
 }
 
 extern "C" int pcgrl_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n, void* stream) {
-  return rollout_dispatch(cfg, b, actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0, n});
+  return rollout_dispatch(cfg, b, actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0u, 0, n});
 }
 
 template <int PROB>
@@ -568,6 +568,17 @@ extern "C" int pcgrl_seed(const pcgrl_buffers* b, const uint32_t* seeds, int n, 
   return cuda_rc(cudaGetLastError(), "pcgrl_seed launch");
 }
 
+#ifdef PCGRL_PROFILE
+#include <chrono>
+static double g_host_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+extern "C" void pcgrl_debug_timers(double* out) { for (int i = 0; i < 8; i++) { out[i] = g_host_t[i]; g_host_t[i] = 0; } }
+#define HT(i) do { auto now_ = std::chrono::high_resolution_clock::now(); g_host_t[i] += std::chrono::duration<double, std::micro>(now_ - ht_).count(); ht_ = now_; } while (0)
+#define HT_BEGIN() auto ht_ = std::chrono::high_resolution_clock::now(); g_host_t[7] += 1
+#else
+#define HT(i) do {} while (0)
+#define HT_BEGIN() do {} while (0)
+#endif
+
 static int staging_slots(int n) {
   int r = n / 64;
   return r < 16 ? 16 : (r > 255 ? 255 : r);
@@ -575,7 +586,7 @@ static int staging_slots(int n) {
 
 extern "C" size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n) {
   if (!cfg || n <= 0) return 0;
-  return PCGRL_STAGING_HEADER + sizeof(StepRecord) * (size_t)n + (size_t)staging_slots(n) * cfg->width * cfg->height;
+  return staging_layout(n, staging_slots(n), cfg->width * cfg->height).total;
 }
 
 extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, pcgrl_host_io* io,
@@ -590,44 +601,59 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   const bool delta = io->mode == 1;
   if (delta && (!io->d_staging || !io->h_staging || io->staging_bytes < pcgrl_host_staging_bytes(cfg, n)))
     return fail(-1, "mode 1 needs d_staging / h_staging of pcgrl_host_staging_bytes() bytes");
+  HT_BEGIN();
   cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
+  HT(0);
 
   if (delta && io->synced) {
+    if (n >= (1 << 24)) return fail(-1, "delta transport supports n < 2^24 envs per call");
     const int nslots = staging_slots(n);
-    Staging sg{(uint8_t*)io->d_staging, (uint32_t)io->reset_base, nslots, n};
+    const StagingLayout L = staging_layout(n, nslots, (int)cells);
+    Staging sg{(uint8_t*)io->d_staging, (uint32_t)io->reset_base, (uint32_t)io->change_base, nslots, n};
     rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, sg);
     if (rc) return rc;
-    cudaMemcpyAsync(io->h_staging, io->d_staging, pcgrl_host_staging_bytes(cfg, n), cudaMemcpyDeviceToHost, s);
+    HT(1);
+    cudaMemcpyAsync(io->h_staging, io->d_staging, L.total, cudaMemcpyDeviceToHost, s);
     if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
+    HT(2);
     rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
     if (rc) return rc;
-    // apply the records to the caller's host arrays
+    HT(3);
+    // reward / done / cursor arrive in their final layout; the observation arrays are patched from the change list
     const uint8_t* hs = (const uint8_t*)io->h_staging;
-    const uint32_t total = *(const uint32_t*)hs;
-    const StepRecord* rec = (const StepRecord*)(hs + PCGRL_STAGING_HEADER);
-    const uint8_t* slots = hs + PCGRL_STAGING_HEADER + sizeof(StepRecord) * (size_t)n;
+    const uint32_t total_resets = ((const uint32_t*)hs)[0], total_changes = ((const uint32_t*)hs)[1];
+    memcpy(io->reward, hs + L.reward_off, sizeof(double) * (size_t)n);
+    memcpy(io->done, hs + L.done_off, (size_t)n);
+    const uint8_t* hpos = hs + L.pos_off;
+    if (io->pos && !wide) memcpy(io->pos, hpos, 2 * (size_t)n);
+    const ChangeRecord* rec = (const ChangeRecord*)(hs + L.rec_off);
+    const uint8_t* slots = hs + L.slot_off;
+    uint32_t nchg = total_changes - (uint32_t)io->change_base;
+    if (nchg > (uint32_t)n) nchg = (uint32_t)n;
     bool overflow = false;
-    for (int e = 0; e < n; e++) {
-      const StepRecord r = rec[e];
-      io->reward[e] = r.reward;
-      io->done[e] = r.done;
-      if (io->pos && !wide) { io->pos[2 * e] = r.posx; io->pos[2 * e + 1] = r.posy; }
-      if (r.flags & PCGRL_REC_RESET) {
+    for (uint32_t k = 0; k < nchg; k++) {
+      const ChangeRecord r = rec[k];
+      const size_t e = r.env_kind & 0xffffffu;
+      const uint32_t kind = r.env_kind >> 24;
+      if (e >= (size_t)n) continue;
+      if (kind == PCGRL_REC_RESET) {
         if (r.slot == 0xFF) overflow = true;
-        else if (io->map) memcpy(io->map + (size_t)e * cells, slots + (size_t)r.slot * cells, cells);
-        if (io->heatmap) memset(io->heatmap + (size_t)e * cells, 0, cells);
-      } else if (r.flags & PCGRL_REC_CHANGED) {
-        if (r.flags & PCGRL_REC_MULTI) {
+        else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
+        if (io->heatmap) memset(io->heatmap + e * cells, 0, cells);
+      } else {
+        if (kind == PCGRL_REC_MULTI) {
           if (r.slot == 0xFF) overflow = true;
-          else if (io->map) memcpy(io->map + (size_t)e * cells, slots + (size_t)r.slot * cells, cells);
+          else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
         } else if (io->map) {
-          io->map[(size_t)e * cells + r.cell] = r.tile;
+          io->map[e * cells + r.cell] = r.tile;
         }
-        if (io->heatmap) io->heatmap[(size_t)e * cells + (wide ? (size_t)r.cell : (size_t)r.posy * cfg->width + r.posx)] += 1;
+        if (io->heatmap) io->heatmap[e * cells + (wide ? (size_t)r.cell : (size_t)hpos[2 * e + 1] * cfg->width + hpos[2 * e])] += 1;
       }
     }
-    io->reset_base = (int64_t)total;
-    if (overflow && io->map) {  // more resets than staging slots in one step: fetch the whole map batch
+    io->reset_base = (int64_t)total_resets;
+    io->change_base = (int64_t)total_changes;
+    HT(4);
+    if (overflow && io->map) {  // more whole-map updates than staging slots in one step: fetch the whole map batch
       cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
       rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host (map refetch)");
     }
@@ -636,7 +662,7 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
 
   // full copies (mode 0, or the first / re-arming call of mode 1)
   if (delta) cudaMemsetAsync(io->d_staging, 0, PCGRL_STAGING_HEADER, s);
-  rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0, n});
+  rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0u, 0, n});
   if (rc) return rc;
   if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
   if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, cells * n, cudaMemcpyDeviceToHost, s);
@@ -645,7 +671,7 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   cudaMemcpyAsync(io->done, b->done, (size_t)n, cudaMemcpyDeviceToHost, s);
   if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
   rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
-  if (delta && rc == 0) { io->synced = 1; io->reset_base = 0; }
+  if (delta && rc == 0) { io->synced = 1; io->reset_base = 0; io->change_base = 0; }
   return rc;
 }
 

@@ -262,23 +262,38 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
 }
 
 // ------------------------------------------------------------------------------------------------
-// delta transport for pcgrl_step_host (mode 1): one 16-byte record per env + fresh maps of auto-reset envs
-// staging buffer = [uint32 running reset counter, pad to 16 B][StepRecord x n][nslots x H*W bytes]
+// delta transport for pcgrl_step_host (mode 1).  Staging buffer, copied to the host in ONE D2H transfer:
+//   [header 16 B: u32 running reset counter, u32 running change counter]
+//   [reward f64 x n][done u8 x n][pos u8 x 2n]   final array layout: the host bulk-copies them
+//   [ChangeRecord x n]   compacted: one record per env whose observation changed this step
+//   [nslots x H*W bytes] fresh maps of auto-reset envs / multi-cell edits
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) StepRecord {
-  double reward;
-  uint8_t done, posx, posy, flags;  // flags: 1 = one map cell changed, 2 = env was reset (whole observation replaced)
-  uint16_t cell;                    // y*W + x of the changed cell
-  uint8_t tile, slot;               // new tile; staging slot of the fresh map (0xFF: none / overflow)
+struct __align__(8) ChangeRecord {
+  uint32_t env_kind;  // env index (24 bits) | kind << 24
+  uint16_t cell;      // y*W + x of the changed cell (single-cell edit)
+  uint8_t tile, slot; // new tile; staging slot of the whole map (0xFF: none / overflow)
 };
-#define PCGRL_REC_CHANGED 1
-#define PCGRL_REC_RESET 2
-#define PCGRL_REC_MULTI 4 /* several cells changed: the whole map is staged, the heat map is kept */
+#define PCGRL_REC_CHANGED 1 /* one map cell changed, heat map += 1 at the heat cell */
+#define PCGRL_REC_RESET 2   /* env was reset: whole map replaced (slot), heat map cleared */
+#define PCGRL_REC_MULTI 4   /* several cells changed: whole map replaced (slot), heat map += 1 */
 #define PCGRL_STAGING_HEADER 16
 
+struct StagingLayout { size_t reward_off, done_off, pos_off, rec_off, slot_off, total; };
+__host__ __device__ __forceinline__ StagingLayout staging_layout(int n, int nslots, int cells) {
+  StagingLayout L;
+  L.reward_off = PCGRL_STAGING_HEADER;
+  L.done_off = L.reward_off + sizeof(double) * (size_t)n;
+  L.pos_off = L.done_off + (size_t)n;
+  L.rec_off = (L.pos_off + 2 * (size_t)n + 15) & ~(size_t)15;
+  L.slot_off = L.rec_off + sizeof(ChangeRecord) * (size_t)n;
+  L.total = L.slot_off + (size_t)nslots * cells;
+  return L;
+}
+
 struct Staging {
-  uint8_t* base;        // nullptr: transport disabled
-  uint32_t reset_base;  // value of the running counter at the start of this step
+  uint8_t* base;         // nullptr: transport disabled
+  uint32_t reset_base;   // values of the running counters at the start of this step
+  uint32_t change_base;
   int nslots;
   int n;
 };
@@ -288,31 +303,36 @@ __device__ __forceinline__ void write_record(const Staging& sg, const pcgrl_conf
                                              const uint8_t* new_map, bool multi = false) {
   if (!sg.base) return;
   const int cells = cfg.width * cfg.height;
-  int slot = 0xFF;
+  const StagingLayout L = staging_layout(sg.n, sg.nslots, cells);
+  if (lane == 0) {
+    reinterpret_cast<double*>(sg.base + L.reward_off)[e] = reward;
+    sg.base[L.done_off + e] = done ? 1 : 0;
+    sg.base[L.pos_off + 2 * e] = (uint8_t)x;
+    sg.base[L.pos_off + 2 * e + 1] = (uint8_t)y;
+  }
   multi = multi && changed && !was_reset;
+  if (!(changed || was_reset)) return;
+  int slot = 0xFF;
   if (was_reset || multi) {
     uint32_t s = 0;
     if (lane == 0) s = atomicAdd(reinterpret_cast<uint32_t*>(sg.base), 1u) - sg.reset_base;
     s = __shfl_sync(FULL_MASK, s, 0);
     if (s < (uint32_t)sg.nslots) {
       slot = (int)s;
-      uint8_t* dst = sg.base + PCGRL_STAGING_HEADER + (size_t)sg.n * sizeof(StepRecord) + (size_t)slot * cells;
+      uint8_t* dst = sg.base + L.slot_off + (size_t)slot * cells;
       __syncwarp();
       for (int i = lane; i < cells; i += 32) dst[i] = new_map[i];
     }
   }
   if (lane == 0) {
-    StepRecord r;
-    r.reward = reward;
-    r.done = done ? 1 : 0;
-    r.posx = (uint8_t)x;
-    r.posy = (uint8_t)y;
-    r.flags = (uint8_t)((changed && !was_reset ? PCGRL_REC_CHANGED : 0) | (was_reset ? PCGRL_REC_RESET : 0) |
-                        (multi ? PCGRL_REC_MULTI : 0));
+    const uint32_t k = atomicAdd(reinterpret_cast<uint32_t*>(sg.base) + 1, 1u) - sg.change_base;
+    ChangeRecord r;
+    const uint32_t kind = was_reset ? PCGRL_REC_RESET : (multi ? PCGRL_REC_MULTI : PCGRL_REC_CHANGED);
+    r.env_kind = (uint32_t)e | (kind << 24);
     r.cell = (uint16_t)cell;
     r.tile = (uint8_t)tile;
     r.slot = (uint8_t)slot;
-    reinterpret_cast<StepRecord*>(sg.base + PCGRL_STAGING_HEADER)[e] = r;
+    if (k < (uint32_t)sg.n) reinterpret_cast<ChangeRecord*>(sg.base + L.rec_off)[k] = r;
   }
 }
 

@@ -155,10 +155,10 @@ int pcgrl_seed(const pcgrl_buffers* bufs, const uint32_t* seeds, int n, void* st
  * observation / reward / done out, stream synchronised on return.  Host pointers should be pinned.
  *
  * mode 0 (full):  H2D actions, pcgrl_step, D2H of map / heatmap / pos / reward / done (and info_stats) in full.
- * mode 1 (delta): the step kernels additionally emit one 16-byte record per env (reward, done, cursor, the one
- *                 map cell that changed) plus the fresh maps of the envs that were auto-reset into a small
- *                 device staging buffer; ONE D2H copy of that buffer returns and the library applies the
- *                 records to the caller's host arrays, which therefore always hold the complete current
+ * mode 1 (delta): the step kernels additionally write reward / done / cursor in their final layout, a compacted
+ *                 list of 8-byte change records (env, changed cell, new tile) and the fresh maps of the envs that
+ *                 were auto-reset into a small device staging buffer; ONE D2H copy of that buffer returns and the
+ *                 library patches the caller's host arrays, which therefore always hold the complete current
  *                 observation.  The host arrays must persist between calls; `synced` = 0 (set it after
  *                 pcgrl_reset or any device-side step that bypassed this call) makes the next call fall back to
  *                 a full copy and re-arm.  d_staging / h_staging: device and pinned-host scratch of
@@ -177,7 +177,8 @@ typedef struct pcgrl_host_io {
   size_t staging_bytes;
   int32_t mode;           /* 0 full copies, 1 delta records */
   int32_t synced;         /* in/out, mode 1: host arrays are in sync with the device state */
-  int64_t reset_base;     /* in/out, mode 1: running count of staged resets (library-maintained) */
+  int64_t reset_base;     /* in/out, mode 1: running counters of staged whole-map updates / change records */
+  int64_t change_base;    /*                 (library-maintained)                                            */
 } pcgrl_host_io;
 size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n);
 int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions,

@@ -37,15 +37,11 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int* src, int lane
   for (int i = 0; i < N; i++) if (lane == i) dst[i] = src[i];
 }
 
-// Single-step launches from the host transport carry the actions of one-int representations INSIDE the kernel
-// parameters (one byte per env, CUDA 12 large kernel parameters): no H2D copy is enqueued at all.
-#define PCGRL_PARAM_ACTIONS_MAX 8192
-struct PackedActions { uint8_t a[PCGRL_PARAM_ACTIONS_MAX]; };
-
 template <int PROB>
-__device__ __forceinline__ void rollout_body(const pcgrl_config& cfg, const pcgrl_buffers& b,
-                                             const int32_t* __restrict__ actions, const uint8_t* packed,
-                                             double* reward_out, uint8_t* done_out, int T, int n, const Staging& sg) {
+__global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
+                                                      const __grid_constant__ pcgrl_buffers b,
+                                                      const int32_t* __restrict__ actions, double* reward_out,
+                                                      uint8_t* done_out, int T, int n, Staging sg) {
   constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
   __shared__ WarpSmem smem[WPB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -74,7 +70,7 @@ __device__ __forceinline__ void rollout_body(const pcgrl_config& cfg, const pcgr
   load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
   load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
   // first step's action: pull its line into L1 now so the load in apply_action does not add a round trip
-  if (!packed) asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)e * adim));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)e * adim));
   Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
   KP();
 #ifdef PCGRL_PROFILE
@@ -82,10 +78,7 @@ __device__ __forceinline__ void rollout_body(const pcgrl_config& cfg, const pcgr
 #endif
 
   for (int t = 0; t < T; t++) {
-    int32_t packed_act[1];
-    const int32_t* act;
-    if (packed) { packed_act[0] = (int32_t)packed[e]; act = packed_act; }  // T == 1, one int per env
-    else act = actions + ((size_t)t * n + e) * adim;
+    const int32_t* act = actions + ((size_t)t * n + e) * adim;
     iteration++;  // pcgrl_env.py:130
     int old[NS];
 #pragma unroll
@@ -152,21 +145,6 @@ __device__ __forceinline__ void rollout_body(const pcgrl_config& cfg, const pcgr
     atomicMax(acc + 6, (unsigned long long)(kp[3] - kp[2]));
   }
 #endif
-}
-
-template <int PROB>
-__global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
-                                                      const __grid_constant__ pcgrl_buffers b,
-                                                      const int32_t* __restrict__ actions, double* reward_out,
-                                                      uint8_t* done_out, int T, int n, Staging sg) {
-  rollout_body<PROB>(cfg, b, actions, nullptr, reward_out, done_out, T, n, sg);
-}
-
-template <int PROB>
-__global__ void __launch_bounds__(32 * WPB, 7) k_step_packed(const __grid_constant__ pcgrl_config cfg,
-                                                          const __grid_constant__ pcgrl_buffers b,
-                                                          const __grid_constant__ PackedActions pa, int n, Staging sg) {
-  rollout_body<PROB>(cfg, b, nullptr, pa.a, nullptr, nullptr, 1, n, sg);
 }
 
 template <int PROB>
@@ -601,24 +579,6 @@ extern "C" void pcgrl_debug_timers(double* out) { for (int i = 0; i < 8; i++) { 
 #define HT_BEGIN() do {} while (0)
 #endif
 
-// T = 1 step of a fused problem with the actions carried in the kernel parameters (see PackedActions).
-// Returns 1 if this fast path does not apply (caller falls back to the H2D copy).
-static int step_packed(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* host_actions, int n, cudaStream_t s,
-                       Staging sg) {
-  if (cfg->problem > PCGRL_PROB_ZELDA || action_dim_host(cfg->representation) != 1 || n > PCGRL_PARAM_ACTIONS_MAX) return 1;
-  static thread_local PackedActions pa;
-  for (int i = 0; i < n; i++) {
-    const int32_t a = host_actions[i];
-    if ((uint32_t)a > 255u) return 1;
-    pa.a[i] = (uint8_t)a;
-  }
-  if (cfg->problem == PCGRL_PROB_BINARY)
-    k_step_packed<PCGRL_PROB_BINARY><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, pa, n, sg);
-  else
-    k_step_packed<PCGRL_PROB_ZELDA><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, pa, n, sg);
-  return cuda_rc(cudaGetLastError(), "pcgrl_step_host launch");
-}
-
 static int staging_slots(int n) {
   int r = n / 64;
   return r < 16 ? 16 : (r > 255 ? 255 : r);
@@ -642,17 +602,15 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   if (delta && (!io->d_staging || !io->h_staging || io->staging_bytes < pcgrl_host_staging_bytes(cfg, n)))
     return fail(-1, "mode 1 needs d_staging / h_staging of pcgrl_host_staging_bytes() bytes");
   HT_BEGIN();
+  cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
+  HT(0);
+
   if (delta && io->synced) {
     if (n >= (1 << 24)) return fail(-1, "delta transport supports n < 2^24 envs per call");
     const int nslots = staging_slots(n);
     const StagingLayout L = staging_layout(n, nslots, (int)cells);
     Staging sg{(uint8_t*)io->d_staging, (uint32_t)io->reset_base, (uint32_t)io->change_base, nslots, n};
-    rc = step_packed(cfg, b, io->actions, n, s, sg);  // actions inside the kernel parameters when they fit
-    HT(0);
-    if (rc == 1) {
-      cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
-      rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, sg);
-    }
+    rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, sg);
     if (rc) return rc;
     HT(1);
     cudaMemcpyAsync(io->h_staging, io->d_staging, L.total, cudaMemcpyDeviceToHost, s);
@@ -703,7 +661,6 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   }
 
   // full copies (mode 0, or the first / re-arming call of mode 1)
-  cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
   if (delta) cudaMemsetAsync(io->d_staging, 0, PCGRL_STAGING_HEADER, s);
   rc = rollout_dispatch(cfg, b, d_actions, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0u, 0, n});
   if (rc) return rc;

@@ -313,9 +313,7 @@ class HostStepIO:
             self.staging_bytes = nbytes
         self.struct = s
         self.ref = C.byref(s)
-        # delta mode carries one-int actions of the fused problems inside the kernel parameters, one byte per env
-        packed = mode == "delta" and env._adim == 1 and n <= 8192 and env._prob.name in ("binary", "zelda")
-        self.h2d_bytes = n if packed else self.actions.numel() * 4
+        self.h2d_bytes = self.actions.numel() * 4
         self.full_bytes = sum(t.numel() * t.element_size() for t in
                               (self.map, self.heatmap, self.pos, self.reward, self.done, self.info_stats) if t is not None)
         info_bytes = 0 if self.info_stats is None else self.info_stats.numel() * 4

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
       bool unused;
-      map_stats<PROB>(board, cfg, lane, st, unused);
+      map_stats_shared<PROB>(board, cfg, lane, st, unused);
     }
     KP();
 #ifdef PCGRL_PROFILE
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(32 * WPB) k_get_stats(const __grid_constant__ 
   const Board board = load_board<NP>(maps + (size_t)e * cfg.width * cfg.height, cfg.width, cfg.height, lane, smem[wib].bits);
   int st[NS];
   bool need_solver;
-  map_stats<PROB>(board, cfg, lane, st, need_solver);
+  map_stats_shared<PROB>(board, cfg, lane, st, need_solver);
   store_row<NS>(stats_out + (size_t)e * PCGRL_MAX_STATS, st, lane);
   if (lane >= NS && lane < PCGRL_MAX_STATS) stats_out[(size_t)e * PCGRL_MAX_STATS + lane] = 0;
   if constexpr (ProblemTraits<PROB>::SOLVER) if (need_solver) solver_enqueue(q, e, SOLVE_STATS_ONLY, lane);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(32 * WPB) k_step_update(const __grid_constant_
   }
   if (change > 0) {
     bool need_solver;
-    map_stats<PROB>(board, cfg, lane, st, need_solver);
+    map_stats_shared<PROB>(board, cfg, lane, st, need_solver);
     store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
     if (need_solver) solver_enqueue(q, e, SOLVE_FOR_STEP, lane);
   }

@@ -65,7 +65,7 @@ __device__ __forceinline__ void mt_twist_phase(uint32_t* k, int lane) {
   __syncwarp();
 }
 
-__device__ __forceinline__ void mt_twist_warp(uint32_t* k, int lane) {
+__device__ __noinline__ void mt_twist_warp(uint32_t* k, int lane) {  // one copy: every draw site may reach it
   __syncwarp();
   mt_twist_phase<0, 227, 397>(k, lane);
   mt_twist_phase<227, 454, -227>(k, lane);

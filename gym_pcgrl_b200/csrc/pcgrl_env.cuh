@@ -186,34 +186,32 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
     rng_home = rng.stage(sm.mt, lane);  // the reset consumes 2*H*W (+2) draws and usually crosses a twist
     TP();
     // helper.py:343-352 get_int_prob, then RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]
-    double cdf[PCGRL_MAX_TILES];
+    // (cold path: loops are kept rolled -- the reset code is rarely resident in the instruction cache)
     double total = 0.0, acc = 0.0;
-#pragma unroll
-    for (int t = 0; t < PCGRL_MAX_TILES; t++) if (t < T) total += r.tile_prob[t];
-#pragma unroll
-    for (int t = 0; t < PCGRL_MAX_TILES; t++) {
-      if (t < T) { acc += r.tile_prob[t] / total; cdf[t] = acc; }
-      else cdf[t] = __longlong_as_double(0x7ff0000000000000LL);
-    }
+    unsigned long long thr[PCGRL_MAX_TILES];
+#pragma unroll 1
+    for (int t = 0; t < T; t++) total += r.tile_prob[t];
     // searchsorted(cdf, u, side='right') == #{t : cdf[t] <= u}.  u = k * 2^-53 with the 53-bit integer
     // k = (a << 26) | b, and cdf[t] * 2^53 is exact, so cdf[t] <= u  <=>  ceil(cdf[t] * 2^53) <= k: the per-cell
     // comparisons are done on integers, bit-identical to numpy's double comparison.
-    unsigned long long thr[PCGRL_MAX_TILES];
+    double norm = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < T; t++) norm += r.tile_prob[t] / total;  // cdf[-1] of cumsum(p)
 #pragma unroll
-    for (int t = 0; t < PCGRL_MAX_TILES; t++) {
-      if (t < T) {
-        cdf[t] /= acc;
-        const double scaled = ceil(cdf[t] * 9007199254740992.0);
-        thr[t] = (scaled >= 18446744073709551615.0) ? 0xffffffffffffffffull : (unsigned long long)scaled;
-      } else {
-        thr[t] = 0xffffffffffffffffull;
-      }
+    for (int t = 0; t < PCGRL_MAX_TILES; t++) thr[t] = 0xffffffffffffffffull;
+#pragma unroll 1
+    for (int t = 0; t < T; t++) {
+      acc += r.tile_prob[t] / total;                              // cumsum(p)[t]
+      const double scaled = ceil((acc / norm) * 9007199254740992.0);
+      const unsigned long long v = (scaled >= 18446744073709551615.0) ? 0xffffffffffffffffull : (unsigned long long)scaled;
+#pragma unroll
+      for (int u = 0; u < PCGRL_MAX_TILES; u++) if (u == t) thr[u] = v;
     }
     const int nchunks = (cells + 31) >> 5;
     for (int s0 = 0; s0 < cells; s0 += 256) {  // segments of 256 cells: 512 draws staged at once, 8 cells per lane
       const int nseg = min(256, cells - s0);
       rng.fill(sm.draws, 2 * nseg, lane);  // H*W random_sample() doubles in row-major order
-#pragma unroll
+#pragma unroll 2
       for (int k = 0; k < 8; k++) {
         const int j = k * 32 + lane;  // cell inside the segment
         uint32_t tile = 0;
@@ -242,7 +240,7 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
   }
   if (rng_home) rng.unstage(rng_home, lane);
   TP();
-  map_stats<PROB>(board, cfg, lane, st, need_solver);
+  map_stats_shared<PROB>(board, cfg, lane, st, need_solver);
   TP();
   if (redraw_probs) {  // binary_prob.py:68-72 (problem stream)
     const double p_empty = pr.next_double(lane);

@@ -83,6 +83,13 @@ __device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cf
   }
 }
 
+// One out-of-line copy of map_stats per problem: the step path and the (cold) reset path execute the same
+// instructions, so the reset finds the BFS code already in the instruction cache and the kernels stay small.
+template <int PROB>
+__device__ __noinline__ void map_stats_shared(const Board& b, const pcgrl_config& cfg, int lane, int* st, bool& need_solver) {
+  map_stats<PROB>(b, cfg, lane, st, need_solver);
+}
+
 // Problem.get_reward: fp64, terms summed left to right exactly as the reference writes them
 // (compiled with -fmad=false so no product is fused into the adds).
 template <int PROB>

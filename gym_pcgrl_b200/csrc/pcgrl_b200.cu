@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
       bool unused;
-      map_stats_shared<PROB>(board, cfg, lane, st, unused);
+      map_stats<PROB>(board, cfg, lane, st, unused);
     }
     KP();
 #ifdef PCGRL_PROFILE

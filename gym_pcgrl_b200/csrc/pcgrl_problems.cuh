@@ -83,8 +83,8 @@ __device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cf
   }
 }
 
-// One out-of-line copy of map_stats per problem: the step path and the (cold) reset path execute the same
-// instructions, so the reset finds the BFS code already in the instruction cache and the kernels stay small.
+// Out-of-line copy of map_stats for the cold paths (reset): keeps the kernels small; the hot step path inlines
+// map_stats so that its statistics stay in registers.
 template <int PROB>
 __device__ __noinline__ void map_stats_shared(const Board& b, const pcgrl_config& cfg, int lane, int* st, bool& need_solver) {
   map_stats<PROB>(b, cfg, lane, st, need_solver);

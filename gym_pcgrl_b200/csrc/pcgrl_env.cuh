@@ -240,7 +240,12 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
   }
   if (rng_home) rng.unstage(rng_home, lane);
   TP();
-  map_stats_shared<PROB>(board, cfg, lane, st, need_solver);
+  {  // the out-of-line call gets its own array so that the caller's statistics can stay in registers
+    int tmp[ProblemTraits<PROB>::NSTATS];
+    map_stats_shared<PROB>(board, cfg, lane, tmp, need_solver);
+#pragma unroll
+    for (int i = 0; i < ProblemTraits<PROB>::NSTATS; i++) st[i] = tmp[i];
+  }
   TP();
   if (redraw_probs) {  // binary_prob.py:68-72 (problem stream)
     const double p_empty = pr.next_double(lane);

@@ -186,27 +186,28 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
     rng_home = rng.stage(sm.mt, lane);  // the reset consumes 2*H*W (+2) draws and usually crosses a twist
     TP();
     // helper.py:343-352 get_int_prob, then RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]
-    // (cold path: loops are kept rolled -- the reset code is rarely resident in the instruction cache)
-    double total = 0.0, acc = 0.0;
-    unsigned long long thr[PCGRL_MAX_TILES];
-#pragma unroll 1
-    for (int t = 0; t < T; t++) total += r.tile_prob[t];
+    // One probability per lane (a single load round trip), sequential sums in the reference's order via shuffles,
+    // the two rounds of divisions done by all lanes at once.
     // searchsorted(cdf, u, side='right') == #{t : cdf[t] <= u}.  u = k * 2^-53 with the 53-bit integer
     // k = (a << 26) | b, and cdf[t] * 2^53 is exact, so cdf[t] <= u  <=>  ceil(cdf[t] * 2^53) <= k: the per-cell
     // comparisons are done on integers, bit-identical to numpy's double comparison.
-    double norm = 0.0;
+    const double p_lane = (lane < T) ? r.tile_prob[lane] : 0.0;
+    double total = 0.0;
 #pragma unroll 1
-    for (int t = 0; t < T; t++) norm += r.tile_prob[t] / total;  // cdf[-1] of cumsum(p)
-#pragma unroll
-    for (int t = 0; t < PCGRL_MAX_TILES; t++) thr[t] = 0xffffffffffffffffull;
+    for (int t = 0; t < T; t++) total += __shfl_sync(FULL_MASK, p_lane, t);      // get_int_prob: total += prob[t]
+    const double q_lane = p_lane / total;                                          // result[i] /= total
+    double acc = 0.0, cdf_lane = 0.0;
 #pragma unroll 1
-    for (int t = 0; t < T; t++) {
-      acc += r.tile_prob[t] / total;                              // cumsum(p)[t]
-      const double scaled = ceil((acc / norm) * 9007199254740992.0);
-      const unsigned long long v = (scaled >= 18446744073709551615.0) ? 0xffffffffffffffffull : (unsigned long long)scaled;
-#pragma unroll
-      for (int u = 0; u < PCGRL_MAX_TILES; u++) if (u == t) thr[u] = v;
+    for (int t = 0; t < T; t++) {                                                  // cdf = p.cumsum()
+      acc += __shfl_sync(FULL_MASK, q_lane, t);
+      if (lane == t) cdf_lane = acc;
     }
+    const double scaled = ceil((cdf_lane / acc) * 9007199254740992.0);             // cdf /= cdf[-1]; * 2^53
+    const unsigned long long thr_lane =
+        (lane >= T || scaled >= 18446744073709551615.0) ? 0xffffffffffffffffull : (unsigned long long)scaled;
+    unsigned long long thr[PCGRL_MAX_TILES];
+#pragma unroll
+    for (int t = 0; t < PCGRL_MAX_TILES; t++) thr[t] = __shfl_sync(FULL_MASK, thr_lane, t);
     const int nchunks = (cells + 31) >> 5;
     for (int s0 = 0; s0 < cells; s0 += 256) {  // segments of 256 cells: 512 draws staged at once, 8 cells per lane
       const int nseg = min(256, cells - s0);

@@ -27,9 +27,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_image(const uint8_t* __rest
   const int tid = threadIdx.x;
   const uint32_t block_elem0 = blockIdx.x * (uint32_t)(OBS_THREADS * EPT);
   const uint32_t k0 = block_elem0 + (uint32_t)tid * EPT;
-  union { OutT v[EPT]; uint4 q[4]; } u;
-#pragma unroll
-  for (int r = 0; r < 4; r++) u.q[r] = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int EPC = 16 / (int)sizeof(OutT);  // elements per 16-byte chunk
   if (k0 < total) {
     const uint32_t per_env = (uint32_t)S_h * S_w;
     uint32_t p = k0 / (uint32_t)C;
@@ -46,28 +44,31 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_image(const uint8_t* __rest
       return (my >= 0 && my < H && mx >= 0 && mx < W) ? (int)m[my * W + mx] : pad_value;
     };
     int t = fetch();
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {  // four 16-byte chunks per thread, each built in registers
+      union { OutT v[EPC]; uint4 q; } u;
 #pragma unroll
-    for (int q = 0; q < EPT; q++) {
-      u.v[q] = (C == 1) ? (OutT)t : (OutT)(c == t ? 1 : 0);  // np.eye(dim)[map]
-      if (++c == C) {
-        c = 0;
-        if (++j == S_w) {
-          j = 0;
-          if (++i == S_h) {
-            i = 0;
-            if (++e < n) {
-              m += (size_t)H * W;
-              if (crop) { ox = (int)pos[2 * e] - pad; oy = (int)pos[2 * e + 1] - pad; }
+      for (int q = 0; q < EPC; q++) {
+        u.v[q] = (C == 1) ? (OutT)t : (OutT)(c == t ? 1 : 0);  // np.eye(dim)[map]
+        if (++c == C) {
+          c = 0;
+          if (++j == S_w) {
+            j = 0;
+            if (++i == S_h) {
+              i = 0;
+              if (++e < n) {
+                m += (size_t)H * W;
+                if (crop) { ox = (int)pos[2 * e] - pad; oy = (int)pos[2 * e + 1] - pad; }
+              }
             }
           }
+          if (e < n) t = fetch();
         }
-        if (e < n) t = fetch();
       }
+      // park (swizzled inside each thread's group of four to spread the banks)
+      tile_s[tid * 4 + (r ^ (tid & 3))] = u.q;
     }
   }
-  // park (swizzled inside each thread's group of four to spread the banks), then stream out coalesced
-#pragma unroll
-  for (int r = 0; r < 4; r++) tile_s[tid * 4 + (r ^ (tid & 3))] = u.q[r];
   __syncthreads();
   const size_t total_bytes = (size_t)total * sizeof(OutT);
   const size_t block_byte0 = (size_t)block_elem0 * sizeof(OutT);

@@ -154,7 +154,10 @@ int pcgrl_seed(const pcgrl_buffers* bufs, const uint32_t* seeds, int n, void* st
  * End-to-end step with HOST buffers (the call a reference-side VecEnv binding makes): host actions in, host
  * observation / reward / done out, stream synchronised on return.  Host pointers should be pinned.
  *
- * mode 0 (full):  H2D actions, pcgrl_step, D2H of map / heatmap / pos / reward / done (and info_stats) in full.
+ * The actions are read by the kernel straight from the host buffer when it is pinned and device-mapped (any
+ * cudaHostAlloc / torch pin_memory allocation); pageable buffers are copied H2D through d_actions first.
+ *
+ * mode 0 (full):  pcgrl_step, then D2H of map / heatmap / pos / reward / done (and info_stats) in full.
  * mode 1 (delta): the step kernels additionally write reward / done / cursor in their final layout, a compacted
  *                 list of 8-byte change records (env, changed cell, new tile) and the fresh maps of the envs that
  *                 were auto-reset into a small device staging buffer; ONE D2H copy of that buffer returns and the

@@ -25,7 +25,10 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_image(const uint8_t* __rest
   constexpr int EPT = 64 / (int)sizeof(OutT);  // elements per thread
   __shared__ uint4 tile_s[OBS_THREADS * 4];
   const int tid = threadIdx.x;
-  const uint32_t block_elem0 = blockIdx.x * (uint32_t)(OBS_THREADS * EPT);
+  const uint32_t tile_elems = (uint32_t)(OBS_THREADS * EPT);
+  const uint32_t ntiles = (total + tile_elems - 1) / tile_elems;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // persistent CTAs: 16 KB output tile per trip
+  const uint32_t block_elem0 = tile * tile_elems;
   const uint32_t k0 = block_elem0 + (uint32_t)tid * EPT;
   constexpr int EPC = 16 / (int)sizeof(OutT);  // elements per 16-byte chunk
   if (k0 < total) {
@@ -84,6 +87,8 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_image(const uint8_t* __rest
       const uint8_t* vb = reinterpret_cast<const uint8_t*>(&val);
       for (int b = 0; off + b < total_bytes; b++) ob[off + b] = vb[b];
     }
+  }
+  __syncthreads();  // the tile buffer is reused by the next trip
   }
 }
 

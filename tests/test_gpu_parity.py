@@ -441,3 +441,35 @@ def test_full_size_batches_match_oracle(case):
     np.testing.assert_array_equal(t2n(t["map"]), ref["map"])
     np.testing.assert_array_equal(t2n(t["stats"])[:, :S], ref["stats"][:, :S])
     np.testing.assert_array_equal(t2n(t["rng"]).view(np.uint32), ref["rng"])
+
+
+@pytest.mark.parametrize("env_id", ["binary-narrow-v0", "sokoban-wide-v0"])
+def test_step_is_cuda_graph_capturable(env_id):
+    """The C ABI only enqueues on the caller's stream, so a step can be captured once in a CUDA graph and replayed
+    (launch-bound inner loops: graphs instead of a tracing compiler)."""
+    import torch
+    n, T = 256, 30
+    envs = []
+    for _ in range(2):
+        env = util.host_env(env_id, {}, num_envs=n, device="cuda")
+        env.set_rng_states(np.stack([util.randomstate_words(40 + i) for i in range(n)]))
+        env.reset()
+        envs.append(env)
+    arng = np.random.RandomState(8)
+    acts = torch.from_numpy(np.stack([random_actions(envs[0], arng, n) for _ in range(T + 1)])).cuda()
+    static_a = acts[0].clone()
+    envs[0].step(static_a)          # warm-up outside the capture (one-time function attributes, allocations)
+    envs[1].step(acts[0])
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        envs[0].step(static_a)
+    torch.cuda.synchronize()
+    # the capture itself does not execute the step: replay T times with fresh actions
+    for t in range(1, T + 1):
+        static_a.copy_(acts[t])
+        graph.replay()
+        _, r, d, _ = envs[1].step(acts[t])
+        assert torch.equal(envs[0]._tens["reward"], r) and torch.equal(envs[0]._tens["done"].bool(), d), "step %d" % t
+    assert torch.equal(envs[0]._tens["map"], envs[1]._tens["map"])
+    assert torch.equal(envs[0]._tens["stats"], envs[1]._tens["stats"])

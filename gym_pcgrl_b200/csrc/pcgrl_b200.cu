@@ -699,13 +699,11 @@ extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, con
   if (total >= (1ull << 32)) return fail(-1, "observation tensor too large (>= 2^32 elements): split the batch");
   cudaStream_t s = (cudaStream_t)stream;
   if (out_dtype == 0) {
-    unsigned blocks = (unsigned)((total + OBS_THREADS * 64 - 1) / (OBS_THREADS * 64));
-    if (blocks > 148u * 8u) blocks = 148u * 8u;  // persistent: 8 CTAs per SM loop over the output tiles
+    const unsigned blocks = (unsigned)((total + OBS_THREADS * 64 - 1) / (OBS_THREADS * 64));  // one 16 KB tile per CTA
     k_obs_image<uint8_t><<<blocks, OBS_THREADS, 0, s>>>(maps, pos, (uint8_t*)out, (uint32_t)total, n, cfg->height, cfg->width,
                                                         S_h, S_w, crop_size, pad_value, channels);
   } else {
-    unsigned blocks = (unsigned)((total + OBS_THREADS * 16 - 1) / (OBS_THREADS * 16));
-    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    const unsigned blocks = (unsigned)((total + OBS_THREADS * 16 - 1) / (OBS_THREADS * 16));
     k_obs_image<float><<<blocks, OBS_THREADS, 0, s>>>(maps, pos, (float*)out, (uint32_t)total, n, cfg->height, cfg->width,
                                                       S_h, S_w, crop_size, pad_value, channels);
   }

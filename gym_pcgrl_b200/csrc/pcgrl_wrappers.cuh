@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(OBS_THREADS) k_obs_image(const uint8_t* __rest
   const int tid = threadIdx.x;
   const uint32_t tile_elems = (uint32_t)(OBS_THREADS * EPT);
   const uint32_t ntiles = (total + tile_elems - 1) / tile_elems;
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // persistent CTAs: 16 KB output tile per trip
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // one trip with the default grid (a persistent
+  // grid of 8 CTAs/SM was measured slower: 0.52 vs 0.61 of the HBM peak)
   const uint32_t block_elem0 = tile * tile_elems;
   const uint32_t k0 = block_elem0 + (uint32_t)tid * EPT;
   constexpr int EPC = 16 / (int)sizeof(OutT);  // elements per 16-byte chunk

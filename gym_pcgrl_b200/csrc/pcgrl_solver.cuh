@@ -527,7 +527,7 @@ __device__ __forceinline__ void node_put(uint32_t* nodes, uint32_t* cache, int i
 template <int GAME>
 __device__ void search_pass(const Level& L, const SState& root0, int b, int power, uint32_t* nodes, uint32_t* cache,
                             uint32_t* heap, uint32_t* table, int table_mask, const volatile int32_t* best_win,
-                            int pass_index, int* res, int lane) {
+                            int pass_index, int* res, int* exhausted, int lane) {
   const bool check_lose = (GAME != GAME_SOKOBAN);
   const bool sk_small = (GAME == GAME_SOKOBAN) && L.small;
   int nn = 1, nheap = 0, head = 0, iterations = 0;
@@ -543,6 +543,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     node_put(nodes, cache, 0, root);
     if (b >= 0) { heap[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
     res[0] = 0;
+    *exhausted = 0;
   }
   __syncwarp();
   while (true) {
@@ -681,6 +682,212 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     SState bs;
     node_fetch(nodes, cache, best < 0 ? 0 : best, nn, bs);
     res[1] = st_depth(bs); res[2] = st_h(bs); res[3] = (int)bs.misc;
+    *exhausted = (b >= 0 ? nheap == 0 : head >= nn) ? 1 : 0;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// BFSAgent.getSolution, 32 queue nodes per round.  The FIFO queue of the reference IS the node list in creation
+// order, so iterations k .. k+31 pop nodes head .. head+31, which all exist already.  Processing them together is
+// exact because a node of the batch influences a later one only through
+//   (1) the visited set  -> a node is accepted iff it is not lost, its key is not in the table and no EARLIER lane
+//                           of the batch holds the same key (key equality is an equivalence, the first lane wins);
+//   (2) the best node    -> ordered reduction: minimum (h, depth), earliest node on ties, the current best on ties;
+//   (3) the child order  -> children are appended at prefix-sum offsets (lane order, then `directions` order);
+// and the first winning node in lane order ends the search with iterations = its queue position + 1.
+// Returns (lane 0 writes res): res[0] won / -1 cancelled, res[1] depth, res[2] h, res[3] misc; *exhausted = 1 when
+// the queue ran empty without a win.
+// ------------------------------------------------------------------------------------------------
+template <int GAME>
+__device__ void search_bfs_batched(const Level& L, const SState& root0, int power, uint32_t* nodes, uint32_t* table,
+                                   int table_mask, const volatile int32_t* best_win, int pass_index, int* res,
+                                   int* exhausted, int lane) {
+  const bool check_lose = (GAME != GAME_SOKOBAN);
+  const bool sk_small = (GAME == GAME_SOKOBAN) && L.small;
+  int nn = 1, head = 0, iterations = 0;
+  int best = -1, best_h = 0, best_depth = 0;
+  if (lane == 0) {
+    SState root = root0;
+    if (sk_small) {
+      const unsigned long long occ = sk_occupancy(L, root);
+      root.misc = (uint32_t)occ;
+      root.pad = (uint32_t)(occ >> 32);
+    }
+    root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
+    node_store(nodes, 0, root);
+    res[0] = 0;
+    *exhausted = 0;
+  }
+  __syncwarp();
+  while (iterations < power && head < nn) {
+    int cancel = 0;
+    if (lane == 0) cancel = (*best_win < pass_index) ? 1 : 0;
+    if (__shfl_sync(FULL_MASK, cancel, 0)) {
+      if (lane == 0) res[0] = -1;
+      __syncwarp();
+      return;
+    }
+    const int B = min(32, min(nn - head, power - iterations));
+    const bool active = lane < B;
+    SState cs;
+    cs.m[0] = cs.m[1] = cs.m[2] = cs.m[3] = cs.ks = cs.dh = cs.misc = cs.pad = 0u;
+    if (active) node_load(nodes, head + lane, cs);
+    const bool lost = active && check_lose && st_health(cs) <= 0;
+    bool win = false;
+    if (active && !lost) {
+      if (sk_small) {
+        const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
+        win = (occ & L.target64) == L.target64 && L.ntargets == L.ncrates && L.ntargets > 0;
+      } else {
+        win = g_win<GAME>(L, cs);
+      }
+    }
+    const unsigned winmask = __ballot_sync(FULL_MASK, win);
+    if (winmask) {  // first winning node in queue order
+      const int w = __ffs(winmask) - 1;
+      if (lane == w) { res[0] = 1; res[1] = st_depth(cs); res[2] = st_h(cs); res[3] = (int)cs.misc; }
+      __syncwarp();
+      return;
+    }
+    iterations += B;
+    const bool cand = active && !lost;
+    // (1a) visited table (read-only here): exact key compare on a fingerprint hit
+    const uint32_t hsh = key_hash(cs);
+    const uint32_t fp = (hsh >> 15) & 0x1ffffu;
+    uint32_t slot = hsh & (uint32_t)table_mask;
+    bool seen = false;
+    if (cand) {
+      while (true) {
+        const uint32_t ent = table[slot];
+        if (ent == 0u) break;
+        if ((ent >> 15) == fp) {
+          SState o;
+          node_load(nodes, (int)(ent & 0x7fffu) - 1, o);
+          if (o.m[0] == cs.m[0] && o.m[1] == cs.m[1] && o.m[2] == cs.m[2] && o.m[3] == cs.m[3] && o.ks == cs.ks) { seen = true; break; }
+        }
+        slot = (slot + 1) & (uint32_t)table_mask;
+      }
+    }
+    // (1b) duplicates inside the batch: group lanes by hash, compare the full key with the group's first lane
+    const bool fresh = cand && !seen;
+    const unsigned long long mval = fresh ? (unsigned long long)hsh : (0x100000000ull | (unsigned long long)lane);
+    const unsigned grp = __match_any_sync(FULL_MASK, mval);
+    const int leader = __ffs(grp) - 1;
+    const uint32_t l0 = __shfl_sync(FULL_MASK, cs.m[0], leader), l1 = __shfl_sync(FULL_MASK, cs.m[1], leader);
+    const uint32_t l2 = __shfl_sync(FULL_MASK, cs.m[2], leader), l3 = __shfl_sync(FULL_MASK, cs.m[3], leader);
+    const uint32_t l4 = __shfl_sync(FULL_MASK, cs.ks, leader);
+    const bool same_as_leader = (l0 == cs.m[0] && l1 == cs.m[1] && l2 == cs.m[2] && l3 == cs.m[3] && l4 == cs.ks);
+    bool dup = fresh && leader != lane && same_as_leader;
+    const bool collision = fresh && leader != lane && !same_as_leader;  // equal hash, different key (rare)
+    if (__any_sync(FULL_MASK, collision)) {
+      // exact fallback: every lane in turn broadcasts its key; later fresh lanes with the same key become duplicates
+      dup = false;
+      for (int src = 0; src < B; src++) {
+        const bool src_ok = __shfl_sync(FULL_MASK, (int)(fresh && !dup), src) != 0;
+        const uint32_t s0 = __shfl_sync(FULL_MASK, cs.m[0], src), s1 = __shfl_sync(FULL_MASK, cs.m[1], src);
+        const uint32_t s2 = __shfl_sync(FULL_MASK, cs.m[2], src), s3 = __shfl_sync(FULL_MASK, cs.m[3], src);
+        const uint32_t s4 = __shfl_sync(FULL_MASK, cs.ks, src);
+        if (src_ok && lane > src && fresh && s0 == cs.m[0] && s1 == cs.m[1] && s2 == cs.m[2] && s3 == cs.m[3] && s4 == cs.ks) dup = true;
+      }
+    }
+    const bool accept = fresh && !dup;
+    if (accept) {  // insert (other lanes insert concurrently: claim an empty slot with CAS)
+      const uint32_t ent = (fp << 15) | (uint32_t)(head + lane + 1);
+      while (atomicCAS(&table[slot], 0u, ent) != 0u) slot = (slot + 1) & (uint32_t)table_mask;
+    }
+    // (2) best node: minimum (h, depth), earliest lane; the current best survives ties
+    {
+      unsigned long long k = 0xffffffffffffffffull;
+      if (accept) k = ((unsigned long long)(uint32_t)(st_h(cs) + SOLVER_PRIO_BIAS) << 24) | ((unsigned long long)st_depth(cs) << 8) | (unsigned long long)lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL_MASK, k, o);
+        k = other < k ? other : k;
+      }
+      if (k != 0xffffffffffffffffull) {
+        const int bh = (int)(k >> 24) - SOLVER_PRIO_BIAS, bd = (int)((k >> 8) & 0xffffu), bl = (int)(k & 0xffu);
+        if (best < 0 || bh < best_h || (bh == best_h && bd < best_depth)) { best = head + bl; best_h = bh; best_depth = bd; }
+      }
+    }
+    // (3) children of the accepted nodes, appended in (lane, direction) order
+    SState c[4];
+    int h4[4];
+    unsigned vmask = 0;
+    if (accept) {
+      const int cd = st_depth(cs);
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        c[d] = cs;
+        bool valid = false;
+        int h = 0;
+        if (GAME == GAME_SOKOBAN) {
+          const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
+          if (sk_small) {
+            const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
+            const int nx = st_px(cs) + dx, ny = st_py(cs) + dy;
+            const unsigned long long nbit = 1ull << (ny * L.bw + nx);
+            h = st_h(cs);
+            if (!((L.solid64 | occ) & nbit)) {
+              st_set_pos(c[d], nx, ny);
+              valid = true;
+            } else if (occ & nbit) {
+              const int cx = nx + dx, cy = ny + dy;
+              if (cx >= 0 && cy >= 0 && cx < L.bw && cy < L.bh) {
+                const unsigned long long cbit = 1ull << (cy * L.bw + cx);
+                if (!((L.solid64 | occ) & cbit)) {
+                  st_set_pos(c[d], nx, ny);
+                  sk_set_crate(c[d], sk_crate_at(cs, nx, ny), cx, cy);
+                  const unsigned long long occ2 = occ ^ nbit ^ cbit;
+                  c[d].misc = (uint32_t)occ2;
+                  c[d].pad = (uint32_t)(occ2 >> 32);
+                  valid = ((occ2 & L.dead64) == 0ull);
+                  h = sk_heuristic(L, c[d]);
+                }
+              }
+            }
+          } else {
+            const bool crate_move = sk_update(L, c[d], dx, dy);
+            valid = (c[d].ks & 0xffffu) != (cs.ks & 0xffffu) && !(crate_move && sk_deadlocked(L, c[d]));
+            h = sk_heuristic(L, c[d]);
+          }
+        } else if (GAME == GAME_DDAVE) {
+          const int dx = (d == 1) ? -1 : (d == 2) ? 1 : 0, dy = (d == 3) ? -1 : 0;
+          dd_update(L, c[d], dx, dy);
+          valid = true;
+          h = dd_heuristic(L, c[d]);
+        } else {
+          const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
+          md_update(L, c[d], dx, dy);
+          valid = true;
+          h = md_heuristic(L, c[d]);
+        }
+        c[d].dh = (uint32_t)(cd + 1) | ((uint32_t)(h + SOLVER_PRIO_BIAS) << 16);
+        h4[d] = h;
+        if (valid) vmask |= 1u << d;
+      }
+    }
+    int cnt = __popc(vmask), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    int dst = nn + incl - cnt;
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+      if ((vmask >> d) & 1u) { node_store(nodes, dst, c[d]); dst++; }
+    (void)h4;
+    nn += total;
+    head += B;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    SState bs;
+    node_load(nodes, best < 0 ? 0 : best, bs);
+    res[1] = st_depth(bs); res[2] = st_h(bs); res[3] = (int)bs.misc;
+    *exhausted = (head >= nn) ? 1 : 0;
   }
   __syncwarp();
 }
@@ -718,22 +925,35 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
     for (int i = lane; i < table_size; i += 32) table[i] = 0u;
     __syncwarp();
     __shared__ int res_s[4];
+    __shared__ int exhausted_s;
     int* res = res_s;
     if (lane == 0) {
       SState root;
       level_init<GAME>(L, root, W, H);
       root_s = root;
       res[0] = 0; res[1] = 0; res[2] = 0; res[3] = 0;
+      exhausted_s = 0;
       if (L.overflow) atomicExch(q.status, 1);
     }
     __syncwarp();
     if (!L.overflow) {
       const SState root = root_s;
-      search_pass<GAME>(L, root, b, cfg.solver_power, nodes, cache, heap, table, table_size - 1, q.best_win + item, pass, res, lane);
+      if (b < 0)
+        search_bfs_batched<GAME>(L, root, cfg.solver_power, nodes, table, table_size - 1, q.best_win + item, pass, res, &exhausted_s, lane);
+      else
+        search_pass<GAME>(L, root, b, cfg.solver_power, nodes, cache, heap, table, table_size - 1, q.best_win + item, pass, res, &exhausted_s, lane);
     }
     __syncwarp();
     if (lane == 0) {
       if (res[0] == 1) atomicMin(q.best_win + item, pass);
+      // A pass whose queue ran empty without a win has popped every reachable state exactly once.  Where the visited
+      // key IS the state (sokoban, mdungeon) every other pass would pop the same states in the same number of
+      // iterations and also fail, and its best node has the same minimum heuristic -> the other passes are cancelled
+      // (best_win = -1 - pass).  sokoban reports the heuristic only, so any exhausted pass serves; mdungeon reports
+      // the counters of the BFS pass's best node, so only its BFS pass may cancel.  ddave's key omits airTime / jumps:
+      // no rule.
+      if (res[0] == 0 && exhausted_s && (GAME == GAME_SOKOBAN || (GAME == GAME_MDUNGEON && b < 0)))
+        atomicMin(q.best_win + item, -1 - pass);
       int32_t* r = q.results + ((size_t)item * 4 + pass) * 4;
       r[0] = res[0]; r[1] = res[1]; r[2] = res[2]; r[3] = res[3];
       __threadfence();
@@ -741,7 +961,9 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
         __threadfence();
         const volatile int32_t* rr = q.results + (size_t)item * 16;
         int sel = 3;
-        for (int p = 0; p < 4; p++) if (rr[p * 4] == 1) { sel = p; break; }
+        const int bw = *(const volatile int32_t*)(q.best_win + item);
+        if (bw < 0) sel = -1 - bw;  // exhausted pass: nobody can win
+        else for (int p = 0; p < 4; p++) if (rr[p * 4] == 1) { sel = p; break; }
         const int won = (rr[sel * 4] == 1), depth = rr[sel * 4 + 1], h = rr[sel * 4 + 2];
         const uint32_t misc = (uint32_t)rr[sel * 4 + 3];
         int32_t* st = stats + (size_t)e * PCGRL_MAX_STATS;

@@ -30,7 +30,7 @@ def main():
             solver = bench.WORKLOADS[name]["prob"] in ("sokoban", "ddave", "mdungeon")
             steps = max(50, a.steps // 4) if solver else a.steps
             cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", name, "--steps", str(steps),
-                   "--warmup", "50", "--chunk", "50", "--cpu-seconds", str(a.cpu_seconds)]
+                   "--warmup", "128", "--chunk", "128", "--cpu-seconds", str(a.cpu_seconds)]
             p = subprocess.run(cmd, capture_output=True, text=True)
             line = p.stdout.strip().split("\n")[-1] if p.stdout.strip() else ""
             try:

@@ -297,6 +297,388 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
   (void)H;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Solver problems, T-step rollouts: ENV-ASYNCHRONOUS persistent kernel.
+//
+// The lock-step pipeline above (update -> k_solve -> finish -> k_solve) makes every batched step wait for the
+// slowest search of the batch.  Environments never interact, so for a rollout whose actions are known in advance
+// each env can run through its T steps on its own clock: a warp pulls an env index from a global counter, keeps the
+// bitboards / cursor / statistics in registers like k_rollout, and when the map satisfies the solver precondition
+// it runs _run_game INLINE: the four passes in the reference's order, stopping at the first win
+// (sokoban_prob.py:110-122, ddave_prob.py:122-135, mdungeon_prob.py:125-138).
+//
+// A CTA holds ASYNC_WPB env warps and ONE search arena (visited table + node ring + heap, 94.5 KB at power 5000)
+// guarded by a shared-memory lock, plus two lock-guarded reset staging areas; two CTAs fit one SM.
+//
+// Tail: the rollout ends when the slowest env does, and a single search that runs all four passes to the
+// iteration cap costs ~20 ms.  So the owner POSTS passes 1..3 of every search in a request slot in HBM; warps that
+// have run out of envs become helpers: they claim posted passes (atomicAnd on open_mask), run them on their own
+// CTA's arena from the env's map in HBM, and publish the result.  The owner runs pass 0, then every pass nobody has
+// claimed, then waits for the claimed ones (a helper never blocks, so the wait is finite) and merges in the
+// reference's order exactly like k_solve (first winning pass; an exhausted pass proves that nobody wins).  While
+// all warps still have envs of their own there are no helpers and no speculative work at all.
+// ------------------------------------------------------------------------------------------------
+#define ASYNC_RESET_AREAS 2
+
+struct ArenaHead {
+  Level L;
+  SState root;
+  int res[4];
+  int exhausted;
+  int lock;
+  int reset_lock[ASYNC_RESET_AREAS];
+};
+
+__device__ __forceinline__ void arena_lock(int* lock, int lane) {
+  if (lane == 0) {
+    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(256);
+    __threadfence_block();
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ bool arena_trylock(int* lock, int lane) {
+  int got = 0;
+  if (lane == 0) {
+    got = (atomicCAS(lock, 0, 1) == 0) ? 1 : 0;
+    __threadfence_block();
+  }
+  return __shfl_sync(FULL_MASK, got, 0) != 0;
+}
+__device__ __forceinline__ void arena_unlock(int* lock, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicExch(lock, 0);
+  }
+}
+__device__ __forceinline__ int ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+
+struct ArenaRefs {
+  ArenaHead* A;
+  uint32_t *table, *cache, *heap, *nodes;
+  int table_size;
+};
+
+// One pass of _run_game on the level in A.L (arena lock held); publishes the result in the request slot.
+template <int GAME>
+__device__ __noinline__ void async_run_pass(const pcgrl_config& cfg, const ArenaRefs& R, AsyncGroup* G, int pass, int lane) {
+  ArenaHead& A = *R.A;
+  const int b = (GAME == GAME_SOKOBAN) ? ((pass == 0) ? -1 : (pass == 1) ? 2 : (pass == 2) ? 1 : 0)
+                                       : ((pass == 0) ? 2 : (pass == 1) ? 1 : (pass == 2) ? 0 : -1);
+  __syncwarp();
+  uint4* t4 = reinterpret_cast<uint4*>(R.table);
+  for (int i = lane; i < (R.table_size >> 2); i += 32) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (lane == 0) { A.res[0] = 0; A.res[1] = 0; A.res[2] = 0; A.res[3] = 0; A.exhausted = 0; }
+  __syncwarp();
+  const SState root = A.root;
+  if (b < 0)
+    search_bfs_batched<GAME>(A.L, root, cfg.solver_power, R.nodes, R.table, R.table_size - 1, &G->best_win, pass, A.res, &A.exhausted, lane);
+  else
+    search_pass<GAME>(A.L, root, b, cfg.solver_power, R.nodes, R.cache, R.heap, R.table, R.table_size - 1, &G->best_win, pass, A.res, &A.exhausted, lane);
+  __syncwarp();
+  if (lane == 0) {
+    if (A.res[0] == 1) atomicMin(&G->best_win, pass);
+    // exhaustion rule: see k_solve
+    if (A.res[0] == 0 && A.exhausted && (GAME == GAME_SOKOBAN || (GAME == GAME_MDUNGEON && b < 0))) atomicMin(&G->best_win, -1 - pass);
+    G->results[pass * 4 + 0] = A.res[0]; G->results[pass * 4 + 1] = A.res[1];
+    G->results[pass * 4 + 2] = A.res[2]; G->results[pass * 4 + 3] = A.res[3];
+    __threadfence();
+    atomicOr(&G->done_mask, 1 << pass);
+  }
+  __syncwarp();
+}
+
+// _run_game for the map held in `board` (== the env's map in HBM); arena lock held by the caller.  Patches the
+// play-through statistics in st.
+template <int PROB>
+__device__ __noinline__ void solve_inline(const pcgrl_config& cfg, const Board& board, const ArenaRefs& R, AsyncHeader* hdr,
+                                          AsyncGroup* G, int e, int lane, int* st, int32_t* status) {
+  constexpr int GAME = GameOf<PROB>::GAME;
+  ArenaHead& A = *R.A;
+  const int W = cfg.width, H = cfg.height;
+  __syncwarp();
+  if (lane < H)
+    for (int x = 0; x < W; x++) A.L.tiles[lane * W + x] = (uint8_t)tile_at(board, x);
+  __threadfence();  // helpers read this env's map from HBM
+  __syncwarp();
+  if (lane == 0) {
+    SState root;
+    level_init<GAME>(A.L, root, W, H);
+    A.root = root;
+    if (A.L.overflow && status) atomicExch(status, 1);
+  }
+  __syncwarp();
+  int won = 0, depth = 0, h = 0;
+  uint32_t misc = 0;
+  if (!A.L.overflow) {
+    if (lane == 0) {
+      G->env = e;
+      G->best_win = 4;
+      G->done_mask = 0;
+      __threadfence();
+      atomicExch(&G->open_mask, 0xE);
+      atomicAdd(&hdr->posted, 3);
+    }
+    __syncwarp();
+    async_run_pass<GAME>(cfg, R, G, 0, lane);
+    for (int pass = 1; pass < 4; pass++) {
+      int mine = 0, skip = 0;
+      if (lane == 0) {
+        const int bw = ld_volatile(&G->best_win);
+        // once an earlier pass has won (or some pass exhausted) every remaining unclaimed pass is dropped at once
+        const int want = (bw < pass) ? (0xE & ~((1 << pass) - 1)) : (1 << pass);
+        const int got = atomicAnd(&G->open_mask, ~want) & want;
+        if (got) atomicSub(&hdr->posted, __popc(got));
+        if (bw < pass) {
+          for (int p = pass; p < 4; p++) if ((got >> p) & 1) G->results[p * 4] = -1;
+          if (got) { __threadfence(); atomicOr(&G->done_mask, got); }
+          skip = 1;
+        } else {
+          mine = (got >> pass) & 1;
+        }
+      }
+      mine = __shfl_sync(FULL_MASK, mine, 0);
+      skip = __shfl_sync(FULL_MASK, skip, 0);
+      if (skip) break;
+      if (mine) async_run_pass<GAME>(cfg, R, G, pass, lane);
+    }
+    if (lane == 0) {
+      while ((ld_volatile(&G->done_mask) & 0xF) != 0xF) __nanosleep(500);
+      __threadfence();
+      const volatile int32_t* rr = G->results;
+      const int bw = ld_volatile(&G->best_win);
+      int sel = 3;
+      if (bw < 0) sel = -1 - bw;  // exhausted pass: nobody can win
+      else for (int p = 0; p < 4; p++) if (rr[p * 4] == 1) { sel = p; break; }
+      A.res[0] = (rr[sel * 4] == 1) ? 1 : 0; A.res[1] = rr[sel * 4 + 1]; A.res[2] = rr[sel * 4 + 2]; A.res[3] = rr[sel * 4 + 3];
+    }
+    __syncwarp();
+    won = A.res[0]; depth = A.res[1]; h = A.res[2]; misc = (uint32_t)A.res[3];
+  }
+  __syncwarp();
+  const int dist_win = won ? 0 : h, sol_len = won ? depth : 0;
+  if (GAME == GAME_SOKOBAN) {  // sokoban_prob.py:110-122,143-144
+    st[4] = dist_win; st[5] = sol_len;
+  } else if (GAME == GAME_DDAVE) {  // ddave_prob.py:122-135,164-168
+    st[9] = dist_win; st[10] = sol_len; st[7] = (int)(misc >> 16); st[8] = (int)((misc >> 8) & 0xffu);
+  } else {  // mdungeon_prob.py:125-138,166-170
+    st[9] = dist_win; st[10] = sol_len;
+    st[6] = (int)(misc & 0xffu); st[7] = (int)((misc >> 8) & 0xffu); st[8] = (int)((misc >> 16) & 0xffu);
+  }
+}
+
+// A warp without envs of its own: claim a posted pass of somebody else's search and run it on this CTA's arena.
+template <int PROB>
+__device__ __noinline__ void async_help(const pcgrl_config& cfg, const pcgrl_buffers& b, const ArenaRefs& R, AsyncHeader* hdr,
+                                        AsyncGroup* groups, int ngroups, int n, int lane) {
+  constexpr int GAME = GameOf<PROB>::GAME;
+  ArenaHead& A = *R.A;
+  const int W = cfg.width, H = cfg.height, cells = W * H;
+  int start = (blockIdx.x * ASYNC_WPB + (threadIdx.x >> 5)) % ngroups;
+  while (true) {
+    int stop = 0, has = 0;
+    if (lane == 0) { stop = ld_volatile(&hdr->envs_done) >= n; has = ld_volatile(&hdr->posted) > 0; }
+    stop = __shfl_sync(FULL_MASK, stop, 0);
+    has = __shfl_sync(FULL_MASK, has, 0);
+    if (stop) break;
+    if (!has) { __nanosleep(2000); continue; }
+    if (!arena_trylock(&A.lock, lane)) { __nanosleep(2000); continue; }
+    int fg = -1, fp = 0;
+    for (int g0 = 0; g0 < ngroups && fg < 0; g0 += 32) {
+      int g = start + g0 + lane;
+      if (g >= ngroups) g -= ngroups;
+      const int m = (g0 + lane < ngroups) ? ld_volatile(&groups[g].open_mask) : 0;
+      unsigned cand = __ballot_sync(FULL_MASK, m != 0);
+      while (cand && fg < 0) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        int ok = 0, p = 0;
+        if (lane == src) {
+          p = __ffs(m) - 1;
+          ok = (atomicAnd(&groups[g].open_mask, ~(1 << p)) >> p) & 1;
+          if (ok) { atomicSub(&hdr->posted, 1); __threadfence(); }
+        }
+        ok = __shfl_sync(FULL_MASK, ok, src);
+        if (ok) { fg = __shfl_sync(FULL_MASK, g, src); fp = __shfl_sync(FULL_MASK, p, src); }
+      }
+    }
+    if (fg >= 0) {
+      AsyncGroup* G = groups + fg;
+      start = fg;
+      int skip = 0, e = 0;
+      if (lane == 0) {
+        e = ld_volatile(&G->env);
+        if (ld_volatile(&G->best_win) < fp) {  // already decided: nothing to run
+          G->results[fp * 4] = -1;
+          __threadfence();
+          atomicOr(&G->done_mask, 1 << fp);
+          skip = 1;
+        }
+      }
+      skip = __shfl_sync(FULL_MASK, skip, 0);
+      e = __shfl_sync(FULL_MASK, e, 0);
+      if (!skip) {
+        const uint8_t* gm = b.map + (size_t)e * cells;
+        for (int i = lane; i < cells; i += 32) A.L.tiles[i] = __ldcg(gm + i);
+        __syncwarp();
+        if (lane == 0) {
+          SState root;
+          level_init<GAME>(A.L, root, W, H);
+          A.root = root;
+        }
+        __syncwarp();
+        async_run_pass<GAME>(cfg, R, G, fp, lane);
+      }
+    }
+    arena_unlock(&A.lock, lane);
+    if (fg < 0) __nanosleep(1000);
+  }
+  (void)H;
+}
+
+template <int PROB>
+__global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __grid_constant__ pcgrl_config cfg,
+                                                                     const __grid_constant__ pcgrl_buffers b,
+                                                                     const int32_t* __restrict__ actions, double* reward_out,
+                                                                     uint8_t* done_out, int T, int n, AsyncHeader* hdr,
+                                                                     AsyncGroup* groups, uint32_t* node_pool,
+                                                                     size_t nodes_per_pass, int table_size) {
+  constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
+  extern __shared__ __align__(16) uint32_t dyn[];
+  __shared__ ArenaHead A;
+  __shared__ uint32_t wbits[ASYNC_WPB][3 * PCGRL_SBITS_STRIDE];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  ArenaRefs R;
+  R.A = &A;
+  R.table = dyn;
+  R.cache = dyn + table_size;
+  R.heap = R.cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;
+  R.nodes = node_pool + (size_t)blockIdx.x * nodes_per_pass * SOLVER_NODE_WORDS;
+  R.table_size = table_size;
+  const size_t heap_words = (size_t)3 * cfg.solver_power + 8;
+  WarpSmem* reset_areas = reinterpret_cast<WarpSmem*>(R.heap + ((heap_words + 3) & ~(size_t)3));
+  const int my_area = wib % ASYNC_RESET_AREAS;
+  WarpSmem& reset_sm = reset_areas[my_area];
+  AsyncGroup* G = groups + blockIdx.x * ASYNC_WPB + wib;
+  const int ngroups = gridDim.x * ASYNC_WPB;
+  if (threadIdx.x == 0) {
+    A.lock = 0;
+    for (int i = 0; i < ASYNC_RESET_AREAS; i++) A.reset_lock[i] = 0;
+  }
+  __syncthreads();
+  const int W = cfg.width, H = cfg.height, cells = W * H;
+  const int adim = action_dim(cfg.representation);
+  const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
+
+#ifdef PCGRL_PROFILE
+  // status int64[64 + k]: 0 searches, 1 search cycles, 2 lock-wait cycles, 3 resets, 4 reset cycles, 5 envs,
+  // 6 env cycles, 7 max env cycles, 8 max search cycles, 9 max warp cycles (all its envs)
+  unsigned long long* prof = reinterpret_cast<unsigned long long*>(b.status) + 64;
+  const long long warp_t0 = clock64();
+#define AP_ADD(k, v) do { if (lane == 0) atomicAdd(prof + (k), (unsigned long long)(v)); } while (0)
+#define AP_MAX(k, v) do { if (lane == 0) atomicMax(prof + (k), (unsigned long long)(v)); } while (0)
+#define AP_NOW() clock64()
+#else
+#define AP_ADD(k, v) do {} while (0)
+#define AP_MAX(k, v) do {} while (0)
+#define AP_NOW() 0ll
+#endif
+  while (true) {
+    int e = 0;
+    if (lane == 0) e = atomicAdd(&hdr->work, 1);
+    e = __shfl_sync(FULL_MASK, e, 0);
+    if (e >= n) break;
+    const long long env_t0 = AP_NOW();
+    const EnvRefs r = env_refs(cfg, b, e);
+    WarpRng rng;
+    rng.init(r.rng_rep, (cfg.representation == PCGRL_REP_NARROW || cfg.representation >= PCGRL_REP_NARROWCAST) ? lane : -1);
+    int x = 0, y = 0;
+    if (cfg.representation != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
+    int iteration = b.iteration[e], changes = b.changes[e];
+    int st[NS], start[NS];
+    load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
+    load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
+    Board board = load_board<NP>(r.map, W, H, lane, wbits[wib]);
+
+    for (int t = 0; t < T; t++) {
+      const int32_t* act = actions + ((size_t)t * n + e) * adim;
+      iteration++;  // pcgrl_env.py:130
+      int old[NS];
+#pragma unroll
+      for (int i = 0; i < NS; i++) old[i] = st[i];
+      int hx, hy, cell, tile;
+      bool multi;
+      const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi);
+      if (change > 0) {  // pcgrl_env.py:135-138
+        changes += change;
+        bool need_solver;
+        map_stats<PROB>(board, cfg, lane, st, need_solver);
+        if (need_solver) {
+          const long long t0 = AP_NOW();
+          arena_lock(&A.lock, lane);
+          const long long t1 = AP_NOW();
+          solve_inline<PROB>(cfg, board, R, hdr, G, e, lane, st, b.status);
+          arena_unlock(&A.lock, lane);
+          const long long t2 = AP_NOW();
+          AP_ADD(0, 1); AP_ADD(1, t2 - t1); AP_ADD(2, t1 - t0); AP_MAX(8, t2 - t1);
+          (void)t0; (void)t1; (void)t2;
+        }
+      }
+      const double reward = (change > 0) ? problem_reward<PROB>(cfg, st, old) : 0.0;  // :142
+      const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
+                        iteration >= cfg.max_iterations;                              // :143
+      if (lane == 0) {
+        if (reward_out) reward_out[(size_t)t * n + e] = reward;
+        if (done_out) done_out[(size_t)t * n + e] = done ? 1 : 0;
+        if (t == T - 1) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
+      }
+      if (t == T - 1) store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+      if (done && auto_reset) {
+        bool need_solver;
+        const long long t0 = AP_NOW();
+        arena_lock(&A.reset_lock[my_area], lane);
+        const long long t1 = AP_NOW();
+        env_reset<PROB>(cfg, b, e, lane, reset_sm, rng, board, x, y, st, need_solver);
+        arena_unlock(&A.reset_lock[my_area], lane);
+        const long long t2 = AP_NOW();
+        AP_ADD(2, t1 - t0); AP_ADD(3, 1); AP_ADD(4, t2 - t1);
+        if (need_solver) {
+          arena_lock(&A.lock, lane);
+          const long long t3 = AP_NOW();
+          solve_inline<PROB>(cfg, board, R, hdr, G, e, lane, st, b.status);
+          arena_unlock(&A.lock, lane);
+          const long long t4 = AP_NOW();
+          AP_ADD(0, 1); AP_ADD(1, t4 - t3); AP_ADD(2, t3 - t2); AP_MAX(8, t4 - t3);
+          (void)t3; (void)t4;
+        }
+        (void)t0; (void)t1; (void)t2;
+#pragma unroll
+        for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
+        iteration = 0;
+        changes = 0;
+      } else if (change > 0) {
+        heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);  // :137
+      }
+    }
+    rng.finish(lane);
+    if (lane == 0) {
+      if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
+      b.iteration[e] = iteration;
+      b.changes[e] = changes;
+    }
+    store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+    store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start, lane);
+    __syncwarp();
+    if (lane == 0) atomicAdd(&hdr->envs_done, 1);
+    AP_ADD(5, 1); AP_ADD(6, AP_NOW() - env_t0); AP_MAX(7, AP_NOW() - env_t0);
+    (void)env_t0;
+  }
+#ifdef PCGRL_PROFILE
+  AP_MAX(9, clock64() - warp_t0);
+#endif
+  async_help<PROB>(cfg, b, R, hdr, groups, ngroups, n, lane);
+}
+
 __global__ void k_seed(uint32_t* rng, const uint32_t* __restrict__ seeds, int n) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
@@ -455,6 +837,44 @@ static GroupStreams* group_streams() {
   return &gs;
 }
 
+// T > 1 steps of a solver problem through the env-asynchronous persistent kernel (k_rollout_async).
+template <int PROB>
+static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                         uint8_t* done_out, int T, int n, cudaStream_t s) {
+  if constexpr (GameOf<PROB>::GAME >= 0) {
+    int table_size;
+    const size_t smem = ((solver_arena_words(cfg, &table_size) + 3) & ~(size_t)3) * sizeof(uint32_t) + ASYNC_RESET_AREAS * sizeof(WarpSmem);
+    static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
+    if (configured[PROB] < smem) {
+      cudaError_t ce = cudaFuncSetAttribute(k_rollout_async<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (ce != cudaSuccess) return cuda_rc(ce, "k_rollout_async shared memory opt-in");
+      configured[PROB] = smem;
+    }
+    static thread_local int sm_dev = -1, sm_count = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sm_dev != dev) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); sm_dev = dev; }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_async<PROB>, 32 * ASYNC_WPB, smem);
+    if (per_sm < 1) return fail(-1, "k_rollout_async does not fit one SM (solver_power too large)");
+    const SolverLayout lay = solver_layout(cfg, n);
+    int grid = (n + ASYNC_WPB - 1) / ASYNC_WPB;
+    if (grid > sm_count * per_sm) grid = sm_count * per_sm;
+    if (grid > 4 * lay.slots) grid = 4 * lay.slots;  // one node pool per CTA
+    if (grid > ASYNC_MAX_CTAS) grid = ASYNC_MAX_CTAS;
+    char* region = (char*)b->scratch + lay.async_off;
+    AsyncHeader* hdr = (AsyncHeader*)region;
+    AsyncGroup* groups = (AsyncGroup*)(region + 256);
+    cudaMemsetAsync(region, 0, 256 + sizeof(AsyncGroup) * (size_t)grid * ASYNC_WPB, s);
+    uint32_t* pool = (uint32_t*)((char*)b->scratch + lay.nodes_off);
+    k_rollout_async<PROB><<<grid, 32 * ASYNC_WPB, smem, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, hdr, groups, pool,
+                                                             lay.nodes_per_pass, table_size);
+    return cuda_rc(cudaGetLastError(), "pcgrl_rollout (async) launch");
+  } else {
+    return fail(-1, "not a solver problem");
+  }
+}
+
 // T consecutive PcgrlEnv.step calls of a solver problem.  T == 1 (and the host transport) is one lock-step batch.
 // For T > 1 the actions of all steps are known, so the batch is split into independent env groups, each advancing
 // through its own T steps on its own stream: a search that runs to the iteration cap stalls one group, not the batch.
@@ -462,6 +882,9 @@ template <int PROB>
 static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                           uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   const int adim = action_dim_host(cfg->representation);
+  // PCGRL_SOLVER_ASYNC=0 selects the older stream-group pipeline below (kept for comparison)
+  static const bool use_async = !(getenv("PCGRL_SOLVER_ASYNC") && atoi(getenv("PCGRL_SOLVER_ASYNC")) == 0);
+  if (T > 1 && use_async && !sg.base) return rollout_async<PROB>(cfg, b, actions, reward_out, done_out, T, n, s);
   const GroupPlan plan = solver_group_plan(cfg, n);
   if (T == 1 || plan.groups == 1) {
     for (int t = 0; t < T; t++) {

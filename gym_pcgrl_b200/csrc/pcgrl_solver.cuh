@@ -41,10 +41,24 @@ struct SolverQueue {
 };
 
 struct SolverLayout {
-  size_t queue_bytes, old_stats_off, heat_off, nodes_off, total;
+  size_t queue_bytes, old_stats_off, heat_off, nodes_off, async_off, total;
   int slots;
   size_t nodes_per_pass;
 };
+
+// k_rollout_async bookkeeping (see pcgrl_b200.cu): one header + one 128-byte request slot per env warp
+#define ASYNC_MAX_CTAS 512
+#define ASYNC_WPB 4
+struct AsyncHeader { int32_t work, envs_done, posted, pad; };
+struct __align__(16) AsyncGroup {
+  int32_t env;         // env whose map (in HBM) is being solved
+  int32_t open_mask;   // passes posted and not yet claimed (bit p)
+  int32_t done_mask;   // passes finished, skipped or cancelled (bit p)
+  int32_t best_win;    // earliest pass (reference order) that has won; -1 - p: pass p exhausted the state space; 4: none
+  int32_t results[16]; // [pass][won / -1 cancelled, depth, h, counters]
+  int32_t pad[12];
+};
+static inline size_t async_region_bytes() { return 256 + sizeof(AsyncGroup) * (size_t)ASYNC_MAX_CTAS * ASYNC_WPB; }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -61,7 +75,8 @@ static inline SolverLayout solver_layout(const pcgrl_config* c, int n, int max_s
   L.nodes_off = L.heat_off + align_up(6 * (size_t)n, 256);
   L.slots = n < max_slots ? n : max_slots;
   L.nodes_per_pass = (size_t)4 * (size_t)c->solver_power + 8;
-  L.total = L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t);
+  L.async_off = align_up(L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t), 256);
+  L.total = L.async_off + async_region_bytes();
   return L;
 }
 
@@ -987,14 +1002,23 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
   }
 }
 
+// Shared-memory words of one search: visited table (power of two >= 1.5 * power) + node ring + binary heap.
+// The open list grows by at most 3 per iteration (one pop, at most four pushes), so 3 * power + 8 entries suffice;
+// with the default power of 5000 one search needs 94.5 KB and TWO searches fit one SM.
+static inline size_t solver_arena_words(const pcgrl_config* cfg, int* table_size_out) {
+  int table_size = 1024;
+  while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
+  const size_t heap_words = (size_t)3 * cfg->solver_power + 8;
+  if (table_size_out) *table_size_out = table_size;
+  return (size_t)table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words;
+}
+
 // opt in to the large dynamic shared memory of k_solve (once per power setting; call before multi-threaded enqueue)
 template <int PROB>
 static inline void solver_prepare(const pcgrl_config* cfg) {
   if constexpr (GameOf<PROB>::GAME >= 0) {
-    int table_size = 1024;
-    while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
-    const size_t heap_words = (size_t)4 * cfg->solver_power + 8;
-    const size_t smem = (table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words) * sizeof(uint32_t);
+    int table_size;
+    const size_t smem = solver_arena_words(cfg, &table_size) * sizeof(uint32_t);
     static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
     if (configured[PROB] < smem) {
       cudaFuncSetAttribute(k_solve<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1009,10 +1033,8 @@ static inline void solver_launch(const pcgrl_config* cfg, int32_t* stats, int32_
   if constexpr (GameOf<PROB>::GAME >= 0) {
   if (!q.count) return;
   const SolverLayout lay = solver_layout(cfg, n, max_slots);
-  int table_size = 1024;
-  while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
-  const size_t heap_words = (size_t)4 * cfg->solver_power + 8;
-  const size_t smem = (table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words) * sizeof(uint32_t);
+  int table_size;
+  const size_t smem = solver_arena_words(cfg, &table_size) * sizeof(uint32_t);
   solver_prepare<PROB>(cfg);
   uint32_t* pool = (uint32_t*)((char*)scratch + lay.nodes_off);
   k_solve<PROB><<<4 * lay.slots, 32, smem, s>>>(*cfg, stats, start_stats, maps, q, pool, lay.nodes_per_pass, lay.slots, table_size);

@@ -359,7 +359,7 @@ def main():
                               "ms_per_step": e2e_full_ms_max / K, "api": "pcgrl_step_host mode 0 (every array copied back in full)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": KERNEL_NAMES.get(WORKLOAD["prob"], "k_step_update/k_solve/k_step_finish"),
+                         "traffic": None, "peak_source": peak_src, "kernel": KERNEL_NAMES.get(WORKLOAD["prob"], "k_rollout_async<%s>" % WORKLOAD["prob"]),
                          "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(W, H),
                          "units_per_launch": n * chunk, "avg_launch_ms": avg_launch_s * 1e3},
             "cpu_baseline": cpu_baseline,

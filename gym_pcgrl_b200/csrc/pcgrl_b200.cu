@@ -327,11 +327,22 @@ struct ArenaHead {
   int exhausted;
   int lock;
   int reset_lock[ASYNC_RESET_AREAS];
+  int helper;
 };
 
+// nanosleep may return early (PTX only bounds it from above), so waiting loops pace themselves with the global timer
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void pause_ns(unsigned ns) {
+  const unsigned long long t0 = global_ns();
+  do { __nanosleep(ns); } while (global_ns() - t0 < ns);
+}
 __device__ __forceinline__ void arena_lock(int* lock, int lane) {
   if (lane == 0) {
-    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(256);
+    while (atomicCAS(lock, 0, 1) != 0) pause_ns(1000);
     __threadfence_block();
   }
   __syncwarp();
@@ -443,7 +454,7 @@ __device__ __noinline__ void solve_inline(const pcgrl_config& cfg, const Board& 
       if (mine) async_run_pass<GAME>(cfg, R, G, pass, lane);
     }
     if (lane == 0) {
-      while ((ld_volatile(&G->done_mask) & 0xF) != 0xF) __nanosleep(500);
+      while ((ld_volatile(&G->done_mask) & 0xF) != 0xF) pause_ns(2000);
       __threadfence();
       const volatile int32_t* rr = G->results;
       const int bw = ld_volatile(&G->best_win);
@@ -481,8 +492,8 @@ __device__ __noinline__ void async_help(const pcgrl_config& cfg, const pcgrl_buf
     stop = __shfl_sync(FULL_MASK, stop, 0);
     has = __shfl_sync(FULL_MASK, has, 0);
     if (stop) break;
-    if (!has) { __nanosleep(2000); continue; }
-    if (!arena_trylock(&A.lock, lane)) { __nanosleep(2000); continue; }
+    if (!has) { pause_ns(10000); continue; }
+    if (!arena_trylock(&A.lock, lane)) { pause_ns(10000); continue; }
     int fg = -1, fp = 0;
     for (int g0 = 0; g0 < ngroups && fg < 0; g0 += 32) {
       int g = start + g0 + lane;
@@ -531,7 +542,7 @@ __device__ __noinline__ void async_help(const pcgrl_config& cfg, const pcgrl_buf
       }
     }
     arena_unlock(&A.lock, lane);
-    if (fg < 0) __nanosleep(1000);
+    if (fg < 0) pause_ns(5000);
   }
   (void)H;
 }
@@ -563,6 +574,7 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
   const int ngroups = gridDim.x * ASYNC_WPB;
   if (threadIdx.x == 0) {
     A.lock = 0;
+    A.helper = 0;
     for (int i = 0; i < ASYNC_RESET_AREAS; i++) A.reset_lock[i] = 0;
   }
   __syncthreads();
@@ -676,7 +688,10 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
 #ifdef PCGRL_PROFILE
   AP_MAX(9, clock64() - warp_t0);
 #endif
-  async_help<PROB>(cfg, b, R, hdr, groups, ngroups, n, lane);
+  // one helper per CTA (there is one arena): the first warp that runs out of envs; the others are done
+  int first = 0;
+  if (lane == 0) first = (atomicExch(&A.helper, 1) == 0) ? 1 : 0;
+  if (__shfl_sync(FULL_MASK, first, 0)) async_help<PROB>(cfg, b, R, hdr, groups, ngroups, n, lane);
 }
 
 __global__ void k_seed(uint32_t* rng, const uint32_t* __restrict__ seeds, int n) {

@@ -247,7 +247,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from gym_pcgrl_b200 import HostStepIO
+    from gym_pcgrl_b200 import HostRolloutIO, HostStepIO
     n = WORKLOAD["envs_per_gpu"]
     K, Wm, chunk = args.steps, max(args.warmup, 3), max(1, min(args.chunk, args.steps))
     env = make_env(n, dev, env_offset=rank * n)
@@ -319,13 +319,32 @@ def main():
 
     e2e_s, io, rsum = run_e2e("delta")
     e2e_full_s, io_full, _ = run_e2e("full")
+
+    # ---- e2e_rollout: the open-loop host call (pcgrl_rollout_host): `chunk` steps per call, pinned host actions in,
+    # every step's reward / done plus the final observation back on the host, stream synchronised per call
+    def run_e2e_rollout():
+        rio = HostRolloutIO(env, chunk, with_obs=True, with_info=False)
+        ncalls = max(1, K // chunk)
+        acts_h = torch.from_numpy(host_actions(env, (ncalls + 1) * chunk, n, 199 + rank)).pin_memory()
+        base, stride = acts_h.data_ptr(), acts_h.stride(0) * 4 * chunk
+        rio.struct.actions = base
+        env.rollout_host(rio)
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(ncalls):
+            rio.struct.actions = base + (1 + c) * stride
+            env.rollout_host(rio)
+        barrier()
+        return time.perf_counter() - t0, rio, ncalls * chunk
+
+    e2e_roll_s, rio, roll_steps = run_e2e_rollout()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks
-    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, e2e_full_s * 1e3], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, e2e_full_s * 1e3, e2e_roll_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, e2e_full_ms_max = float(t_dev[0]), float(t_dev[1]), float(t_dev[2])
+    dev_ms_max, e2e_ms_max, e2e_full_ms_max, e2e_roll_ms_max = float(t_dev[0]), float(t_dev[1]), float(t_dev[2]), float(t_dev[3])
 
     if rank == 0:
         total_envs = n * world
@@ -357,6 +376,11 @@ def main():
             "e2e_full_copy": {"value": total_envs * K / (e2e_full_ms_max * 1e-3), "unit": "env-steps/s",
                               "h2d_bytes_per_step": io_full.h2d_bytes * world, "d2h_bytes_per_step": io_full.d2h_bytes * world,
                               "ms_per_step": e2e_full_ms_max / K, "api": "pcgrl_step_host mode 0 (every array copied back in full)"},
+            "e2e_rollout": {"value": total_envs * roll_steps / (e2e_roll_ms_max * 1e-3), "unit": "env-steps/s",
+                            "h2d_bytes_per_step": rio.h2d_bytes * world // chunk, "d2h_bytes_per_step": rio.d2h_bytes * world // chunk,
+                            "ms_per_step": e2e_roll_ms_max / roll_steps, "steps_per_call": chunk,
+                            "api": "pcgrl_rollout_host (open loop: %d steps per call, pinned host actions in; every step's reward + done "
+                                   "and the final map+heatmap+pos back on the host)" % chunk},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": KERNEL_NAMES.get(WORKLOAD["prob"], "k_rollout_async<%s>" % WORKLOAD["prob"]),

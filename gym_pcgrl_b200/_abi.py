@@ -78,6 +78,13 @@ class PcgrlHostIO(C.Structure):
     ]
 
 
+class PcgrlHostRolloutIO(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("map", C.c_void_p),
+        ("heatmap", C.c_void_p), ("pos", C.c_void_p), ("info_stats", C.c_void_p),
+    ]
+
+
 # name -> dtype string, trailing shape as a function of (H, W); leading dim is n
 BUFFER_SPECS = [
     ("map", "uint8", lambda h, w: (h, w)),

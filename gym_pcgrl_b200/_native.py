@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpcgrl_b200.so")
 
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
-           "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map"]
+           "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host"]
 
 _lib = None
 
@@ -52,6 +52,9 @@ def lib():
         L.pcgrl_seed.argtypes = [C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
         L.pcgrl_step_host.restype = C.c_int
         L.pcgrl_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_rollout_host.restype = C.c_int
+        L.pcgrl_rollout_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_void_p]
         L.pcgrl_obs_image.restype = C.c_int
         L.pcgrl_obs_image.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -1122,6 +1122,38 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   return rc;
 }
 
+extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, double* d_reward,
+                                  uint8_t* d_done, pcgrl_host_rollout_io* io, int T, int n, void* stream) {
+  if (!io || !io->actions || !io->reward || !io->done || !d_actions || !d_reward || !d_done)
+    return fail(-1, "NULL rollout io pointer");
+  if (T <= 0) return fail(-1, "T must be > 0");
+  int rc = check_common(cfg, b, n);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t cells = (size_t)cfg->width * cfg->height, tn = (size_t)T * n;
+  const int adim = action_dim_host(cfg->representation);
+  const bool wide = cfg->representation == PCGRL_REP_WIDE;
+  const int32_t* act_ptr = d_actions;
+  static const bool zero_copy = !(getenv("PCGRL_ZERO_COPY_ACTIONS") && atoi(getenv("PCGRL_ZERO_COPY_ACTIONS")) == 0);
+  if (zero_copy) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, io->actions) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      act_ptr = (const int32_t*)attr.devicePointer;
+    else
+      cudaGetLastError();  // pageable memory: not an error
+  }
+  if (act_ptr == d_actions) cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * tn * adim, cudaMemcpyHostToDevice, s);
+  rc = rollout_dispatch(cfg, b, act_ptr, d_reward, d_done, T, n, stream, Staging{nullptr, 0u, 0u, 0, n});
+  if (rc) return rc;
+  cudaMemcpyAsync(io->reward, d_reward, sizeof(double) * tn, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(io->done, d_done, tn, cudaMemcpyDeviceToHost, s);
+  if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
+  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, cells * n, cudaMemcpyDeviceToHost, s);
+  if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
+  if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
+  return cuda_rc(cudaStreamSynchronize(s), "pcgrl_rollout_host");
+}
+
 extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, const uint8_t* pos, void* out, int n,
                                int crop_size, int pad_value, int one_hot, int out_dtype, void* stream) {
   if (!cfg || !maps || !out) return fail(-1, "NULL argument");

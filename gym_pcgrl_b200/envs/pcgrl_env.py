@@ -170,6 +170,18 @@ class BatchedPcgrlEnv:
                                                       _native.stream_ptr(self._dev)), "pcgrl_rollout")
         return reward_out, done_out.view(torch.bool)
 
+    def rollout_host(self, io):
+        """T steps on HOST buffers in one native call (pcgrl_rollout_host, see HostRolloutIO): pinned host
+        actions [T,N(,k)] in; every step's reward / done and the final observation back in pinned host memory."""
+        import torch
+        self.native_config
+        with torch.cuda.device(self._dev):
+            _native.check(_native.lib().pcgrl_rollout_host(
+                C.addressof(self._cfg), C.addressof(self._cbufs), io.d_actions.data_ptr(), io.d_reward.data_ptr(),
+                io.d_done.data_ptr(), C.addressof(io.struct), io.T, self.num_envs, _native.stream_ptr(self._dev)),
+                "pcgrl_rollout_host")
+        return io.reward, io.done
+
     def step_host(self, io):
         """End-to-end step on HOST buffers through pcgrl_step_host (see HostStepIO).  Hot loop: everything
         that does not change between calls is cached, the device guard is only taken when needed."""
@@ -322,6 +334,36 @@ class HostStepIO:
     def invalidate(self):
         """Call after env.reset() / env.step() / env.rollout(): the next step_host re-syncs with a full copy."""
         self.struct.synced = 0
+
+
+class HostRolloutIO:
+    """Pinned host buffers + device staging for ``BatchedPcgrlEnv.rollout_host`` (pcgrl_host_rollout_io)."""
+
+    def __init__(self, env, T, with_obs=True, with_info=False):
+        import torch
+        env._ensure_buffers()
+        n, h, w = env.num_envs, env._prob._height, env._prob._width
+        pin = dict(pin_memory=True)
+        self.T = int(T)
+        ashape = (self.T, n, env._adim) if env._adim > 1 else (self.T, n)
+        self.actions = torch.zeros(ashape, dtype=torch.int32, **pin)
+        self.reward = torch.zeros((self.T, n), dtype=torch.float64, **pin)
+        self.done = torch.zeros((self.T, n), dtype=torch.uint8, **pin)
+        self.map = torch.zeros((n, h, w), dtype=torch.uint8, **pin) if with_obs else None
+        self.heatmap = torch.zeros((n, h, w), dtype=torch.uint8, **pin) if with_obs else None
+        self.pos = torch.zeros((n, 2), dtype=torch.uint8, **pin) if with_obs and env._rep.name != "wide" else None
+        self.info_stats = torch.zeros((n, _abi.MAX_STATS), dtype=torch.int32, **pin) if with_info else None
+        self.d_actions = torch.zeros(ashape, dtype=torch.int32, device=env._dev)
+        self.d_reward = torch.zeros((self.T, n), dtype=torch.float64, device=env._dev)
+        self.d_done = torch.zeros((self.T, n), dtype=torch.uint8, device=env._dev)
+        s = _abi.PcgrlHostRolloutIO()
+        for name in ("actions", "reward", "done", "map", "heatmap", "pos", "info_stats"):
+            t = getattr(self, name)
+            setattr(s, name, None if t is None else t.data_ptr())
+        self.struct = s
+        self.h2d_bytes = self.actions.numel() * 4
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in
+                             (self.reward, self.done, self.map, self.heatmap, self.pos, self.info_stats) if t is not None)
 
 
 class PcgrlEnv:

@@ -188,6 +188,28 @@ int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t*
                     pcgrl_host_io* io, int n, void* stream);
 
 /*
+ * pcgrl_rollout_host: T consecutive PcgrlEnv.step calls on HOST buffers in one call -- the open-loop form of the
+ * reference's rollout loop (README.md:59-72: `for _ in range(T): obs, r, d, info = env.step(action)`) for callers
+ * whose actions do not depend on the observations (random-action rollouts, replays of recorded trajectories).
+ *   actions  in  [T][n][adim] (pinned host memory is read by the device directly, pageable memory is copied),
+ *   reward   out [T][n], done out [T][n]: every step's results,
+ *   map / heatmap / pos / info_stats: the observation after the last step (NULL = not wanted).
+ * d_actions / d_reward / d_done are caller-owned device staging buffers of the same shapes.  Synchronises the
+ * stream before returning.  Solver problems run through the env-asynchronous rollout kernel.
+ */
+typedef struct pcgrl_host_rollout_io {
+  const int32_t* actions; /* in  [T][n][adim]         */
+  double* reward;         /* out [T][n]               */
+  uint8_t* done;          /* out [T][n]               */
+  uint8_t* map;           /* out [n][H][W] or NULL    */
+  uint8_t* heatmap;       /* out [n][H][W] or NULL    */
+  uint8_t* pos;           /* out [n][2]    or NULL    */
+  int32_t* info_stats;    /* out [n][PCGRL_MAX_STATS] or NULL */
+} pcgrl_host_rollout_io;
+int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions, double* d_reward,
+                       uint8_t* d_done, pcgrl_host_rollout_io* io, int T, int n, void* stream);
+
+/*
  * Batched observation / action wrappers (reference: gym_pcgrl/wrappers.py -- "next" row f1 of the scope table).
  *
  * pcgrl_obs_image: Cropped (:163-206) + OneHotEncoding (:67-104) + ToImage (:18-60) in one pass.

@@ -11,7 +11,7 @@ import pytest
 
 import oracle
 import util
-from gym_pcgrl_b200 import PROBLEMS, BatchedPcgrlEnv, HostStepIO, PcgrlEnv, _abi, _native
+from gym_pcgrl_b200 import PROBLEMS, BatchedPcgrlEnv, HostRolloutIO, HostStepIO, PcgrlEnv, _abi, _native
 
 pytestmark = pytest.mark.gpu
 
@@ -314,6 +314,34 @@ def test_rollout_api_equals_stepping(case):
         keys.append("pos")
     for k in keys:
         assert torch.equal(envs[0]._tens[k], envs[1]._tens[k]), k
+    envs[0].check_status()
+
+
+@pytest.mark.parametrize("case", ROLLOUT_CASES, ids=[c[0] for c in ROLLOUT_CASES])
+def test_rollout_host_equals_stepping(case):
+    """pcgrl_rollout_host (T steps, host buffers in / out) == T device-side pcgrl_step calls."""
+    import torch
+    env_id, kwargs, n, T = case
+    envs = []
+    for _ in range(2):
+        env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
+        env.set_rng_states(np.stack([util.randomstate_words(70 + i) for i in range(n)]))
+        env.reset()
+        envs.append(env)
+    wide = env_id.split("-")[1] == "wide"
+    io = HostRolloutIO(envs[0], T, with_obs=True, with_info=True)
+    arng = np.random.RandomState(4)
+    for chunk in range(2):          # two consecutive calls: state carries over
+        acts = np.stack([random_actions(envs[0], arng, n) for _ in range(T)])
+        io.actions[:] = torch.from_numpy(acts).reshape(io.actions.shape)
+        rew, done = envs[0].rollout_host(io)
+        for t in range(T):
+            obs, r, d, _ = envs[1].step(torch.from_numpy(acts[t]).cuda())
+            assert torch.equal(rew[t], r.cpu()) and torch.equal(done[t].bool(), d.cpu()), "%s chunk %d step %d" % (env_id, chunk, t)
+        assert torch.equal(io.map, obs["map"].cpu()) and torch.equal(io.heatmap, obs["heatmap"].cpu())
+        if not wide:
+            assert torch.equal(io.pos, obs["pos"].cpu())
+        assert torch.equal(io.info_stats, envs[1]._tens["info_stats"].cpu())
     envs[0].check_status()
 
 

@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
                                                                      const int32_t* __restrict__ actions, double* reward_out,
                                                                      uint8_t* done_out, int T, int n, AsyncHeader* hdr,
                                                                      AsyncGroup* groups, uint32_t* node_pool,
-                                                                     size_t nodes_per_pass, int table_size) {
+                                                                     size_t nodes_per_pass, int table_size, Staging sg) {
   constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ ArenaHead A;
@@ -668,8 +668,10 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
         for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
         iteration = 0;
         changes = 0;
-      } else if (change > 0) {
-        heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);  // :137
+        if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
+      } else {
+        if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);  // :137
+        if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map, multi);
       }
     }
     rng.finish(lane);
@@ -852,10 +854,10 @@ static GroupStreams* group_streams() {
   return &gs;
 }
 
-// T > 1 steps of a solver problem through the env-asynchronous persistent kernel (k_rollout_async).
+// T >= 1 steps of a solver problem through the env-asynchronous persistent kernel (k_rollout_async).
 template <int PROB>
 static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
-                         uint8_t* done_out, int T, int n, cudaStream_t s) {
+                         uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   if constexpr (GameOf<PROB>::GAME >= 0) {
     int table_size;
     const size_t smem = ((solver_arena_words(cfg, &table_size) + 3) & ~(size_t)3) * sizeof(uint32_t) + ASYNC_RESET_AREAS * sizeof(WarpSmem);
@@ -883,23 +885,24 @@ static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
     cudaMemsetAsync(region, 0, 256 + sizeof(AsyncGroup) * (size_t)grid * ASYNC_WPB, s);
     uint32_t* pool = (uint32_t*)((char*)b->scratch + lay.nodes_off);
     k_rollout_async<PROB><<<grid, 32 * ASYNC_WPB, smem, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, hdr, groups, pool,
-                                                             lay.nodes_per_pass, table_size);
+                                                             lay.nodes_per_pass, table_size, sg);
     return cuda_rc(cudaGetLastError(), "pcgrl_rollout (async) launch");
   } else {
     return fail(-1, "not a solver problem");
   }
 }
 
-// T consecutive PcgrlEnv.step calls of a solver problem.  T == 1 (and the host transport) is one lock-step batch.
-// For T > 1 the actions of all steps are known, so the batch is split into independent env groups, each advancing
-// through its own T steps on its own stream: a search that runs to the iteration cap stalls one group, not the batch.
+// T consecutive PcgrlEnv.step calls of a solver problem.  Default: the env-asynchronous kernel (any T, one launch).
+// PCGRL_SOLVER_ASYNC=0 selects the older multi-launch pipeline kept for comparison: T == 1 is one lock-step batch
+// (update -> k_solve -> finish -> k_solve); for T > 1 the batch is split into independent env groups, each advancing
+// through its own T steps on its own stream, so that a capped search stalls one group, not the batch.
 template <int PROB>
 static int rollout_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                           uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   const int adim = action_dim_host(cfg->representation);
   // PCGRL_SOLVER_ASYNC=0 selects the older stream-group pipeline below (kept for comparison)
   static const bool use_async = !(getenv("PCGRL_SOLVER_ASYNC") && atoi(getenv("PCGRL_SOLVER_ASYNC")) == 0);
-  if (T > 1 && use_async && !sg.base) return rollout_async<PROB>(cfg, b, actions, reward_out, done_out, T, n, s);
+  if (use_async) return rollout_async<PROB>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
   const GroupPlan plan = solver_group_plan(cfg, n);
   if (T == 1 || plan.groups == 1) {
     for (int t = 0; t < T; t++) {

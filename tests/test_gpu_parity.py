@@ -345,6 +345,37 @@ def test_rollout_host_equals_stepping(case):
     envs[0].check_status()
 
 
+def test_lockstep_solver_pipeline_still_matches_oracle():
+    """PCGRL_SOLVER_ASYNC=0 (multi-launch update -> k_solve -> finish pipeline, stream groups for T > 1) stays
+    bit-exact; the switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import oracle, util\n"
+        "from test_gpu_parity import random_actions, t2n\n"
+        "n, T = 160, 24\n"
+        "env = util.host_env('sokoban-wide-v0', {}, num_envs=n, device='cuda')\n"
+        "states = np.stack([util.randomstate_words(900 + i) for i in range(n)])\n"
+        "env.set_rng_states(states); env.reset()\n"
+        "ref = oracle.OracleEnv(env.native_config, n, threads=4); ref.set_rng_states(states); ref.reset()\n"
+        "arng = np.random.RandomState(2)\n"
+        "acts = np.stack([random_actions(env, arng, n) for _ in range(T)])\n"
+        "rew, done = env.rollout(torch.from_numpy(acts[:T // 2]).cuda())\n"
+        "for k in range(T // 2):\n"
+        "    ref.step(acts[k]); assert np.array_equal(t2n(rew[k]), ref['reward']), k\n"
+        "for k in range(T // 2, T):\n"
+        "    _, r, d, _ = env.step(torch.from_numpy(acts[k]).cuda()); ref.step(acts[k])\n"
+        "    assert np.array_equal(t2n(r), ref['reward']) and np.array_equal(t2n(d).astype(np.uint8), ref['done']), k\n"
+        "assert np.array_equal(t2n(env._tens['map']), ref['map'])\n"
+        "assert np.array_equal(t2n(env._tens['stats'])[:, :6], ref['stats'][:, :6])\n"
+        "env.check_status(); print('lockstep ok')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PCGRL_SOLVER_ASYNC="0")
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "lockstep ok" in p.stdout, p.stderr[-2000:]
+
+
 HOST_CASES = [
     ("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.2), 128, 60),
     ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 512, 200),

@@ -1081,7 +1081,16 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
     uint32_t nchg = total_changes - (uint32_t)io->change_base;
     if (nchg > (uint32_t)n) nchg = (uint32_t)n;
     bool overflow = false;
+    const uint32_t PF = 8;  // the records scatter over the 2 x n x H x W host arrays: fetch the target lines ahead
     for (uint32_t k = 0; k < nchg; k++) {
+      if (k + PF < nchg) {
+        const ChangeRecord& f = rec[k + PF];
+        const size_t fe = f.env_kind & 0xffffffu;
+        if (fe < (size_t)n) {
+          if (io->map) __builtin_prefetch(io->map + fe * cells + f.cell, 1);
+          if (io->heatmap) __builtin_prefetch(io->heatmap + fe * cells + (wide ? (size_t)f.cell : (size_t)hpos[2 * fe + 1] * cfg->width + hpos[2 * fe]), 1);
+        }
+      }
       const ChangeRecord r = rec[k];
       const size_t e = r.env_kind & 0xffffffu;
       const uint32_t kind = r.env_kind >> 24;

@@ -5,13 +5,15 @@
 // order of CPython's binary heap under ties, on visited-set semantics and on best-node tie-breaks, so the
 // search itself is reproduced operation by operation; what is B200-specific is the placement:
 //
-//   * envs whose map satisfies the solver precondition are compacted into a work queue by the step kernels;
-//   * one CTA per (queued env, pass): the 4 passes of _run_game run SPECULATIVELY IN PARALLEL, a pass is
-//     cancelled as soon as a pass earlier in the reference's order has won; the last CTA to finish merges
-//     the 4 results in the reference's order;
-//   * binary heap (packed 32-bit entries: priority | node index) and the visited hash table live in shared
-//     memory (~112 KB per CTA); the append-only node store (32 B per node) lives in HBM scratch and stays
-//     L2 resident;
+//   * the per-step API and rollouts run through k_rollout_async (pcgrl_b200.cu): every env warp runs _run_game
+//     inline with the search routines of this file; idle warps take over posted passes;
+//   * pcgrl_reset / pcgrl_get_stats (and PCGRL_SOLVER_ASYNC=0) use the queue form: envs whose map satisfies the solver
+//     precondition are compacted into a work queue, k_solve runs one CTA per (queued env, pass) with the 4 passes of
+//     _run_game SPECULATIVELY IN PARALLEL, a pass is cancelled as soon as a pass earlier in the reference's order has
+//     won, the last CTA to finish merges the 4 results in the reference's order;
+//   * binary heap (packed 32-bit entries: priority | node index), the visited hash table and a ring of the 128 newest
+//     nodes live in shared memory (94.5 KB per search at power 5000: two searches per SM); the append-only node store
+//     (32 B per node) lives in HBM scratch and stays L2 resident;
 //   * states are fixed-width: 5 key words (exactly the information of State.getKey) + 3 payload words.
 //
 // Limits (checked by pcgrl_config_validate / reported through status[0]): width, height <= 14,

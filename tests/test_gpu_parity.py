@@ -345,6 +345,54 @@ def test_rollout_host_equals_stepping(case):
     envs[0].check_status()
 
 
+def _async_fuzz_cases():
+    rs = np.random.RandomState(2024)
+    reps = ["narrow", "turtle", "wide", "narrowcast", "narrowmulti", "turtlecast"]
+    cases = []
+    for k in range(12):
+        prob = ["sokoban", "mdungeon", "ddave"][k % 3]
+        rep = reps[rs.randint(len(reps))]
+        w, h = int(rs.randint(3, 9)), int(rs.randint(3, 9))
+        kwargs = dict(width=w, height=h, change_percentage=float(rs.choice([0.2, 0.5, 0.9])))
+        if prob == "sokoban" and rs.rand() < 0.5:   # levels that keep the solver busy
+            kwargs["probs"] = {"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}
+        if rs.rand() < 0.3:
+            kwargs["solver_power"] = int(rs.choice([50, 700]))
+        n = int(rs.choice([1, 3, 5, 37, 130, 301]))
+        T = int(rs.choice([1, 2, 7, 33]))
+        cases.append(("%s-%s-v0" % (prob, rep), kwargs, n, T, 300 + k))
+    return cases
+
+
+@pytest.mark.parametrize("case", _async_fuzz_cases(), ids=lambda c: "%s-%dx%d-n%d-T%d" % (c[0], c[1]["width"], c[1]["height"], c[2], c[3]))
+def test_async_solver_rollout_fuzz_matches_oracle(case):
+    """k_rollout_async on random small solver configurations (odd batch sizes incl. fewer envs than warps of one CTA,
+    every representation, short / long fragments, small iteration caps): three consecutive rollouts vs the oracle."""
+    import torch
+    env_id, kwargs, n, T, seed = case
+    env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
+    states = np.stack([util.randomstate_words(seed * 1000 + i) for i in range(n)])
+    env.set_rng_states(states)
+    env.reset()
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    ref.set_rng_states(states)
+    ref.reset()
+    S, wide = util.nstats(env_id.split("-")[0]), env_id.split("-")[1] == "wide"
+    arng = np.random.RandomState(seed)
+    for chunk in range(3):
+        acts = np.stack([random_actions(env, arng, n) for _ in range(T)])
+        rew, done = env.rollout(torch.from_numpy(acts).cuda())
+        for k in range(T):
+            ref.step(acts[k])
+            ctx = "%s chunk %d step %d" % (env_id, chunk, k)
+            np.testing.assert_array_equal(t2n(rew[k]), ref["reward"], err_msg=ctx + " reward")
+            np.testing.assert_array_equal(t2n(done[k]).astype(np.uint8), ref["done"], err_msg=ctx + " done")
+        assert_state_equal(env, ref, S, "%s chunk %d" % (env_id, chunk), wide)
+        np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, :S], ref["info_stats"][:, :S])
+    np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"], err_msg="rng state")
+    env.check_status()
+
+
 def test_lockstep_solver_pipeline_still_matches_oracle():
     """PCGRL_SOLVER_ASYNC=0 (multi-launch update -> k_solve -> finish pipeline, stream groups for T > 1) stays
     bit-exact; the switch is read once per process, hence the subprocess."""

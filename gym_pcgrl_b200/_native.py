@@ -10,7 +10,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpcgrl_b200.so")
+LIB_PATH = os.environ.get("PCGRL_B200_LIB") or os.path.join(_HERE, "csrc", "libpcgrl_b200.so")  # override: A/B builds
 
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",

@@ -1145,16 +1145,10 @@ extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* 
   const size_t cells = (size_t)cfg->width * cfg->height, tn = (size_t)T * n;
   const int adim = action_dim_host(cfg->representation);
   const bool wide = cfg->representation == PCGRL_REP_WIDE;
+  // one bulk H2D copy of all T action rows (a T-step kernel that read pinned host memory directly would pay a PCIe
+  // round trip per env-step; the per-step call does read them in place, see pcgrl_step_host)
+  cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * tn * adim, cudaMemcpyHostToDevice, s);
   const int32_t* act_ptr = d_actions;
-  static const bool zero_copy = !(getenv("PCGRL_ZERO_COPY_ACTIONS") && atoi(getenv("PCGRL_ZERO_COPY_ACTIONS")) == 0);
-  if (zero_copy) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, io->actions) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-      act_ptr = (const int32_t*)attr.devicePointer;
-    else
-      cudaGetLastError();  // pageable memory: not an error
-  }
-  if (act_ptr == d_actions) cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * tn * adim, cudaMemcpyHostToDevice, s);
   rc = rollout_dispatch(cfg, b, act_ptr, d_reward, d_done, T, n, stream, Staging{nullptr, 0u, 0u, 0, n});
   if (rc) return rc;
   cudaMemcpyAsync(io->reward, d_reward, sizeof(double) * tn, cudaMemcpyDeviceToHost, s);

@@ -50,7 +50,9 @@ struct SolverLayout {
 
 // k_rollout_async bookkeeping (see pcgrl_b200.cu): one header + one 128-byte request slot per env warp
 #define ASYNC_MAX_CTAS 512
-#define ASYNC_WPB 4
+#ifndef ASYNC_WPB
+#define ASYNC_WPB 4 /* env warps per CTA (= per search arena) */
+#endif
 struct AsyncHeader { int32_t work, envs_done, posted, pad; };
 struct __align__(16) AsyncGroup {
   int32_t env;         // env whose map (in HBM) is being solved

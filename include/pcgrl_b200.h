@@ -191,7 +191,7 @@ int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t*
  * pcgrl_rollout_host: T consecutive PcgrlEnv.step calls on HOST buffers in one call -- the open-loop form of the
  * reference's rollout loop (README.md:59-72: `for _ in range(T): obs, r, d, info = env.step(action)`) for callers
  * whose actions do not depend on the observations (random-action rollouts, replays of recorded trajectories).
- *   actions  in  [T][n][adim] (pinned host memory is read by the device directly, pageable memory is copied),
+ *   actions  in  [T][n][adim] (copied to d_actions in one H2D transfer; pin the buffer for full PCIe speed),
  *   reward   out [T][n], done out [T][n]: every step's results,
  *   map / heatmap / pos / info_stats: the observation after the last step (NULL = not wanted).
  * d_actions / d_reward / d_done are caller-owned device staging buffers of the same shapes.  Synchronises the

@@ -42,8 +42,9 @@ def main():
             f.write(json.dumps(d) + "\n")
             f.flush()
             rows.append(d)
-            print("%-28s value %.3e  e2e %.3e  cpu(port,%d cores) %.3e  roofline %.4f" % (
-                name, d["value"], d["e2e"]["value"], d["cpu_baseline"]["cores"], d["cpu_baseline"]["value"], d["roofline"]["frac"]), flush=True)
+            print("%-28s value %.3e  e2e %.3e  e2e_rollout %.3e  cpu(port,%d cores) %.3e  roofline %.4f" % (
+                name, d["value"], d["e2e"]["value"], d.get("e2e_rollout", {}).get("value", float("nan")),
+                d["cpu_baseline"]["cores"], d["cpu_baseline"]["value"], d["roofline"]["frac"]), flush=True)
 
 
 if __name__ == "__main__":

@@ -73,6 +73,34 @@ def test_config_freeze_matches_header_layout():
     assert C.sizeof(_abi.PcgrlBuffers) == 17 * 8
 
 
+def test_ctypes_mirrors_match_the_c_compiler(tmp_path):
+    """Every struct of include/pcgrl_b200.h: sizeof and each field offset as gcc lays them out == the ctypes mirror."""
+    import subprocess
+    structs = {"pcgrl_config": _abi.PcgrlConfig, "pcgrl_buffers": _abi.PcgrlBuffers, "pcgrl_host_io": _abi.PcgrlHostIO,
+               "pcgrl_host_rollout_io": _abi.PcgrlHostRolloutIO}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pcgrl_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    seen = 0
+    for ln in out:
+        if not ln.strip():
+            continue
+        cname, field, value = ln.split()
+        ct = structs[cname]
+        expect = C.sizeof(ct) if field == "sizeof" else getattr(ct, field).offset
+        assert int(value) == expect, (cname, field, value, expect)
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
+
+
 def test_native_library_builds_loads_and_exports_every_symbol():
     native_build.build()
     lib = _native.lib()

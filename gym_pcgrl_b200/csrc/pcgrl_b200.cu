@@ -77,8 +77,12 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   bool prof_reset = false, prof_changed = false;
 #endif
 
-  for (int t = 0; t < T; t++) {
-    const int32_t* act = actions + ((size_t)t * n + e) * adim;
+  // per-step pointers advance by one row of the [T][n] arrays (no 64-bit index arithmetic inside the loop)
+  const int32_t* act = actions + (size_t)e * adim;
+  const size_t act_stride = (size_t)n * adim;
+  double* rew_row = reward_out ? reward_out + e : nullptr;
+  uint8_t* done_row = done_out ? done_out + e : nullptr;
+  for (int t = 0; t < T; t++, act += act_stride) {
     iteration++;  // pcgrl_env.py:130
     int old[NS];
 #pragma unroll
@@ -101,12 +105,11 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
                       iteration >= cfg.max_iterations;                            // :143
     if (lane == 0) {
-      b.reward[e] = reward;
-      b.done[e] = done ? 1 : 0;
-      if (reward_out) reward_out[(size_t)t * n + e] = reward;
-      if (done_out) done_out[(size_t)t * n + e] = done ? 1 : 0;
+      if (rew_row) { *rew_row = reward; rew_row += n; }
+      if (done_row) { *done_row = done ? 1 : 0; done_row += n; }
     }
-    if (t == T - 1) {
+    if (t == T - 1) {  // the env's own reward / done / info buffers describe the last step only
+      if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
       store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
       if (PROB == PCGRL_PROB_BINARY && lane == NS)  // info["path-imp"] (binary_prob.py:137), before any auto-reset
         b.info_stats[(size_t)e * PCGRL_MAX_STATS + NS] = st[1] - start[1];

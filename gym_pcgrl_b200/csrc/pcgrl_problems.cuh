@@ -97,8 +97,19 @@ __device__ __forceinline__ double problem_reward(const pcgrl_config& cfg, const 
   const double* w = cfg.reward_weight;
   const int32_t* ip = cfg.iparam;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
-  if (PROB == PCGRL_PROB_BINARY)  // binary_prob.py:98-106
-    return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], INF, INF) * w[1];
+  if (PROB == PCGRL_PROB_BINARY) {  // binary_prob.py:98-106
+    // get_range_reward on integers is exact in int32: (regions, 1, 1) follows helper.py:366-376 case by case and
+    // (path, inf, inf) always takes the second case, min(new, inf) - min(old, inf) = new - old; the two products and
+    // the sum are then the same fp64 operations as in the reference.
+    const int nv = n[0], ov = o[0];
+    int r0;
+    if (nv == 1 && ov == 1) r0 = 0;
+    else if (ov <= 1 && nv <= 1) r0 = min(nv, 1) - min(ov, 1);
+    else if (ov >= 1 && nv >= 1) r0 = max(ov, 1) - max(nv, 1);
+    else if (nv > 1 && ov < 1) r0 = 1 - nv + ov - 1;
+    else r0 = 1 - ov + nv - 1;  // nv < 1 && ov > 1
+    return (double)r0 * w[0] + (double)(n[1] - o[1]) * w[1];
+  }
   if (PROB == PCGRL_PROB_ZELDA)  // zelda_prob.py:124-142
     return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 1, 1) * w[1] +
            range_reward(n[2], o[2], 1, 1) * w[2] + range_reward(n[3], o[3], 2, ip[0]) * w[3] +

@@ -295,6 +295,13 @@ __device__ __forceinline__ bool first_cell(uint32_t m, int& row, int& col) {
 
 __device__ __forceinline__ uint32_t cell_bit(int row, int col, int lane) { return (lane == row) ? (1u << col) : 0u; }
 
+// the same cell as a one-bit board, without materialising (row, col): the first non-empty row keeps its lowest bit
+__device__ __forceinline__ bool first_cell_seed(uint32_t m, int lane, uint32_t& seed) {
+  const uint32_t rows = __ballot_sync(FULL_MASK, m != 0u);
+  seed = (rows != 0u && lane == __ffs(rows) - 1) ? (m & (0u - m)) : 0u;
+  return rows != 0u;
+}
+
 // BFS from `seed` over `pass` (G/helper.py:222-237 run_dikjstra): returns the eccentricity of the seed inside
 // its component, the visited set and the last non-empty frontier (the cells at maximum distance).
 __device__ __forceinline__ int bfs_ecc(uint32_t seed, uint32_t pass, uint32_t& visited, uint32_t& last) {
@@ -349,9 +356,9 @@ __device__ __forceinline__ int count_regions(uint32_t pass, int lane) {
   const uint32_t iso = pass & ~neighbours(pass, lane);  // single-cell components, all at once
   int regions = popc_all(iso);
   uint32_t remaining = pass & ~iso;
-  int row, col;
-  while (first_cell(remaining, row, col)) {
-    remaining &= ~flood(cell_bit(row, col, lane), remaining);
+  uint32_t seed;
+  while (first_cell_seed(remaining, lane, seed)) {
+    remaining &= ~flood(seed, remaining);
     regions++;
   }
   return regions;
@@ -384,16 +391,16 @@ __device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane
   const int ndom = popc_all(hd) + popc_all(vd);
   int regions = popc_all(iso) + ndom, best = ndom > 0 ? 1 : 0;
   uint32_t remaining = pass & ~iso & ~dominoes;
-  int row, col;
-  while (first_cell(remaining, row, col)) {
+  uint32_t seed;
+  while (first_cell_seed(remaining, lane, seed)) {
     uint32_t visited, last;
-    const int d1 = bfs_ecc(cell_bit(row, col, lane), remaining, visited, last);
+    const int d1 = bfs_ecc(seed, remaining, visited, last);
     remaining &= ~visited;
     regions++;
     if (2 * d1 > best) {
-      first_cell(last, row, col);
+      first_cell_seed(last, lane, seed);
       uint32_t v2, l2;
-      const int d2 = bfs_ecc(cell_bit(row, col, lane), visited, v2, l2);
+      const int d2 = bfs_ecc(seed, visited, v2, l2);
       best = max(best, d2);
     }
   }

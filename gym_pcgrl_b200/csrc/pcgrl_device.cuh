@@ -126,6 +126,25 @@ struct WarpRng {
     do { v = next(lane) & mask; } while (v > rng);
     return (int)v;
   }
+  // x = randint(nx); y = randint(ny) -- the cursor draw of the narrow representations (narrow_rep.py:105-106).
+  // Fast path: both 32-bit draws sit in the cached window and both are accepted at the first attempt; anything else
+  // (rejection, window refill, twist, n == 1) replays the two generic calls from the unchanged position.
+  __device__ __forceinline__ void randint2(int nx, int ny, int lane, int& x, int& y) {
+    const uint32_t rx = (uint32_t)(nx - 1), ry = (uint32_t)(ny - 1);
+    const int off = pos - base;
+    if (rx != 0u && ry != 0u && off >= 0 && off <= 30 && pos <= 622) {
+      const uint32_t a = __shfl_sync(FULL_MASK, cache, off) & (0xffffffffu >> __clz(rx));
+      const uint32_t b = __shfl_sync(FULL_MASK, cache, off + 1) & (0xffffffffu >> __clz(ry));
+      if (a <= rx && b <= ry) {
+        x = (int)a; y = (int)b;
+        pos += 2;
+        dirty = true;
+        return;
+      }
+    }
+    x = randint(nx, lane);
+    y = randint(ny, lane);
+  }
   // `count` (<= 512) consecutive tempered draws into shared memory
   __device__ __forceinline__ void fill(uint32_t* buf, int count, int lane) {
     int filled = 0;

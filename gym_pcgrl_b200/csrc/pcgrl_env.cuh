@@ -129,8 +129,7 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
   tile = newt < 0 ? 0 : newt;
   if (rep == PCGRL_REP_NARROW || rep == PCGRL_REP_NARROWCAST || rep == PCGRL_REP_NARROWMULTI) {
     if (cfg.flags & PCGRL_FLAG_RANDOM_TILE) {
-      x = rng.randint(W, lane);
-      y = rng.randint(H, lane);
+      rng.randint2(W, H, lane, x, y);
     } else {
       x += 1;
       if (x >= W) { x = 0; y += 1; if (y >= H) y = 0; }

@@ -326,7 +326,8 @@ __device__ __forceinline__ bool first_cell_seed(uint32_t m, int lane, uint32_t& 
 __device__ __forceinline__ int bfs_ecc(uint32_t seed, uint32_t pass, uint32_t& visited, uint32_t& last) {
   uint32_t f = seed, vis = seed;
   int d = 0;
-  while (true) {  // two waves per termination vote; the tail decides whether the first of the two was the last
+  while (true) {  // two waves per termination vote (the tail decides whether the first of the two was the last);
+                  // the body is written out twice so that the loop-carried boards need no register moves
     const uint32_t n1 = dilate(f) & pass & ~vis;
     const uint32_t v1 = vis | n1;
     const uint32_t n2 = dilate(n1) & pass & ~v1;
@@ -334,9 +335,18 @@ __device__ __forceinline__ int bfs_ecc(uint32_t seed, uint32_t pass, uint32_t& v
       if (__any_sync(FULL_MASK, n1 != 0u)) { vis = v1; f = n1; d += 1; }
       break;
     }
-    vis = v1 | n2;
-    f = n2;
-    d += 2;
+    const uint32_t v2 = v1 | n2;
+    const uint32_t n3 = dilate(n2) & pass & ~v2;
+    const uint32_t v3 = v2 | n3;
+    const uint32_t n4 = dilate(n3) & pass & ~v3;
+    if (!__any_sync(FULL_MASK, n4 != 0u)) {
+      if (__any_sync(FULL_MASK, n3 != 0u)) { vis = v3; f = n3; d += 3; }
+      else { vis = v2; f = n2; d += 2; }
+      break;
+    }
+    vis = v3 | n4;
+    f = n4;
+    d += 4;
   }
   visited = vis;
   last = f;
@@ -346,10 +356,11 @@ __device__ __forceinline__ int bfs_ecc(uint32_t seed, uint32_t pass, uint32_t& v
 // flood fill without levels (component mask of seed)
 __device__ __forceinline__ uint32_t flood(uint32_t seed, uint32_t pass) {
   uint32_t v = seed;
-  while (true) {
-    const uint32_t n = dilate(v) & pass;
-    if (!__any_sync(FULL_MASK, n != v)) break;
-    v = n;
+  while (true) {  // monotone: two dilations per vote, a fixed point of the second is a fixed point
+    const uint32_t n1 = dilate(v) & pass;
+    const uint32_t n2 = dilate(n1) & pass;
+    v = n2;
+    if (!__any_sync(FULL_MASK, n2 != n1)) break;
   }
   return v;
 }

@@ -371,13 +371,17 @@ __device__ __forceinline__ int bfs_dist_to(uint32_t seed, uint32_t target, uint3
   uint32_t f = seed & pass, visited = f;
   int d = 0;
   if (!__any_sync(FULL_MASK, f != 0u)) return -1;
-  while (true) {
-    if (__any_sync(FULL_MASK, (f & target) != 0u)) return d;
-    const uint32_t n = dilate(f) & pass & ~visited;
-    if (!__any_sync(FULL_MASK, n != 0u)) return -1;
-    visited |= n;
-    f = n;
-    d++;
+  if (__any_sync(FULL_MASK, (f & target) != 0u)) return 0;
+  while (true) {  // two waves per pair of votes: "did either wave reach the target", "is the second wave empty"
+    const uint32_t n1 = dilate(f) & pass & ~visited;
+    const uint32_t v1 = visited | n1;
+    const uint32_t n2 = dilate(n1) & pass & ~v1;
+    if (__any_sync(FULL_MASK, ((n1 | n2) & target) != 0u))
+      return __any_sync(FULL_MASK, (n1 & target) != 0u) ? d + 1 : d + 2;
+    if (!__any_sync(FULL_MASK, n2 != 0u)) return -1;  // n1 empty implies n2 empty; neither touched the target
+    visited = v1 | n2;
+    f = n2;
+    d += 2;
   }
 }
 

@@ -38,13 +38,18 @@ __device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cf
         const uint32_t pass = type_mask<0xE5u>(b, rm);
         uint32_t f = player, visited = player;
         int d = 0, min_dist = W * H;
-        while (true) {
-          const uint32_t nx = dilate(f) & pass & ~visited;
-          if (!__any_sync(FULL_MASK, nx != 0u)) break;
-          visited |= nx;
-          f = nx;
-          d++;
-          if (__any_sync(FULL_MASK, (f & enemies) != 0u)) { min_dist = min(min_dist, d); break; }
+        while (true) {  // two waves per pair of votes
+          const uint32_t n1 = dilate(f) & pass & ~visited;
+          const uint32_t v1 = visited | n1;
+          const uint32_t n2 = dilate(n1) & pass & ~v1;
+          if (__any_sync(FULL_MASK, ((n1 | n2) & enemies) != 0u)) {
+            min_dist = __any_sync(FULL_MASK, (n1 & enemies) != 0u) ? d + 1 : d + 2;
+            break;
+          }
+          if (!__any_sync(FULL_MASK, n2 != 0u)) break;  // frontier ran out without touching an enemy
+          visited = v1 | n2;
+          f = n2;
+          d += 2;
         }
         st[5] = min_dist;
       }

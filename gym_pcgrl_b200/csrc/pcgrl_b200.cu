@@ -77,12 +77,10 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   bool prof_reset = false, prof_changed = false;
 #endif
 
-  // per-step pointers advance by one row of the [T][n] arrays (no 64-bit index arithmetic inside the loop)
-  const int32_t* act = actions + (size_t)e * adim;
-  const size_t act_stride = (size_t)n * adim;
-  double* rew_row = reward_out ? reward_out + e : nullptr;
-  uint8_t* done_row = done_out ? done_out + e : nullptr;
-  for (int t = 0; t < T; t++, act += act_stride) {
+  // one 32-bit row offset (t * n + e) is the only loop-carried index (rollout_dispatch checks T * n * adim < 2^31)
+  uint32_t row = (uint32_t)e;
+  for (int t = 0; t < T; t++, row += (uint32_t)n) {
+    const int32_t* act = actions + (size_t)(row * (uint32_t)adim);
     iteration++;  // pcgrl_env.py:130
     int old[NS];
 #pragma unroll
@@ -105,8 +103,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
                       iteration >= cfg.max_iterations;                            // :143
     if (lane == 0) {
-      if (rew_row) { *rew_row = reward; rew_row += n; }
-      if (done_row) { *done_row = done ? 1 : 0; done_row += n; }
+      if (reward_out) reward_out[row] = reward;
+      if (done_out) done_out[row] = done ? 1 : 0;
     }
     if (t == T - 1) {  // the env's own reward / done / info buffers describe the last step only
       if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
@@ -958,6 +956,8 @@ static int rollout_dispatch(const pcgrl_config* cfg, const pcgrl_buffers* b, con
   if (rc) return rc;
   if (!actions) return fail(-1, "actions is NULL");
   if (T <= 0) return fail(-1, "T must be > 0");
+  if ((unsigned long long)T * (unsigned long long)n * (unsigned long long)action_dim_host(cfg->representation) >= (1ull << 31))
+    return fail(-1, "T * n * action_dim must be < 2^31 per call: split the rollout");
   cudaStream_t s = (cudaStream_t)stream;
   switch (cfg->problem) {
     case PCGRL_PROB_BINARY: return rollout_fused<PCGRL_PROB_BINARY>(cfg, b, actions, reward_out, done_out, T, n, s, sg);

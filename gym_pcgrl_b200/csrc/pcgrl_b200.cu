@@ -862,15 +862,15 @@ static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
   if constexpr (GameOf<PROB>::GAME >= 0) {
     int table_size;
     const size_t smem = ((solver_arena_words(cfg, &table_size) + 3) & ~(size_t)3) * sizeof(uint32_t) + ASYNC_RESET_AREAS * sizeof(WarpSmem);
-    static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
-    if (configured[PROB] < smem) {
-      cudaError_t ce = cudaFuncSetAttribute(k_rollout_async<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (ce != cudaSuccess) return cuda_rc(ce, "k_rollout_async shared memory opt-in");
-      configured[PROB] = smem;
-    }
-    static thread_local int sm_dev = -1, sm_count = 0;
+    static size_t configured[SOLVER_MAX_DEVICES][PCGRL_NUM_PROBLEMS] = {};  // the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
+    if (dev < 0 || dev >= SOLVER_MAX_DEVICES || configured[dev][PROB] < smem) {
+      cudaError_t ce = cudaFuncSetAttribute(k_rollout_async<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (ce != cudaSuccess) return cuda_rc(ce, "k_rollout_async shared memory opt-in");
+      if (dev >= 0 && dev < SOLVER_MAX_DEVICES) configured[dev][PROB] = smem;
+    }
+    static thread_local int sm_dev = -1, sm_count = 0;
     if (sm_dev != dev) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); sm_dev = dev; }
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_async<PROB>, 32 * ASYNC_WPB, smem);

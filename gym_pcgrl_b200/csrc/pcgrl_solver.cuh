@@ -29,6 +29,7 @@ enum { SOLVE_FOR_STEP = 0, SOLVE_FOR_RESET = 1, SOLVE_STATS_ONLY = 2 };
 enum { GAME_SOKOBAN = 0, GAME_DDAVE = 1, GAME_MDUNGEON = 2 };
 
 #define SOLVER_MAX_SLOTS 148
+#define SOLVER_MAX_DEVICES 64
 #define SOLVER_NODE_WORDS 8
 #define SOLVER_PRIO_BIAS 2048
 
@@ -1023,10 +1024,12 @@ static inline void solver_prepare(const pcgrl_config* cfg) {
   if constexpr (GameOf<PROB>::GAME >= 0) {
     int table_size;
     const size_t smem = solver_arena_words(cfg, &table_size) * sizeof(uint32_t);
-    static size_t configured[PCGRL_NUM_PROBLEMS] = {0, 0, 0, 0, 0};
-    if (configured[PROB] < smem) {
+    static size_t configured[SOLVER_MAX_DEVICES][PCGRL_NUM_PROBLEMS] = {};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= SOLVER_MAX_DEVICES || configured[dev][PROB] < smem) {
       cudaFuncSetAttribute(k_solve<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured[PROB] = smem;
+      if (dev >= 0 && dev < SOLVER_MAX_DEVICES) configured[dev][PROB] = smem;
     }
   }
 }

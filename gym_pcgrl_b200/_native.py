@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("PCGRL_B200_LIB") or os.path.join(_HERE, "csrc", "libp
 
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
-           "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host"]
+           "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host",
+           "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats"]
 
 _lib = None
 
@@ -55,6 +56,11 @@ def lib():
         L.pcgrl_rollout_host.restype = C.c_int
         L.pcgrl_rollout_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int, C.c_void_p]
+        L.pcgrl_smb_scratch_bytes.restype = C.c_size_t
+        L.pcgrl_smb_scratch_bytes.argtypes = [C.c_int, C.c_int]
+        L.pcgrl_smb_get_stats.restype = C.c_int
+        L.pcgrl_smb_get_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
         L.pcgrl_obs_image.restype = C.c_int
         L.pcgrl_obs_image.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -112,6 +118,25 @@ def alloc_buffers(cfg, n, device):
         setattr(b, name, tens[name].data_ptr())
     b.scratch, b.scratch_bytes, b.status = tens["scratch"].data_ptr(), nbytes, tens["status"].data_ptr()
     return tens, b
+
+
+SMB_STAT_NAMES = ["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "jumps", "jumps-dist", "dist-win"]
+
+
+def smb_get_stats(maps, solver_power=10000):
+    """Stand-alone batched SMBProblem.get_stats (pcgrl_smb_get_stats): uint8 CUDA [N,H,W] -> int32 [N, MAX_STATS]
+    (columns SMB_STAT_NAMES).  smb_prob.py:126-148; the batched smb environment itself is not implemented yet."""
+    import torch
+    dev = require_cuda(maps.device)
+    maps = maps.to(torch.uint8).contiguous()
+    n, h, w = maps.shape
+    out = torch.zeros((n, _abi.MAX_STATS), dtype=torch.int32, device=dev)
+    nbytes = int(lib().pcgrl_smb_scratch_bytes(n, int(solver_power)))
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().pcgrl_smb_get_stats(maps.data_ptr(), out.data_ptr(), n, w, h, int(solver_power), scratch.data_ptr(),
+                                        nbytes, stream_ptr(dev)), "pcgrl_smb_get_stats")
+    return out
 
 
 def get_stats(prob, maps):

@@ -18,6 +18,7 @@
 #include "pcgrl_env.cuh"
 #include "pcgrl_solver.cuh"
 #include "pcgrl_wrappers.cuh"
+#include "pcgrl_smb.cuh"
 
 using namespace pcgrl;
 
@@ -1161,6 +1162,27 @@ extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* 
   if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
   if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
   return cuda_rc(cudaStreamSynchronize(s), "pcgrl_rollout_host");
+}
+
+static inline int smb_concurrency(int n) { return n < SMB_MAX_CONCURRENCY ? n : SMB_MAX_CONCURRENCY; }
+
+extern "C" size_t pcgrl_smb_scratch_bytes(int n, int solver_power) {
+  if (n <= 0 || solver_power < 1 || solver_power > 16000) return 0;
+  return sizeof(uint32_t) * pcgrl_smb::workspace_words(solver_power) * (size_t)smb_concurrency(n);
+}
+
+extern "C" int pcgrl_smb_get_stats(const uint8_t* maps, int32_t* stats_out, int n, int width, int height, int solver_power,
+                                   void* scratch, size_t scratch_bytes, void* stream) {
+  if (!maps || !stats_out || !scratch) return fail(-1, "NULL argument");
+  if (n <= 0) return fail(-1, "n must be > 0");
+  if (width < 1 || width > pcgrl_smb::MAX_W || height < 3 || height > pcgrl_smb::MAX_H)
+    return fail(-1, "smb: 1 <= width <= 122 and 3 <= height <= 16");
+  if (solver_power < 1 || solver_power > 16000) return fail(-1, "smb: solver_power must be in [1, 16000]");
+  if (scratch_bytes < pcgrl_smb_scratch_bytes(n, solver_power)) return fail(-1, "scratch buffer too small: see pcgrl_smb_scratch_bytes()");
+  const int conc = smb_concurrency(n);
+  pcgrl_smb::k_smb_get_stats<<<(conc + SMB_THREADS - 1) / SMB_THREADS, SMB_THREADS, 0, (cudaStream_t)stream>>>(
+      maps, stats_out, n, width, height, solver_power, (uint32_t*)scratch, conc, PCGRL_MAX_STATS);
+  return cuda_rc(cudaGetLastError(), "pcgrl_smb_get_stats launch");
 }
 
 extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, const uint8_t* pos, void* out, int n,

@@ -224,6 +224,19 @@ int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, const uint8_t*
 int pcgrl_action_map(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* flat_actions,
                      int32_t* actions_out, int n, void* stream);
 
+/*
+ * smb (first piece): the stand-alone SMBProblem.get_stats operator
+ * (gym_pcgrl/envs/probs/smb_prob.py:126-148 incl. the A* play-through of _run_game :95-124 and probs/smb/engine.py).
+ *   maps [n][height][width] u8 (tiles: empty, solid, enemy, brick, question, coin, tube) ->
+ *   stats_out [n][PCGRL_MAX_STATS] i32: dist-floor, disjoint-tubes, enemies, empty, noise, jumps, jumps-dist, dist-win.
+ * One thread per map; scratch = pcgrl_smb_scratch_bytes(n, solver_power) bytes of caller-owned device memory
+ * (open lists, node stores and visited bitmaps of the searches in flight).  width <= 122, height <= 16,
+ * 1 <= solver_power <= 16000.  The batched smb environment (reset / step) is not implemented yet.
+ */
+size_t pcgrl_smb_scratch_bytes(int n, int solver_power);
+int pcgrl_smb_get_stats(const uint8_t* maps, int32_t* stats_out, int n, int width, int height, int solver_power,
+                        void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

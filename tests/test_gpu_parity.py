@@ -580,3 +580,30 @@ def test_step_is_cuda_graph_capturable(env_id):
         assert torch.equal(envs[0]._tens["reward"], r) and torch.equal(envs[0]._tens["done"].bool(), d), "step %d" % t
     assert torch.equal(envs[0]._tens["map"], envs[1]._tens["map"])
     assert torch.equal(envs[0]._tens["stats"], envs[1]._tens["stats"])
+
+
+def test_smb_get_stats_matches_reference_golden_and_oracle(capsys):
+    """pcgrl_smb_get_stats (one thread per map, A* play-through inline) against the reference's golden vectors and
+    against the smb oracle on a batch larger than the 2048 searches in flight (grid-stride path)."""
+    import time
+    import torch
+    from oracle import smb as smb_oracle
+    d = np.load(os.path.join(util.GOLDEN, "stats_smb.npz"))
+    power = int(d["solver_power"][0])
+    k = 0
+    while "maps_%d" % k in d.files:
+        got = _native.smb_get_stats(torch.from_numpy(d["maps_%d" % k]).cuda(), power)
+        np.testing.assert_array_equal(t2n(got)[:, :8], d["stats_%d" % k], err_msg="group %d" % k)
+        k += 1
+    rs = np.random.RandomState(11)
+    maps = rs.choice(7, size=(3000, 14, 114), p=[0.75, 0.15, 0.02, 0.02, 0.02, 0.02, 0.02]).astype(np.uint8)
+    dm = torch.from_numpy(maps).cuda()
+    got = _native.smb_get_stats(dm, power)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = _native.smb_get_stats(dm, power)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    np.testing.assert_array_equal(t2n(got)[:, :8], smb_oracle.get_stats(maps, power))
+    with capsys.disabled():
+        print("\n[smb] pcgrl_smb_get_stats: %d maps 114x14 in %.2f ms (%.3e maps/s)" % (len(maps), dt * 1e3, len(maps) / dt))

@@ -30,12 +30,12 @@ def main():
         return rs.choice(len(p), size=(n, h, w), p=p).astype(np.uint8)
 
     default = [0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02]
-    g0 = maps_from_probs(16, 114, 14, default)
+    g0 = maps_from_probs(40, 114, 14, default)
     groups.append((114, 14, g0))
     hard = np.concatenate([
-        maps_from_probs(6, 114, 14, [0.55, 0.3, 0.02, 0.05, 0.02, 0.02, 0.04]),       # walls: A*(1) and A*(0) both matter
-        maps_from_probs(4, 114, 14, [0.35, 0.5, 0.02, 0.05, 0.02, 0.02, 0.04]),       # mostly blocked
-        maps_from_probs(4, 114, 14, [0.96, 0.005, 0.01, 0.005, 0.005, 0.01, 0.005]),  # nearly empty: pits, few jumps
+        maps_from_probs(16, 114, 14, [0.55, 0.3, 0.02, 0.05, 0.02, 0.02, 0.04]),       # walls: A*(1) and A*(0) both matter
+        maps_from_probs(8, 114, 14, [0.35, 0.5, 0.02, 0.05, 0.02, 0.02, 0.04]),       # mostly blocked
+        maps_from_probs(12, 114, 14, [0.96, 0.005, 0.01, 0.005, 0.005, 0.01, 0.005]),  # nearly empty: pits, few jumps
     ])
     groups.append((114, 14, hard))
     crafted = np.zeros((6, 14, 114), dtype=np.uint8)
@@ -51,13 +51,14 @@ def main():
     crafted[5][6, 81] = 2                               # bricks, tubes, enemies
     groups.append((114, 14, crafted))
     seq = [g0[0].copy()]                                # single-tile edits of one map: what an episode looks like
-    for _ in range(15):
+    for _ in range(39):
         m = seq[-1].copy()
         m[rs.randint(14), rs.randint(114)] = rs.randint(7)
         seq.append(m)
     groups.append((114, 14, np.stack(seq)))
-    groups.append((30, 10, maps_from_probs(10, 30, 10, default)))      # other sizes through adjust_param
-    groups.append((20, 8, maps_from_probs(8, 20, 8, [0.6, 0.25, 0.02, 0.05, 0.02, 0.02, 0.04])))
+    groups.append((30, 10, maps_from_probs(24, 30, 10, default)))
+    groups.append((122, 16, maps_from_probs(12, 122, 16, [0.7, 0.15, 0.02, 0.05, 0.02, 0.02, 0.04])))   # the device operator's size limit
+    groups.append((20, 8, maps_from_probs(24, 20, 8, [0.6, 0.25, 0.02, 0.05, 0.02, 0.02, 0.04])))
 
     out = {}
     for gi, (w, h, maps) in enumerate(groups):

@@ -28,7 +28,7 @@ def test_smb_get_stats_matches_reference_golden():
             assert got[i].tolist() == stats[i].tolist(), ("group %d map %d" % (k, i), dict(zip(smb.STAT_NAMES, got[i])),
                                                           dict(zip(smb.STAT_NAMES, stats[i])))
         total += len(maps)
-    assert total >= 60
+    assert total >= 180
 
 
 def test_smb_reward_and_episode_over_match_reference_golden():

@@ -1,10 +1,12 @@
 """ctypes mirror of include/pcgrl_b200.h (POD structs + constants).  No CUDA, no torch."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DIM = 32
 MAX_TILES = 8
-MAX_STATS = 12
+MAX_STATS = 16
+MAX_REWARD_TERMS = 12
+INFO_ITERATION, INFO_CHANGES = 14, 15   # info_stats columns: env counters before any auto-reset
 MT_WORDS = 625
 
 PROB_BINARY, PROB_ZELDA, PROB_SOKOBAN, PROB_DDAVE, PROB_MDUNGEON = range(5)
@@ -15,6 +17,7 @@ FLAG_WARP = 2
 FLAG_RANDOM_START = 4
 FLAG_RANDOM_PROBS = 8
 FLAG_AUTO_RESET = 16
+FLAG_HEAT_U16 = 32
 
 PROBLEM_IDS = {"binary": PROB_BINARY, "zelda": PROB_ZELDA, "sokoban": PROB_SOKOBAN,
                "ddave": PROB_DDAVE, "mdungeon": PROB_MDUNGEON}
@@ -53,7 +56,7 @@ class PcgrlConfig(C.Structure):
         ("flags", C.c_uint32), ("solver_power", C.c_int32),
         ("iparam", C.c_int32 * 7),
         ("dparam", C.c_double * 2),
-        ("reward_weight", C.c_double * MAX_STATS),
+        ("reward_weight", C.c_double * MAX_REWARD_TERMS),
         ("tile_prob", C.c_double * MAX_TILES),
     ]
 
@@ -88,7 +91,7 @@ class PcgrlHostRolloutIO(C.Structure):
 # name -> dtype string, trailing shape as a function of (H, W); leading dim is n
 BUFFER_SPECS = [
     ("map", "uint8", lambda h, w: (h, w)),
-    ("heatmap", "uint8", lambda h, w: (h, w)),
+    ("heatmap", "uint8", lambda h, w: (h, w)),       # int16 storage when FLAG_HEAT_U16 is set (max_changes > 255)
     ("pos", "uint8", lambda h, w: (2,)),
     ("iteration", "int32", lambda h, w: ()),
     ("changes", "int32", lambda h, w: ()),

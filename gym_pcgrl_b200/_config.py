@@ -16,6 +16,8 @@ def build_config(prob, rep, max_changes, max_iterations, auto_reset=True):
         flags |= _abi.FLAG_RANDOM_PROBS
     if auto_reset:
         flags |= _abi.FLAG_AUTO_RESET
+    if int(max_changes) > 255:   # a heat-map cell can count up to max_changes edits (pcgrl_env.py:137)
+        flags |= _abi.FLAG_HEAT_U16
     cfg.flags = flags
     cfg.solver_power = p["solver_power"]
     for i, v in enumerate(p["iparam"]):

@@ -108,6 +108,8 @@ def alloc_buffers(cfg, n, device):
     h, w = cfg.height, cfg.width
     tens = {}
     for name, dtype, shape in _abi.BUFFER_SPECS:
+        if name == "heatmap" and (cfg.flags & _abi.FLAG_HEAT_U16):
+            dtype = "int16"   # uint16 counts (<= max_changes <= 65535 / 2 in practice) in torch's signed 16-bit storage
         tens[name] = torch.zeros((n,) + shape(h, w), dtype=getattr(torch, "int32" if dtype == "uint32" else dtype), device=device)
     tens["tile_prob"][:] = torch.tensor(list(cfg.tile_prob), dtype=torch.float64, device=device)[None, :]
     tens["status"] = torch.zeros(4, dtype=torch.int32, device=device)

@@ -12,7 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libpcgrl_b200.so")
 SOURCES = ["pcgrl_b200.cu"]
-HEADERS = ["pcgrl_device.cuh", "pcgrl_problems.cuh", "pcgrl_env.cuh", "pcgrl_solver.cuh", "pcgrl_wrappers.cuh"]
+import glob  # noqa: E402
+
+
+def _headers():
+    """every header next to the translation unit (a stale-check list kept by hand went out of date once)"""
+    return sorted(os.path.basename(p) for p in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")))
+
+
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
@@ -21,7 +28,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "pcgrl_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + _headers()] + [os.path.join(HERE, "..", "include", "pcgrl_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -38,6 +38,12 @@ __device__ __forceinline__ void store_row(int32_t* dst, const int* src, int lane
   for (int i = 0; i < N; i++) if (lane == i) dst[i] = src[i];
 }
 
+// info["iterations"] / info["changes"] (pcgrl_env.py:144-145): the counters at the end of the step, before any auto-reset
+__device__ __forceinline__ void store_info_counters(int32_t* info_row, int iteration, int changes, int lane) {
+  if (lane == PCGRL_INFO_ITERATION) info_row[PCGRL_INFO_ITERATION] = iteration;
+  if (lane == PCGRL_INFO_CHANGES) info_row[PCGRL_INFO_CHANGES] = changes;
+}
+
 template <int PROB>
 __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
                                                       const __grid_constant__ pcgrl_buffers b,
@@ -110,6 +116,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     if (t == T - 1) {  // the env's own reward / done / info buffers describe the last step only
       if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
       store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+      store_info_counters(b.info_stats + (size_t)e * PCGRL_MAX_STATS, iteration, changes, lane);
       if (PROB == PCGRL_PROB_BINARY && lane == NS)  // info["path-imp"] (binary_prob.py:137), before any auto-reset
         b.info_stats[(size_t)e * PCGRL_MAX_STATS + NS] = st[1] - start[1];
     }
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
 #endif
       if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
     } else {
-      if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
+      if (change > 0) heat_increment(cfg, b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
       if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map, multi);
     }
   }
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(32 * WPB) k_reset(const __grid_constant__ pcgr
   store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
   store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  store_info_counters(b.info_stats + (size_t)e * PCGRL_MAX_STATS, 0, 0, lane);
   if (PROB == PCGRL_PROB_BINARY && lane == NS) b.info_stats[(size_t)e * PCGRL_MAX_STATS + NS] = 0;
   if constexpr (ProblemTraits<PROB>::SOLVER) if (need_solver) solver_enqueue(q, e, SOLVE_FOR_RESET, lane);
 }
@@ -269,6 +277,7 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
     if (done_out) done_out[e] = done ? 1 : 0;
   }
   store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+  store_info_counters(b.info_stats + (size_t)e * PCGRL_MAX_STATS, iteration, changes, lane);
   const uint8_t* hc = heat_cell + 6 * (size_t)e;
   const int change = hc[0], hx = hc[1], hy = hc[2], cell = hc[3] | (hc[4] << 8), tile = hc[5] & 0x7f;
   const bool multi = (hc[5] & 0x80) != 0;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(32 * WPB) k_step_finish(const __grid_constant_
     if (need_solver) solver_enqueue(q, e, SOLVE_FOR_RESET, lane);
     write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
   } else {
-    if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);
+    if (change > 0) heat_increment(cfg, b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);
     write_record(sg, cfg, e, lane, reward, done, px, py, change > 0, false, cell, tile, b.map + (size_t)e * cells, multi);
   }
   (void)H;
@@ -646,7 +655,10 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
         if (done_out) done_out[(size_t)t * n + e] = done ? 1 : 0;
         if (t == T - 1) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
       }
-      if (t == T - 1) store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+      if (t == T - 1) {
+        store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
+        store_info_counters(b.info_stats + (size_t)e * PCGRL_MAX_STATS, iteration, changes, lane);
+      }
       if (done && auto_reset) {
         bool need_solver;
         const long long t0 = AP_NOW();
@@ -672,7 +684,7 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
         changes = 0;
         if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
       } else {
-        if (change > 0) heat_increment(b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);  // :137
+        if (change > 0) heat_increment(cfg, b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);  // :137
         if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map, multi);
       }
     }
@@ -738,7 +750,9 @@ extern "C" int pcgrl_config_validate(const pcgrl_config* c) {
   if (c->width < 1 || c->width > PCGRL_MAX_DIM || c->height < 1 || c->height > PCGRL_MAX_DIM)
     return fail(-1, "width/height must be in [1, 32] (one bitboard row per warp lane)");
   if (c->num_tiles != ntiles[c->problem]) return fail(-1, "num_tiles does not match the problem's tile alphabet");
-  if (c->max_changes < 1 || c->max_changes > 255) return fail(-1, "max_changes must be in [1, 255] (uint8 heat map)");
+  if (c->max_changes < 1 || c->max_changes > 65535) return fail(-1, "max_changes must be in [1, 65535]");
+  if (c->max_changes > 255 && !(c->flags & PCGRL_FLAG_HEAT_U16))
+    return fail(-1, "max_changes > 255 needs a uint16 heat map: set PCGRL_FLAG_HEAT_U16");
   if (c->max_iterations < 1) return fail(-1, "max_iterations must be >= 1");
   double tot = 0;
   for (int t = 0; t < c->num_tiles; t++) {
@@ -827,7 +841,7 @@ static int step_solver(const pcgrl_config* cfg, const pcgrl_buffers* b, const in
 static pcgrl_buffers shard_buffers(const pcgrl_config* cfg, const pcgrl_buffers* b, int off, void* scratch, size_t scratch_bytes) {
   const size_t cells = (size_t)cfg->width * cfg->height, o = (size_t)off;
   pcgrl_buffers g = *b;
-  g.map += o * cells; g.heatmap += o * cells; g.pos += 2 * o; g.iteration += o; g.changes += o;
+  g.map += o * cells; g.heatmap = (char*)g.heatmap + o * cells * (size_t)heat_bytes(*cfg); g.pos += 2 * o; g.iteration += o; g.changes += o;
   g.stats += o * PCGRL_MAX_STATS; g.start_stats += o * PCGRL_MAX_STATS; g.info_stats += o * PCGRL_MAX_STATS;
   g.reward += o; g.done += o; g.rng += o * 2 * PCGRL_MT_WORDS; g.tile_prob += o * PCGRL_MAX_TILES;
   g.start_map += o * cells; g.start_valid += o;
@@ -863,18 +877,21 @@ static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
   if constexpr (GameOf<PROB>::GAME >= 0) {
     int table_size;
     const size_t smem = ((solver_arena_words(cfg, &table_size) + 3) & ~(size_t)3) * sizeof(uint32_t) + ASYNC_RESET_AREAS * sizeof(WarpSmem);
-    static size_t configured[SOLVER_MAX_DEVICES][PCGRL_NUM_PROBLEMS] = {};  // the attribute is per device
+    // launch geometry is a function of (device, problem, smem): queried once, not on every per-step call
+    struct Geometry { size_t smem; int sm_count, per_sm; };
+    static thread_local Geometry geo[SOLVER_MAX_DEVICES][PCGRL_NUM_PROBLEMS] = {};
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= SOLVER_MAX_DEVICES || configured[dev][PROB] < smem) {
+    cudaGetDevice(&dev);  // thread-local read in the runtime, no driver round trip
+    Geometry local = {0, 0, 0};
+    Geometry& g = (dev >= 0 && dev < SOLVER_MAX_DEVICES) ? geo[dev][PROB] : local;
+    if (g.smem != smem || g.per_sm < 1) {
       cudaError_t ce = cudaFuncSetAttribute(k_rollout_async<PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (ce != cudaSuccess) return cuda_rc(ce, "k_rollout_async shared memory opt-in");
-      if (dev >= 0 && dev < SOLVER_MAX_DEVICES) configured[dev][PROB] = smem;
+      cudaDeviceGetAttribute(&g.sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.per_sm, k_rollout_async<PROB>, 32 * ASYNC_WPB, smem);
+      g.smem = smem;
     }
-    static thread_local int sm_dev = -1, sm_count = 0;
-    if (sm_dev != dev) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); sm_dev = dev; }
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_async<PROB>, 32 * ASYNC_WPB, smem);
+    const int sm_count = g.sm_count, per_sm = g.per_sm;
     if (per_sm < 1) return fail(-1, "k_rollout_async does not fit one SM (solver_power too large)");
     const SolverLayout lay = solver_layout(cfg, n);
     int grid = (n + ASYNC_WPB - 1) / ASYNC_WPB;
@@ -1044,6 +1061,9 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   const int adim = action_dim_host(cfg->representation);
   const bool wide = cfg->representation == PCGRL_REP_WIDE;
   const bool delta = io->mode == 1;
+  const size_t hb = (size_t)heat_bytes(*cfg);
+  uint8_t* const heat8 = (uint8_t*)io->heatmap;
+  uint16_t* const heat16 = (uint16_t*)io->heatmap;
   if (delta && (!io->d_staging || !io->h_staging || io->staging_bytes < pcgrl_host_staging_bytes(cfg, n)))
     return fail(-1, "mode 1 needs d_staging / h_staging of pcgrl_host_staging_bytes() bytes");
   HT_BEGIN();
@@ -1092,7 +1112,7 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
         const size_t fe = f.env_kind & 0xffffffu;
         if (fe < (size_t)n) {
           if (io->map) __builtin_prefetch(io->map + fe * cells + f.cell, 1);
-          if (io->heatmap) __builtin_prefetch(io->heatmap + fe * cells + (wide ? (size_t)f.cell : (size_t)hpos[2 * fe + 1] * cfg->width + hpos[2 * fe]), 1);
+          if (io->heatmap) __builtin_prefetch(heat8 + hb * (fe * cells + (wide ? (size_t)f.cell : (size_t)hpos[2 * fe + 1] * cfg->width + hpos[2 * fe])), 1);
         }
       }
       const ChangeRecord r = rec[k];
@@ -1102,7 +1122,7 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
       if (kind == PCGRL_REC_RESET) {
         if (r.slot == 0xFF) overflow = true;
         else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
-        if (io->heatmap) memset(io->heatmap + e * cells, 0, cells);
+        if (io->heatmap) memset(heat8 + hb * e * cells, 0, hb * cells);
       } else {
         if (kind == PCGRL_REC_MULTI) {
           if (r.slot == 0xFF) overflow = true;
@@ -1110,7 +1130,10 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
         } else if (io->map) {
           io->map[e * cells + r.cell] = r.tile;
         }
-        if (io->heatmap) io->heatmap[e * cells + (wide ? (size_t)r.cell : (size_t)hpos[2 * e + 1] * cfg->width + hpos[2 * e])] += 1;
+        if (io->heatmap) {
+          const size_t hi = e * cells + (wide ? (size_t)r.cell : (size_t)hpos[2 * e + 1] * cfg->width + hpos[2 * e]);
+          if (hb == 2) heat16[hi] += 1; else heat8[hi] += 1;
+        }
       }
     }
     io->reset_base = (int64_t)total_resets;
@@ -1128,7 +1151,7 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   rc = rollout_dispatch(cfg, b, act_ptr, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0u, 0, n});
   if (rc) return rc;
   if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
-  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, cells * n, cudaMemcpyDeviceToHost, s);
+  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, hb * cells * n, cudaMemcpyDeviceToHost, s);
   if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->reward, b->reward, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->done, b->done, (size_t)n, cudaMemcpyDeviceToHost, s);
@@ -1158,7 +1181,7 @@ extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* 
   cudaMemcpyAsync(io->reward, d_reward, sizeof(double) * tn, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->done, d_done, tn, cudaMemcpyDeviceToHost, s);
   if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
-  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, cells * n, cudaMemcpyDeviceToHost, s);
+  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, (size_t)heat_bytes(*cfg) * cells * n, cudaMemcpyDeviceToHost, s);
   if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
   if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
   return cuda_rc(cudaStreamSynchronize(s), "pcgrl_rollout_host");

@@ -14,11 +14,13 @@ struct EnvRefs {  // per-env base pointers
   double* tile_prob;
 };
 
+__host__ __device__ __forceinline__ int heat_bytes(const pcgrl_config& cfg) { return (cfg.flags & PCGRL_FLAG_HEAT_U16) ? 2 : 1; }
+
 __device__ __forceinline__ EnvRefs env_refs(const pcgrl_config& cfg, const pcgrl_buffers& b, int e) {
   const size_t cells = (size_t)cfg.width * cfg.height;
   EnvRefs r;
   r.map = b.map + (size_t)e * cells;
-  r.heat = b.heatmap + (size_t)e * cells;
+  r.heat = reinterpret_cast<uint8_t*>(b.heatmap) + (size_t)e * cells * heat_bytes(cfg);
   r.start_map = b.start_map + (size_t)e * cells;
   r.rng_rep = b.rng + (size_t)e * 2 * PCGRL_MT_WORDS;
   r.rng_prob = r.rng_rep + PCGRL_MT_WORDS;
@@ -143,11 +145,17 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
   return change;
 }
 
-// _heatmap[y][x] += 1 (pcgrl_env.py:137) as a fire-and-forget 32-bit reduction on the containing word.
-__device__ __forceinline__ void heat_increment(uint8_t* heat_base, size_t byte_off, int lane) {
+// _heatmap[y][x] += 1 (pcgrl_env.py:137) as a fire-and-forget 32-bit reduction on the containing word
+// (uint8 elements, or uint16 with PCGRL_FLAG_HEAT_U16; elem_off counts elements from the start of the batch).
+__device__ __forceinline__ void heat_increment(const pcgrl_config& cfg, void* heat_base, size_t elem_off, int lane) {
   if (lane == 0) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(heat_base) + (byte_off >> 2);
-    atomicAdd(w, 1u << (8u * (uint32_t)(byte_off & 3)));
+    if (cfg.flags & PCGRL_FLAG_HEAT_U16) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(heat_base) + (elem_off >> 1);
+      atomicAdd(w, 1u << (16u * (uint32_t)(elem_off & 1)));
+    } else {
+      uint32_t* w = reinterpret_cast<uint32_t*>(heat_base) + (elem_off >> 2);
+      atomicAdd(w, 1u << (8u * (uint32_t)(elem_off & 3)));
+    }
   }
 }
 
@@ -252,7 +260,7 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
     pr.finish(lane);
     if (lane == 0) { r.tile_prob[0] = p_empty; r.tile_prob[1] = 1 - p_empty; }
   }
-  warp_fill_bytes(r.heat, cells, 0, lane);  // pcgrl_env.py:72
+  warp_fill_bytes(r.heat, cells * heat_bytes(cfg), 0, lane);  // pcgrl_env.py:72
   __syncwarp();
   TP();
 #ifdef PCGRL_PROFILE

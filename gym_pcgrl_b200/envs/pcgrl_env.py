@@ -47,6 +47,7 @@ class BatchedPcgrlEnv:
         self._cfg = None
         self._d_actions = None
         self._pending_states = None
+        self._pending_probs = None
         self._base_seed = None
         self._update_spaces()
         self.seed(seed)
@@ -101,11 +102,24 @@ class BatchedPcgrlEnv:
         self._rep.adjust_param(**kwargs)
         self._update_spaces()
         self._cfg = None
-        if self._tens is not None and (self._prob._height, self._prob._width) != old_shape:
-            # map size changed: state tensors are re-allocated, RNG streams are kept
-            self._pending_states = self._rng_states_numpy()
-            self._tens = None
-            self._cbufs = None
+        if self._tens is not None:
+            probs = kwargs.get('probs')
+            if probs is not None:
+                # problem.py:66-72: Problem._prob is per-env state here (binary redraws it at every reset,
+                # binary_prob.py:68-72), so the given keys -- and only those -- are overwritten for every env;
+                # the next reset() draws its map from them
+                tiles = self._prob.get_tile_types()
+                for t, v in probs.items():
+                    if t in tiles:
+                        self._tens["tile_prob"][:, tiles.index(t)] = float(v)
+            heat_u16 = self._tens["heatmap"].element_size() == 2
+            if (self._prob._height, self._prob._width) != old_shape or heat_u16 != (self._max_changes > 255):
+                # map size (or the heat-map width) changed: state tensors are re-allocated; RNG streams and the per-env
+                # probabilities are kept
+                self._pending_states = self._rng_states_numpy()
+                self._pending_probs = self._tens["tile_prob"].clone()
+                self._tens = None
+                self._cbufs = None
 
     def get_border_tile(self):
         return self._prob.get_tile_types().index(self._prob._border_tile)
@@ -157,13 +171,19 @@ class BatchedPcgrlEnv:
         """T steps in one native call: actions int32 CUDA [T,N] / [T,N,3].  Returns (reward [T,N],
         done [T,N]); the final observation is available through ``observation()``."""
         import torch
+        if self._tens is None:
+            raise RuntimeError("call reset() before rollout()")
         self.native_config
         a = torch.as_tensor(actions).to(device=self._dev, dtype=torch.int32).contiguous()
         T = a.shape[0]
+        if T < 1 or a.numel() != T * self.num_envs * self._adim:
+            raise ValueError("actions must have shape [T,%d%s]" % (self.num_envs, ",%d" % self._adim if self._adim > 1 else ""))
         if reward_out is None:
             reward_out = torch.empty((T, self.num_envs), dtype=torch.float64, device=self._dev)
         if done_out is None:
             done_out = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self._dev)
+        if reward_out.numel() < T * self.num_envs or done_out.numel() < T * self.num_envs:
+            raise ValueError("reward_out / done_out must hold [T,%d] entries" % self.num_envs)
         with torch.cuda.device(self._dev):
             _native.check(_native.lib().pcgrl_rollout(C.byref(self._cfg), C.byref(self._cbufs), a.data_ptr(),
                                                       reward_out.data_ptr(), done_out.data_ptr(), T, self.num_envs,
@@ -236,7 +256,7 @@ class BatchedPcgrlEnv:
         w, h, t = self._prob._width, self._prob._height, self.get_num_tiles()
         self.action_space = self._rep.get_action_space(w, h, t)
         self.observation_space = self._rep.get_observation_space(w, h, t)
-        self.observation_space.spaces['heatmap'] = spaces.Box(low=0, high=self._max_changes, dtype=np.uint8, shape=(h, w))
+        self.observation_space.spaces['heatmap'] = spaces.Box(low=0, high=self._max_changes, dtype=np.uint8 if self._max_changes <= 255 else np.uint16, shape=(h, w))
         self._adim = _abi.action_dim(self._rep.name)
 
     def _rng_states_numpy(self):
@@ -265,6 +285,9 @@ class BatchedPcgrlEnv:
         if self._pending_states is not None:
             self._tens["rng"].copy_(torch.from_numpy(self._pending_states.view(np.int32)))
             self._pending_states = None
+        if self._pending_probs is not None:
+            self._tens["tile_prob"].copy_(self._pending_probs)
+            self._pending_probs = None
 
     def _observation(self):
         return self._obs_cache
@@ -284,8 +307,9 @@ class BatchedPcgrlEnv:
         info = {k: rows[:, i] for i, k in enumerate(self._prob.stat_names) if k in self._prob.debug_info_names}
         for j, k in enumerate(self._prob.extra_info_names):   # derived entries the kernel appends after the stats
             info[k] = rows[:, len(self._prob.stat_names) + j]
-        info["iterations"] = t["iteration"]
-        info["changes"] = t["changes"]
+        # the counters as they were at the end of the step (an auto-reset zeroes the live ones): VecEnv terminal-info
+        info["iterations"] = rows[:, _abi.INFO_ITERATION]
+        info["changes"] = rows[:, _abi.INFO_CHANGES]
         info["max_iterations"] = self._max_iterations
         info["max_changes"] = self._max_changes
         return info
@@ -305,7 +329,7 @@ class HostStepIO:
         pin = dict(pin_memory=True)
         self.actions = torch.zeros((n, env._adim), dtype=torch.int32, **pin)
         self.map = torch.zeros((n, h, w), dtype=torch.uint8, **pin) if with_obs else None
-        self.heatmap = torch.zeros((n, h, w), dtype=torch.uint8, **pin) if with_obs else None
+        self.heatmap = torch.zeros((n, h, w), dtype=env._tens["heatmap"].dtype, **pin) if with_obs else None
         self.pos = torch.zeros((n, 2), dtype=torch.uint8, **pin) if with_obs and env._rep.name != "wide" else None
         self.reward = torch.zeros(n, dtype=torch.float64, **pin)
         self.done = torch.zeros(n, dtype=torch.uint8, **pin)
@@ -350,7 +374,7 @@ class HostRolloutIO:
         self.reward = torch.zeros((self.T, n), dtype=torch.float64, **pin)
         self.done = torch.zeros((self.T, n), dtype=torch.uint8, **pin)
         self.map = torch.zeros((n, h, w), dtype=torch.uint8, **pin) if with_obs else None
-        self.heatmap = torch.zeros((n, h, w), dtype=torch.uint8, **pin) if with_obs else None
+        self.heatmap = torch.zeros((n, h, w), dtype=env._tens["heatmap"].dtype, **pin) if with_obs else None
         self.pos = torch.zeros((n, 2), dtype=torch.uint8, **pin) if with_obs and env._rep.name != "wide" else None
         self.info_stats = torch.zeros((n, _abi.MAX_STATS), dtype=torch.int32, **pin) if with_info else None
         self.d_actions = torch.zeros(ashape, dtype=torch.int32, device=env._dev)

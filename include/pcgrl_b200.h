@@ -28,11 +28,11 @@
 extern "C" {
 #endif
 
-#define PCGRL_ABI_VERSION 1
+#define PCGRL_ABI_VERSION 2
 
-/* PROBLEMS registry order (reference: gym_pcgrl/envs/probs/__init__.py:9-16; smb is out of scope) */
+/* PROBLEMS registry (reference: gym_pcgrl/envs/probs/__init__.py:9-16) */
 enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_DDAVE = 3,
-       PCGRL_PROB_MDUNGEON = 4, PCGRL_NUM_PROBLEMS = 5 };
+       PCGRL_PROB_MDUNGEON = 4, PCGRL_PROB_SMB = 5, PCGRL_NUM_PROBLEMS = 6 };
 /* REPRESENTATIONS (reference: gym_pcgrl/envs/reps/__init__.py:9-16).  Action layout (int32 per env):
  *   narrow      [1]  0 = keep, a>0 writes tile a-1 at the cursor                  (narrow_rep.py:99-114)
  *   turtle      [1]  0..3 move, a>=4 writes tile a-4                               (turtle_rep.py:101-129)
@@ -44,9 +44,16 @@ enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP
        PCGRL_REP_NARROWMULTI = 4, PCGRL_REP_TURTLECAST = 5, PCGRL_NUM_REPS = 6 };
 #define PCGRL_MAX_ACTION_DIM 9
 
-#define PCGRL_MAX_DIM 32     /* width, height <= 32: one bitboard row per warp lane          */
+#define PCGRL_MAX_DIM 32     /* width, height <= 32: one bitboard row per warp lane (all problems but smb) */
+#define PCGRL_SMB_MAX_W 122  /* smb keeps a byte map: width <= 122 (default 114), 3 <= height <= 16       */
+#define PCGRL_SMB_MAX_H 16
 #define PCGRL_MAX_TILES 8    /* zelda / mdungeon alphabets                                    */
-#define PCGRL_MAX_STATS 12   /* stride of every stats row                                     */
+#define PCGRL_MAX_STATS 16   /* stride of every stats row (one 64-byte line)                  */
+#define PCGRL_MAX_REWARD_TERMS 12
+/* info_stats columns written next to the statistics: the env counters at the END of the step, before any
+ * auto-reset (info["iterations"], info["changes"], pcgrl_env.py:144-145) */
+#define PCGRL_INFO_ITERATION 14
+#define PCGRL_INFO_CHANGES 15
 #define PCGRL_MT_WORDS 625   /* MT19937: 624 state words + word 624 = position (numpy `pos`)  */
 
 /* flags */
@@ -55,6 +62,7 @@ enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP
 #define PCGRL_FLAG_RANDOM_START 4u  /* representation.py:41-45                                                */
 #define PCGRL_FLAG_RANDOM_PROBS 8u  /* binary_prob.py:68-72: redraw tile probabilities at every reset          */
 #define PCGRL_FLAG_AUTO_RESET 16u   /* VecEnv semantics: an env that is done is reset inside step()            */
+#define PCGRL_FLAG_HEAT_U16 32u     /* heat map elements are uint16 (required when max_changes > 255)          */
 
 /*
  * Stats row layout (int32, stride PCGRL_MAX_STATS), one order per problem == the key order of
@@ -66,6 +74,7 @@ enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP
  *                                       num-jumps, col-diamonds, dist-win, sol-length
  *   mdungeon (mdungeon_prob.py:151-171) player, exit, potions, treasures, enemies, regions,
  *                                       col-potions, col-treasures, col-enemies, dist-win, sol-length
+ *   smb      (smb_prob.py:126-148)      dist-floor, disjoint-tubes, enemies, empty, noise, jumps, jumps-dist, dist-win
  *
  * iparam[] (integer thresholds set by Problem.adjust_param):
  *   binary   [0] target_path
@@ -73,6 +82,7 @@ enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP
  *   sokoban  [0] max_crates   [1] target_solution
  *   ddave    [0] max_diamonds [1] min_spikes [2] target_jumps [3] target_solution
  *   mdungeon [0] max_enemies  [1] max_potions [2] max_treasures [3] target_solution ; dparam[0] target_col_enemies
+ *   smb      [0] min_empty    [1] min_enemies [2] max_enemies   [3] min_jumps
  *
  * reward_weight[] is in the order the terms are SUMMED in each Problem.get_reward (fp64, left to right):
  *   binary   regions, path-length                                               (binary_prob.py:105-106)
@@ -80,6 +90,7 @@ enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP
  *   sokoban  player, crate, target, regions, ratio, dist-win, sol-length        (sokoban_prob.py:169-175)
  *   ddave    player, dist-floor, exit, spikes, diamonds, key, regions, num-jumps, dist-win, sol-length (ddave_prob.py:196-205)
  *   mdungeon player, exit, enemies, treasures, potions, regions, col-enemies, dist-win, sol-length     (mdungeon_prob.py:197-205)
+ *   smb      dist-floor, disjoint-tubes, enemies, empty, noise, jumps, jumps-dist, dist-win            (smb_prob.py:163-170)
  */
 typedef struct pcgrl_config {
   int32_t problem;         /* PCGRL_PROB_*                                                     */
@@ -92,7 +103,7 @@ typedef struct pcgrl_config {
   int32_t solver_power;    /* ddave/mdungeon/sokoban _solver_power                             */
   int32_t iparam[7];
   double dparam[2];
-  double reward_weight[PCGRL_MAX_STATS];
+  double reward_weight[PCGRL_MAX_REWARD_TERMS];
   double tile_prob[PCGRL_MAX_TILES]; /* Problem._prob values in tile order (un-normalised)     */
 } pcgrl_config;
 
@@ -102,7 +113,8 @@ typedef struct pcgrl_config {
  */
 typedef struct pcgrl_buffers {
   uint8_t* map;         /* [n][H][W]  Representation._map, tile indices                         */
-  uint8_t* heatmap;     /* [n][H][W]  PcgrlEnv._heatmap counts (value-equal to the fp64 array)  */
+  void* heatmap;        /* [n][H][W]  PcgrlEnv._heatmap counts (value-equal to the fp64 array): uint8, or
+                                      uint16 when PCGRL_FLAG_HEAT_U16 is set                        */
   uint8_t* pos;         /* [n][2]     (x, y) cursor of narrow / turtle; unused for wide         */
   int32_t* iteration;   /* [n]        PcgrlEnv._iteration                                       */
   int32_t* changes;     /* [n]        PcgrlEnv._changes                                         */
@@ -170,7 +182,7 @@ int pcgrl_seed(const pcgrl_buffers* bufs, const uint32_t* seeds, int n, void* st
 typedef struct pcgrl_host_io {
   const int32_t* actions; /* in  [n][adim]            */
   uint8_t* map;           /* out [n][H][W] or NULL    */
-  uint8_t* heatmap;       /* out [n][H][W] or NULL    */
+  void* heatmap;          /* out [n][H][W] or NULL (uint8, or uint16 with PCGRL_FLAG_HEAT_U16) */
   uint8_t* pos;           /* out [n][2]    or NULL    */
   double* reward;         /* out [n]                  */
   uint8_t* done;          /* out [n]                  */
@@ -202,7 +214,7 @@ typedef struct pcgrl_host_rollout_io {
   double* reward;         /* out [T][n]               */
   uint8_t* done;          /* out [T][n]               */
   uint8_t* map;           /* out [n][H][W] or NULL    */
-  uint8_t* heatmap;       /* out [n][H][W] or NULL    */
+  void* heatmap;          /* out [n][H][W] or NULL (uint8, or uint16 with PCGRL_FLAG_HEAT_U16) */
   uint8_t* pos;           /* out [n][2]    or NULL    */
   int32_t* info_stats;    /* out [n][PCGRL_MAX_STATS] or NULL */
 } pcgrl_host_rollout_io;

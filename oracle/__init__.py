@@ -47,6 +47,8 @@ def alloc_buffers(cfg, n):
     h, w = cfg.height, cfg.width
     arrs = {}
     for name, dtype, shape in _abi.BUFFER_SPECS:
+        if name == "heatmap" and (cfg.flags & _abi.FLAG_HEAT_U16):
+            dtype = "uint16"
         arrs[name] = np.zeros((n,) + shape(h, w), dtype=dtype)
     arrs["tile_prob"][:] = np.asarray(list(cfg.tile_prob))[None, :]
     arrs["status"] = np.zeros(4, np.int32)

@@ -766,7 +766,10 @@ static int env_reset(const pcgrl_config* cfg, const pcgrl_buffers* b, int i) { /
     tp[0] = mt_double(rng_prob);
     tp[1] = 1 - tp[0];
   }
-  memset(b->heatmap + (size_t)i * cells, 0, (size_t)cells);
+  {
+    const size_t hb = (cfg->flags & PCGRL_FLAG_HEAT_U16) ? 2 : 1;
+    memset((uint8_t*)b->heatmap + hb * (size_t)i * cells, 0, hb * (size_t)cells);
+  }
   return 0;
 }
 
@@ -871,7 +874,8 @@ static int env_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32
   if (cfg->representation != PCGRL_REP_WIDE) { b->pos[2 * i] = (uint8_t)x; b->pos[2 * i + 1] = (uint8_t)y; }
   if (change > 0) {
     b->changes[i] += change;
-    b->heatmap[(size_t)i * cells + y * W + x] += 1;
+    if (cfg->flags & PCGRL_FLAG_HEAT_U16) ((uint16_t*)b->heatmap)[(size_t)i * cells + y * W + x] += 1;
+    else ((uint8_t*)b->heatmap)[(size_t)i * cells + y * W + x] += 1;
     if (get_stats(cfg, map, stats) != 0) return -1;
   }
   b->reward[i] = get_reward(cfg, stats, old_stats);
@@ -879,6 +883,8 @@ static int env_step(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32
              b->iteration[i] >= cfg->max_iterations;
   b->done[i] = (uint8_t)done;
   memcpy(b->info_stats + (size_t)i * S, stats, sizeof(int32_t) * S);
+  b->info_stats[(size_t)i * S + PCGRL_INFO_ITERATION] = b->iteration[i]; /* pcgrl_env.py:144-145, before any auto-reset */
+  b->info_stats[(size_t)i * S + PCGRL_INFO_CHANGES] = b->changes[i];
   if (cfg->problem == PCGRL_PROB_BINARY) /* binary_prob.py:137 "path-imp" */
     b->info_stats[(size_t)i * S + 2] = stats[1] - b->start_stats[(size_t)i * S + 1];
   if (done && (cfg->flags & PCGRL_FLAG_AUTO_RESET)) return env_reset(cfg, b, i);

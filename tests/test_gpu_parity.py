@@ -217,12 +217,99 @@ def test_batched_rollout_matches_oracle(case):
         np.testing.assert_array_equal(t2n(done).astype(np.uint8), ref["done"], err_msg=ctx + " done")
         Si = S + (1 if prob == "binary" else 0)   # binary appends path-imp
         np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, :Si], ref["info_stats"][:, :Si], err_msg=ctx + " info")
+        # info["iterations"] / info["changes"]: the counters BEFORE the auto-reset of the envs that just finished
+        np.testing.assert_array_equal(t2n(info["iterations"]), ref["info_stats"][:, _abi.INFO_ITERATION], err_msg=ctx + " info iterations")
+        np.testing.assert_array_equal(t2n(info["changes"]), ref["info_stats"][:, _abi.INFO_CHANGES], err_msg=ctx + " info changes")
+        fin = ref["done"] != 0
+        if fin.any():
+            assert (ref["info_stats"][fin, _abi.INFO_ITERATION] > 0).all() and (ref["iteration"][fin] == 0).all(), ctx
         ndone += int(ref["done"].sum())
     np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"], err_msg="rng state")
     np.testing.assert_array_equal(t2n(env._tens["tile_prob"]), ref["tile_prob"], err_msg="tile_prob")
     env.check_status()
     if "turtle" not in env_id:  # random turtles mostly walk; their episodes outlast these short runs
         assert ndone > 0, "case never finished an episode; raise steps"
+
+
+def test_adjust_param_probs_after_reset_match_oracle():
+    """adjust_param(probs=...) once the device buffers exist: the reference applies the new probabilities at
+    the next reset (problem.py:66-72), overwriting only the given keys of the per-env Problem._prob."""
+    import torch
+    n = 64
+    for env_id, kwargs, new_probs in (
+            ("binary-narrow-v0", dict(random_probs=False), {"empty": 0.9, "solid": 0.1}),
+            ("binary-wide-v0", {}, {"empty": 0.2}),                     # random_probs stays on: overwritten, then redrawn
+            ("zelda-turtle-v0", {}, {"empty": 0.93, "solid": 0.02, "player": 0.006, "key": 0.006, "door": 0.006})):
+        env = util.host_env(env_id, kwargs, num_envs=n, auto_reset=True, device="cuda")
+        states = np.stack([util.randomstate_words(900 + i) for i in range(n)])
+        env.set_rng_states(states)
+        ref = oracle.OracleEnv(env.native_config, n, threads=8)
+        ref.set_rng_states(states)
+        prob, rep = env_id.split("-")[:2]
+        S, wide = util.nstats(prob), rep == "wide"
+        env.reset()
+        ref.reset()
+        arng = np.random.RandomState(8)
+        for t in range(10):
+            a = random_actions(env, arng, n)
+            env.step(torch.from_numpy(a).cuda())
+            ref.step(a)
+        env.adjust_param(probs=new_probs)
+        tiles = env._prob.get_tile_types()
+        for k, v in new_probs.items():
+            ref.arrs["tile_prob"][:, tiles.index(k)] = v
+        ref.cfg = env.native_config
+        env.reset()
+        ref.reset()
+        assert_state_equal(env, ref, S, "%s reset after adjust_param(probs)" % env_id, wide)
+        np.testing.assert_array_equal(t2n(env._tens["tile_prob"]), ref["tile_prob"])
+        if prob == "zelda":   # the new distribution is visibly in use
+            assert (ref["map"] == 0).mean() > 0.85
+        for t in range(30):
+            a = random_actions(env, arng, n)
+            env.step(torch.from_numpy(a).cuda())
+            ref.step(a)
+            assert_state_equal(env, ref, S, "%s step %d after adjust_param(probs)" % (env_id, t), wide)
+
+
+def test_uint16_heat_map_when_max_changes_exceeds_255():
+    """change_percentage=1.0 on 20x20 gives max_changes = 400: the reference has no limit there (its heat map is
+    float64), here the heat map switches to uint16 (PCGRL_FLAG_HEAT_U16).  Wide edits hammer two cells so that single
+    cells really exceed 255."""
+    import torch
+    n = 32
+    env = util.host_env("binary-wide-v0", dict(width=20, height=20, change_percentage=1.0), num_envs=n, auto_reset=True, device="cuda")
+    assert env._max_changes == 400 and (env.native_config.flags & _abi.FLAG_HEAT_U16)
+    states = np.stack([util.randomstate_words(40 + i) for i in range(n)])
+    env.set_rng_states(states)
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    ref.set_rng_states(states)
+    env.reset()
+    ref.reset()
+    assert env._tens["heatmap"].element_size() == 2
+    arng = np.random.RandomState(2)
+    io = HostStepIO(env, with_obs=True, with_info=True, mode="delta")
+    top = 0
+    for t in range(900):
+        a = np.stack([(arng.random_sample(n) < 0.1).astype(np.int64), np.zeros(n, np.int64), (t % 2) * np.ones(n, np.int64)], axis=1).astype(np.int32)
+        if t % 3 == 2:   # host-buffer path (delta records patch a uint16 host heat map)
+            io.actions.copy_(torch.from_numpy(a))
+            env.step_host(io)
+            np.testing.assert_array_equal(io.heatmap.numpy().view(np.uint16), ref_step(ref, a)["heatmap"], err_msg="host heat %d" % t)
+        else:
+            env.step(torch.from_numpy(a).cuda())
+            ref.step(a)
+            io.invalidate()
+        np.testing.assert_array_equal(t2n(env._tens["heatmap"]).view(np.uint16), ref["heatmap"], err_msg="heat %d" % t)
+        np.testing.assert_array_equal(t2n(env._tens["map"]), ref["map"], err_msg="map %d" % t)
+        np.testing.assert_array_equal(t2n(env._tens["done"]), ref["done"], err_msg="done %d" % t)
+        top = max(top, int(ref["heatmap"].max()))
+    assert top > 255, top
+
+
+def ref_step(ref, a):
+    ref.step(a)
+    return ref
 
 
 def test_partial_reset_mask_and_fixed_start_match_oracle():
@@ -273,11 +360,13 @@ def test_state_dict_roundtrip_and_resize():
     assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
     # adjust_param after the buffers exist: a new map size re-allocates the state but keeps the RNG streams
     rng_before = env._tens["rng"].clone()
+    probs_before = env._tens["tile_prob"].clone()   # binary redraws Problem._prob per env at every reset: it must survive
     env.adjust_param(width=9, height=7, change_percentage=0.5)
     obs = env.reset()
     assert tuple(obs["map"].shape) == (n, 7, 9) and env._max_changes == int(0.5 * 16 * 16)   # quirk Q3: old size
     ref = oracle.OracleEnv(env.native_config, n)
     ref.arrs["rng"][:] = rng_before.cpu().numpy().view(np.uint32)
+    ref.arrs["tile_prob"][:] = probs_before.cpu().numpy()
     ref.reset()
     np.testing.assert_array_equal(t2n(obs["map"]), ref["map"])
     np.testing.assert_array_equal(t2n(env._tens["stats"])[:, :2], ref["stats"][:, :2])

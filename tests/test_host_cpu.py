@@ -69,7 +69,7 @@ def test_config_freeze_matches_header_layout():
     b = util.host_env("binary-narrow-v0", dict(random_tile=False)).native_config
     assert not (b.flags & _abi.FLAG_RANDOM_TILE) and (b.flags & _abi.FLAG_RANDOM_PROBS)
     # the ctypes mirror must have the size the C compiler gives the struct
-    assert C.sizeof(_abi.PcgrlConfig) == 9 * 4 + 7 * 4 + 2 * 8 + 12 * 8 + 8 * 8
+    assert C.sizeof(_abi.PcgrlConfig) == 9 * 4 + 7 * 4 + 2 * 8 + _abi.MAX_REWARD_TERMS * 8 + 8 * 8
     assert C.sizeof(_abi.PcgrlBuffers) == 17 * 8
 
 

@@ -14,16 +14,17 @@ from gym_pcgrl_b200 import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "pcgrl_oracle.c")
+_SRC_SMB = os.path.join(_HERE, "smb_oracle.c")   # the smb problem's restatement, linked into the same library
 _LIB = os.path.join(_HERE, "_build", "libpcgrl_oracle.so")
 _lib = None
 
 
 def build(force=False):
     hdr = os.path.join(_HERE, "..", "include", "pcgrl_b200.h")
-    if not force and os.path.exists(_LIB) and os.path.getmtime(_LIB) >= max(os.path.getmtime(_SRC), os.path.getmtime(hdr)):
+    if not force and os.path.exists(_LIB) and os.path.getmtime(_LIB) >= max(os.path.getmtime(_SRC), os.path.getmtime(_SRC_SMB), os.path.getmtime(hdr)):
         return _LIB
     os.makedirs(os.path.dirname(_LIB), exist_ok=True)
-    subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", _LIB, _SRC, "-lm"])
+    subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", _LIB, _SRC, _SRC_SMB, "-lm"])
     return _LIB
 
 

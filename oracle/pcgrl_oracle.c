@@ -586,11 +586,19 @@ static int run_game(int game, const grid_t* g, int power, game_result_t* r) {
  * ---------------------------------------------------------------------------------------------- */
 static long g_solver_iterations = 0, g_solver_calls = 0;
 
+/* smb (114 x 14 byte map, always-on A* play-through): restated in oracle/smb_oracle.c, linked into this library */
+void smb_get_stats(const uint8_t* map, int w, int h, int power, int32_t* st);
+double smb_get_reward(const int32_t* n, const int32_t* o, const double* w, const int32_t* ip);
+int smb_episode_over(const int32_t* n);
+
 static int get_stats(const pcgrl_config* cfg, const uint8_t* map, int32_t* st) {
   grid_t g = {cfg->width, cfg->height, map};
   const int W = cfg->width, H = cfg->height;
   for (int i = 0; i < S; i++) st[i] = 0;
   switch (cfg->problem) {
+    case PCGRL_PROB_SMB: /* smb_prob.py:126-148 */
+      smb_get_stats(map, W, H, cfg->solver_power, st);
+      return 0;
     case PCGRL_PROB_BINARY: {
       static const int order[1] = {0};
       st[0] = calc_num_regions(&g, order, 1, 1u << 0);
@@ -679,6 +687,8 @@ static double get_reward(const pcgrl_config* cfg, const int32_t* n, const int32_
   const double INF = INFINITY;
   const int32_t* ip = cfg->iparam;
   switch (cfg->problem) {
+    case PCGRL_PROB_SMB: /* smb_prob.py:150-172 */
+      return smb_get_reward(n, o, w, ip);
     case PCGRL_PROB_BINARY: /* binary_prob.py:98-106 */
       return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], INF, INF) * w[1];
     case PCGRL_PROB_ZELDA: /* zelda_prob.py:124-142 */
@@ -711,6 +721,7 @@ static double get_reward(const pcgrl_config* cfg, const int32_t* n, const int32_
 static int episode_over(const pcgrl_config* cfg, const int32_t* n, const int32_t* start) {
   const int32_t* ip = cfg->iparam;
   switch (cfg->problem) {
+    case PCGRL_PROB_SMB: return smb_episode_over(n);                                /* smb_prob.py:174-175 */
     case PCGRL_PROB_BINARY: return n[0] == 1 && n[1] - start[1] >= ip[0];          /* binary_prob.py:119-120 */
     case PCGRL_PROB_ZELDA: return n[5] >= ip[1] && n[6] >= ip[2];                   /* zelda_prob.py:155-156 */
     case PCGRL_PROB_SOKOBAN: return n[5] >= ip[1];                                  /* sokoban_prob.py:188-189 */

@@ -39,6 +39,7 @@ STAT_NAMES = {
               "col-diamonds", "dist-win", "sol-length"],
     "mdungeon": ["player", "exit", "potions", "treasures", "enemies", "regions", "col-potions",
                  "col-treasures", "col-enemies", "dist-win", "sol-length"],
+    "smb": ["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "jumps", "jumps-dist", "dist-win"],
 }
 
 ZELDA_SPARSE = {"empty": 0.93, "solid": 0.02, "player": 0.006, "key": 0.006, "door": 0.006,
@@ -89,7 +90,20 @@ KAT_CONFIGS = [
     # random_start=False: every reset restores the first map (representation.py:41-45)
     ("zelda_wide_fixedstart", "zelda-wide-v0", dict(random_start=False)),
     ("binary_narrow_fixedstart_raster", "binary-narrow-v0", dict(random_start=False, random_tile=False, width=10, height=6, change_percentage=0.3)),
+    # smb: 114x14 default size and smaller levels whose episodes end inside the run.  Every changed
+    # step runs the reference's A* play-through (power 10000) in Python, hence the shorter runs (STEPS_OVERRIDE).
+    ("smb_narrow", "smb-narrow-v0", {}),
+    ("smb_turtle", "smb-turtle-v0", {}),
+    ("smb_wide", "smb-wide-v0", {}),
+    ("smb_narrow_30x10", "smb-narrow-v0", dict(width=30, height=10, change_percentage=0.1)),
+    ("smb_wide_40x8_sparse", "smb-wide-v0", dict(width=40, height=8, change_percentage=0.1,
+                                                  probs={"empty": 0.9, "solid": 0.04, "enemy": 0.01, "brick": 0.02, "question": 0.01, "coin": 0.01, "tube": 0.01})),
+    ("smb_narrowcast_30x10", "smb-narrowcast-v0", dict(width=30, height=10, change_percentage=0.2)),
+    ("smb_turtlecast_warp_24x9", "smb-turtlecast-v0", dict(width=24, height=9, change_percentage=0.3, warp=True)),
+    ("smb_narrowmulti_raster_30x10", "smb-narrowmulti-v0", dict(width=30, height=10, change_percentage=0.2, random_tile=False)),
 ]
+STEPS_OVERRIDE = {"smb_narrow": 120, "smb_turtle": 250, "smb_wide": 120, "smb_narrow_30x10": 400, "smb_wide_40x8_sparse": 400,
+                  "smb_narrowcast_30x10": 300, "smb_turtlecast_warp_24x9": 400, "smb_narrowmulti_raster_30x10": 300}
 
 
 def stats_vector(prob_name, stats):
@@ -378,14 +392,26 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--jobs", type=int, default=len(os.sched_getaffinity(0)))
     ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--names", default="", help="kat/traj only: comma-separated config names or prefixes; the other kat.json entries are kept")
     a = ap.parse_args()
     pool = mp.Pool(a.jobs)
     if a.only in ("", "rng"):
         run_rng()
     if a.only in ("", "kat", "traj"):
-        metas = pool.map(run_kat, [(n, i, k, 0, a.steps) for (n, i, k) in KAT_CONFIGS], chunksize=1)
+        todo = KAT_CONFIGS
+        if a.names:
+            pref = tuple(a.names.split(","))
+            todo = [c for c in KAT_CONFIGS if c[0].startswith(pref)]
+        metas = pool.map(run_kat, [(n, i, k, 0, STEPS_OVERRIDE.get(n, a.steps)) for (n, i, k) in todo], chunksize=1)
+        if a.names:   # merge into the existing file, keeping KAT_CONFIGS order
+            with open(os.path.join(HERE, "kat.json")) as f:
+                old = {m["name"]: m for m in json.load(f)}
+            old.update({m["name"]: m for m in metas})
+            metas_all = [old[c[0]] for c in KAT_CONFIGS if c[0] in old]
+        else:
+            metas_all = metas
         with open(os.path.join(HERE, "kat.json"), "w") as f:
-            json.dump(metas, f, indent=1)
+            json.dump(metas_all, f, indent=1)
         for m in metas:
             print("%-28s ep=%-4d sum=%-9.1f mc/mi=%d/%d %s  (%.0f steps/s)" % (
                 m["name"], m["episodes"], m["sum_reward"], m["max_changes"], m["max_iterations"], m["digest"],

@@ -65,7 +65,8 @@ for _p in ("binary", "ddave", "mdungeon", "zelda"):          # config 5: default
     for _r in ("narrow", "turtle", "wide"):
         WORKLOADS["%s-%s-default" % (_p, _r)] = dict(prob=_p, rep=_r, envs_per_gpu=8192, kwargs={})
 SWEEP = ["zelda-turtle-11x16", "zelda-turtle-11x16-sparse", "sokoban-wide-5x5", "sokoban-wide-5x5-sparse"] + \
-        ["%s-%s-default" % (p, r) for p in ("binary", "ddave", "mdungeon", "zelda") for r in ("narrow", "turtle", "wide")]
+        ["%s-%s-default" % (p, r) for p in ("binary", "ddave", "mdungeon", "zelda") for r in ("narrow", "turtle", "wide")] + \
+        ["smb-narrow-114x14"]
 WORKLOAD = dict(WORKLOADS["binary-narrow-16x16"])
 WORKLOAD_NAME = "binary-narrow 16x16, 4096 envs/GPU, random-action rollout, auto-reset"
 STEADY_STATE_STEPS = 512     # untimed pre-roll: 16x16 episodes last ~150 steps, so resets are in flight afterwards
@@ -493,8 +494,10 @@ class Bench:
             try:
                 env = make_env(n, self.dev, env_offset=self.rank * n, workload=wl)
                 env.reset()
-                self.preroll(env, 256, 77 + self.rank)
-                per_region, launch_ms, _ = self.time_rollout(env, 256, 128, 128, 3, None, 500 + self.rank)
+                # smb runs an A* play-through of up to 2 x 10000 iterations per edited step: shorter runs
+                Ks, Cs, Rs = (64, 32, 2) if wl["prob"] == "smb" else (256, 128, 3)
+                self.preroll(env, Ks, 77 + self.rank)
+                per_region, launch_ms, _ = self.time_rollout(env, Ks, Cs, Cs, Rs, None, 500 + self.rank)
                 # closed loop on the device: one pcgrl_step per step, actions resident in HBM
                 acts = self.device_actions(env, 64, 900 + self.rank)
                 for t in range(4):
@@ -513,9 +516,9 @@ class Bench:
                 tot = n * self.world
                 W, H = env._prob._width, env._prob._height
                 out[name] = {"envs_per_gpu": n, "map": "%dx%d" % (W, H),
-                             "value": tot * 256 / (red[0] * 1e-3), "device_step": tot * 60 / (red[1] * 1e-3),
+                             "value": tot * Ks / (red[0] * 1e-3), "device_step": tot * 60 / (red[1] * 1e-3),
                              "e2e": tot * 48 / (red[2] * 1e-3), "unit": "env-steps/s",
-                             "hbm_frac": tot / self.world * 256 * algorithmic_bytes_per_env_step(W, H) / (red[0] * 1e-3) / 1e9 / measured_peak()[0],
+                             "hbm_frac": tot / self.world * Ks * algorithmic_bytes_per_env_step(W, H) / (red[0] * 1e-3) / 1e9 / measured_peak()[0],
                              "wall_s": time.perf_counter() - t_wall}
                 del env, io
             except Exception as ex:

@@ -9,7 +9,7 @@ MAX_REWARD_TERMS = 12
 INFO_ITERATION, INFO_CHANGES = 14, 15   # info_stats columns: env counters before any auto-reset
 MT_WORDS = 625
 
-PROB_BINARY, PROB_ZELDA, PROB_SOKOBAN, PROB_DDAVE, PROB_MDUNGEON = range(5)
+PROB_BINARY, PROB_ZELDA, PROB_SOKOBAN, PROB_DDAVE, PROB_MDUNGEON, PROB_SMB = range(6)
 REP_NARROW, REP_TURTLE, REP_WIDE, REP_NARROWCAST, REP_NARROWMULTI, REP_TURTLECAST = range(6)
 
 FLAG_RANDOM_TILE = 1
@@ -20,7 +20,7 @@ FLAG_AUTO_RESET = 16
 FLAG_HEAT_U16 = 32
 
 PROBLEM_IDS = {"binary": PROB_BINARY, "zelda": PROB_ZELDA, "sokoban": PROB_SOKOBAN,
-               "ddave": PROB_DDAVE, "mdungeon": PROB_MDUNGEON}
+               "ddave": PROB_DDAVE, "mdungeon": PROB_MDUNGEON, "smb": PROB_SMB}
 REP_IDS = {"narrow": REP_NARROW, "turtle": REP_TURTLE, "wide": REP_WIDE, "narrowcast": REP_NARROWCAST,
            "narrowmulti": REP_NARROWMULTI, "turtlecast": REP_TURTLECAST}
 ACTION_DIMS = {REP_NARROW: 1, REP_TURTLE: 1, REP_WIDE: 3, REP_NARROWCAST: 2, REP_NARROWMULTI: 9, REP_TURTLECAST: 2}
@@ -34,6 +34,7 @@ STAT_NAMES = {
               "col-diamonds", "dist-win", "sol-length"],
     "mdungeon": ["player", "exit", "potions", "treasures", "enemies", "regions", "col-potions",
                  "col-treasures", "col-enemies", "dist-win", "sol-length"],
+    "smb": ["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "jumps", "jumps-dist", "dist-win"],
 }
 
 # order in which each Problem.get_reward sums its terms == order of pcgrl_config.reward_weight
@@ -45,6 +46,7 @@ REWARD_ORDER = {
               "dist-win", "sol-length"],
     "mdungeon": ["player", "exit", "enemies", "treasures", "potions", "regions", "col-enemies",
                  "dist-win", "sol-length"],
+    "smb": ["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "jumps", "jumps-dist", "dist-win"],
 }
 
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PCGRL_B200_LIB") or os.path.join(_HERE, "csrc", "libp
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
            "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host",
-           "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats"]
+           "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats", "pcgrl_reset_cpu", "pcgrl_step_cpu", "pcgrl_get_stats_cpu"]
 
 _lib = None
 
@@ -67,6 +67,12 @@ def lib():
         L.pcgrl_action_map.restype = C.c_int
         L.pcgrl_action_map.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_void_p]
+        L.pcgrl_reset_cpu.restype = C.c_int
+        L.pcgrl_reset_cpu.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int]
+        L.pcgrl_step_cpu.restype = C.c_int
+        L.pcgrl_step_cpu.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int]
+        L.pcgrl_get_stats_cpu.restype = C.c_int
+        L.pcgrl_get_stats_cpu.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_int]
         L.pcgrl_host_staging_bytes.restype = C.c_size_t
         L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:
@@ -127,7 +133,7 @@ SMB_STAT_NAMES = ["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "
 
 def smb_get_stats(maps, solver_power=10000):
     """Stand-alone batched SMBProblem.get_stats (pcgrl_smb_get_stats): uint8 CUDA [N,H,W] -> int32 [N, MAX_STATS]
-    (columns SMB_STAT_NAMES).  smb_prob.py:126-148; the batched smb environment itself is not implemented yet."""
+    (columns SMB_STAT_NAMES).  smb_prob.py:126-148."""
     import torch
     dev = require_cuda(maps.device)
     maps = maps.to(torch.uint8).contiguous()
@@ -141,11 +147,30 @@ def smb_get_stats(maps, solver_power=10000):
     return out
 
 
-def get_stats(prob, maps):
-    """Stand-alone batched Problem.get_stats (pcgrl_get_stats): uint8 CUDA [N,H,W] -> int32 [N, MAX_STATS]."""
+def get_stats_cpu(prob, maps):
+    """Host twin of get_stats (pcgrl_get_stats_cpu): uint8 CPU tensor / array [N,H,W] -> int32 CPU tensor [N, MAX_STATS]."""
+    import numpy as np
     import torch
     from ._config import build_config
     from .envs.reps import REPRESENTATIONS
+    m = np.ascontiguousarray(np.asarray(maps), dtype=np.uint8)
+    n, h, w = m.shape
+    if (h, w) != (prob._height, prob._width):
+        raise ValueError("map shape %s does not match the problem's (height, width) = %s" % ((h, w), (prob._height, prob._width)))
+    cfg = build_config(prob, REPRESENTATIONS["wide"](), 1, 1, auto_reset=False)
+    out = np.zeros((n, _abi.MAX_STATS), dtype=np.int32)
+    check(lib().pcgrl_get_stats_cpu(C.byref(cfg), m.ctypes.data, out.ctypes.data, n), "pcgrl_get_stats_cpu")
+    return torch.from_numpy(out)
+
+
+def get_stats(prob, maps):
+    """Stand-alone batched Problem.get_stats (pcgrl_get_stats): uint8 CUDA [N,H,W] -> int32 [N, MAX_STATS].
+    A CPU tensor goes to the host twin (problems that have one)."""
+    import torch
+    from ._config import build_config
+    from .envs.reps import REPRESENTATIONS
+    if isinstance(maps, torch.Tensor) and maps.device.type == "cpu":
+        return get_stats_cpu(prob, maps)
     dev = require_cuda(maps.device)
     n, h, w = maps.shape
     if (h, w) != (prob._height, prob._width):

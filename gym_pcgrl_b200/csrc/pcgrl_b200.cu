@@ -18,7 +18,7 @@
 #include "pcgrl_env.cuh"
 #include "pcgrl_solver.cuh"
 #include "pcgrl_wrappers.cuh"
-#include "pcgrl_smb.cuh"
+#include "pcgrl_smb_env.cuh"
 
 using namespace pcgrl;
 
@@ -743,11 +743,15 @@ extern "C" int pcgrl_abi_version(void) { return PCGRL_ABI_VERSION; }
 extern "C" const char* pcgrl_last_error(void) { return g_err; }
 
 extern "C" int pcgrl_config_validate(const pcgrl_config* c) {
-  static const int ntiles[PCGRL_NUM_PROBLEMS] = {2, 8, 5, 7, 8};
+  static const int ntiles[PCGRL_NUM_PROBLEMS] = {2, 8, 5, 7, 8, 7};
   if (!c) return fail(-1, "config is NULL");
   if (c->problem < 0 || c->problem >= PCGRL_NUM_PROBLEMS) return fail(-1, "unknown problem id");
   if (c->representation < 0 || c->representation >= PCGRL_NUM_REPS) return fail(-1, "unknown representation id");
-  if (c->width < 1 || c->width > PCGRL_MAX_DIM || c->height < 1 || c->height > PCGRL_MAX_DIM)
+  if (c->problem == PCGRL_PROB_SMB) {
+    if (c->width < 1 || c->width > PCGRL_SMB_MAX_W || c->height < 3 || c->height > PCGRL_SMB_MAX_H)
+      return fail(-1, "smb: 1 <= width <= 122 and 3 <= height <= 16");
+    if (c->solver_power < 1 || c->solver_power > pcgrl_smb::MAX_POWER) return fail(-1, "smb: solver_power must be in [1, 16000]");
+  } else if (c->width < 1 || c->width > PCGRL_MAX_DIM || c->height < 1 || c->height > PCGRL_MAX_DIM)
     return fail(-1, "width/height must be in [1, 32] (one bitboard row per warp lane)");
   if (c->num_tiles != ntiles[c->problem]) return fail(-1, "num_tiles does not match the problem's tile alphabet");
   if (c->max_changes < 1 || c->max_changes > 65535) return fail(-1, "max_changes must be in [1, 65535]");
@@ -760,7 +764,7 @@ extern "C" int pcgrl_config_validate(const pcgrl_config* c) {
     tot += c->tile_prob[t];
   }
   if (!(tot > 0)) return fail(-1, "tile probabilities must not all be zero");
-  if (c->problem >= PCGRL_PROB_SOKOBAN) {
+  if (c->problem >= PCGRL_PROB_SOKOBAN && c->problem != PCGRL_PROB_SMB) {
     const int rc = solver_validate(c);
     if (rc) return fail(-1, solver_validate_message(rc));
   }
@@ -769,6 +773,7 @@ extern "C" int pcgrl_config_validate(const pcgrl_config* c) {
 
 extern "C" size_t pcgrl_scratch_bytes(const pcgrl_config* c, int n_envs) {
   if (!c || n_envs <= 0 || c->problem < PCGRL_PROB_SOKOBAN) return 0;
+  if (c->problem == PCGRL_PROB_SMB) return pcgrl_smb::scratch_bytes(n_envs, c->solver_power);
   return solver_scratch_bytes(c, n_envs);
 }
 
@@ -793,6 +798,60 @@ static inline int action_dim_host(int rep) {
 
 static inline dim3 env_grid(int n) { return dim3((unsigned)((n + WPB - 1) / WPB)); }
 
+// ---- smb: persistent warp-per-env kernels (pcgrl_smb_env.cuh) ----
+static int smb_plan(const pcgrl_config* cfg, int n, pcgrl_smb::Launch* out) {
+  static thread_local int sm_dev = -1, sm_count = 0;
+  static thread_local size_t configured[3] = {0, 0, 0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sm_dev != dev) {
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    sm_dev = dev;
+    configured[0] = configured[1] = configured[2] = 0;
+  }
+  *out = pcgrl_smb::launch_plan(cfg, n, sm_count > 0 ? sm_count : 148);
+  const void* fns[3] = {(const void*)pcgrl_smb::k_smb_rollout, (const void*)pcgrl_smb::k_smb_reset, (const void*)pcgrl_smb::k_smb_get_stats};
+  for (int i = 0; i < 3; i++)
+    if (configured[i] < out->smem) {
+      cudaError_t ce = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem);
+      if (ce != cudaSuccess) return cuda_rc(ce, "smb shared memory opt-in");
+      configured[i] = out->smem;
+    }
+  return 0;
+}
+
+static int smb_reset(const pcgrl_config* cfg, const pcgrl_buffers* b, const uint8_t* mask, int n, cudaStream_t s) {
+  pcgrl_smb::Launch L;
+  int rc = smb_plan(cfg, n, &L);
+  if (rc) return rc;
+  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power);
+  cudaMemsetAsync(sc.work, 0, sizeof(int32_t), s);
+  pcgrl_smb::k_smb_reset<<<L.grid, 32 * SMB_WPB, L.smem, s>>>(*cfg, *b, mask, n, sc, L.fast_cap, L.per_warp_bytes);
+  return cuda_rc(cudaGetLastError(), "pcgrl_reset (smb) launch");
+}
+
+static int smb_rollout(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
+                       uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
+  pcgrl_smb::Launch L;
+  int rc = smb_plan(cfg, n, &L);
+  if (rc) return rc;
+  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power);
+  cudaMemsetAsync(sc.work, 0, sizeof(int32_t), s);
+  pcgrl_smb::k_smb_rollout<<<L.grid, 32 * SMB_WPB, L.smem, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sc, sg, L.fast_cap,
+                                                             L.per_warp_bytes);
+  return cuda_rc(cudaGetLastError(), "pcgrl_step (smb) launch");
+}
+
+static int smb_get_stats(const pcgrl_config* cfg, const uint8_t* maps, int32_t* out, int n, void* scratch, cudaStream_t s) {
+  pcgrl_smb::Launch L;
+  int rc = smb_plan(cfg, n, &L);
+  if (rc) return rc;
+  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(scratch, n, cfg->solver_power);
+  cudaMemsetAsync(sc.work, 0, sizeof(int32_t), s);
+  pcgrl_smb::k_smb_get_stats<<<L.grid, 32 * SMB_WPB, L.smem, s>>>(*cfg, maps, out, n, sc, L.fast_cap, L.per_warp_bytes);
+  return cuda_rc(cudaGetLastError(), "pcgrl_get_stats (smb) launch");
+}
+
 template <int PROB>
 static int reset_impl(const pcgrl_config* cfg, const pcgrl_buffers* b, const uint8_t* mask, int n, cudaStream_t s) {
   SolverQueue q = solver_queue(cfg, b->scratch, n, 0, b->status);
@@ -811,6 +870,7 @@ extern "C" int pcgrl_reset(const pcgrl_config* cfg, const pcgrl_buffers* b, cons
     case PCGRL_PROB_ZELDA: return reset_impl<PCGRL_PROB_ZELDA>(cfg, b, mask, n, s);
     case PCGRL_PROB_SOKOBAN: return reset_impl<PCGRL_PROB_SOKOBAN>(cfg, b, mask, n, s);
     case PCGRL_PROB_DDAVE: return reset_impl<PCGRL_PROB_DDAVE>(cfg, b, mask, n, s);
+    case PCGRL_PROB_SMB: return smb_reset(cfg, b, mask, n, s);
     default: return reset_impl<PCGRL_PROB_MDUNGEON>(cfg, b, mask, n, s);
   }
 }
@@ -982,6 +1042,7 @@ static int rollout_dispatch(const pcgrl_config* cfg, const pcgrl_buffers* b, con
     case PCGRL_PROB_ZELDA: return rollout_fused<PCGRL_PROB_ZELDA>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
     case PCGRL_PROB_SOKOBAN: return rollout_solver<PCGRL_PROB_SOKOBAN>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
     case PCGRL_PROB_DDAVE: return rollout_solver<PCGRL_PROB_DDAVE>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
+    case PCGRL_PROB_SMB: return smb_rollout(cfg, b, actions, reward_out, done_out, T, n, s, sg);
     default: return rollout_solver<PCGRL_PROB_MDUNGEON>(cfg, b, actions, reward_out, done_out, T, n, s, sg);
   }
 }
@@ -1019,6 +1080,7 @@ extern "C" int pcgrl_get_stats(const pcgrl_config* cfg, const uint8_t* maps, int
     case PCGRL_PROB_ZELDA: return get_stats_impl<PCGRL_PROB_ZELDA>(cfg, maps, stats_out, n, scratch, status, s);
     case PCGRL_PROB_SOKOBAN: return get_stats_impl<PCGRL_PROB_SOKOBAN>(cfg, maps, stats_out, n, scratch, status, s);
     case PCGRL_PROB_DDAVE: return get_stats_impl<PCGRL_PROB_DDAVE>(cfg, maps, stats_out, n, scratch, status, s);
+    case PCGRL_PROB_SMB: return smb_get_stats(cfg, maps, stats_out, n, scratch, s);
     default: return get_stats_impl<PCGRL_PROB_MDUNGEON>(cfg, maps, stats_out, n, scratch, status, s);
   }
 }
@@ -1187,25 +1249,89 @@ extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* 
   return cuda_rc(cudaStreamSynchronize(s), "pcgrl_rollout_host");
 }
 
-static inline int smb_concurrency(int n) { return n < SMB_MAX_CONCURRENCY ? n : SMB_MAX_CONCURRENCY; }
+static void smb_operator_config(pcgrl_config* c, int width, int height, int solver_power) {
+  memset(c, 0, sizeof(*c));
+  c->problem = PCGRL_PROB_SMB; c->representation = PCGRL_REP_WIDE; c->width = width; c->height = height;
+  c->num_tiles = pcgrl_smb::NUM_TILES; c->max_changes = 1; c->max_iterations = 1; c->solver_power = solver_power;
+  for (int t = 0; t < pcgrl_smb::NUM_TILES; t++) c->tile_prob[t] = 1.0;
+}
 
 extern "C" size_t pcgrl_smb_scratch_bytes(int n, int solver_power) {
-  if (n <= 0 || solver_power < 1 || solver_power > 16000) return 0;
-  return sizeof(uint32_t) * pcgrl_smb::workspace_words(solver_power) * (size_t)smb_concurrency(n);
+  if (n <= 0 || solver_power < 1 || solver_power > pcgrl_smb::MAX_POWER) return 0;
+  return pcgrl_smb::scratch_bytes(n, solver_power);
 }
 
 extern "C" int pcgrl_smb_get_stats(const uint8_t* maps, int32_t* stats_out, int n, int width, int height, int solver_power,
                                    void* scratch, size_t scratch_bytes, void* stream) {
   if (!maps || !stats_out || !scratch) return fail(-1, "NULL argument");
   if (n <= 0) return fail(-1, "n must be > 0");
-  if (width < 1 || width > pcgrl_smb::MAX_W || height < 3 || height > pcgrl_smb::MAX_H)
-    return fail(-1, "smb: 1 <= width <= 122 and 3 <= height <= 16");
-  if (solver_power < 1 || solver_power > 16000) return fail(-1, "smb: solver_power must be in [1, 16000]");
+  pcgrl_config c;
+  smb_operator_config(&c, width, height, solver_power);
+  int rc = pcgrl_config_validate(&c);
+  if (rc) return rc;
   if (scratch_bytes < pcgrl_smb_scratch_bytes(n, solver_power)) return fail(-1, "scratch buffer too small: see pcgrl_smb_scratch_bytes()");
-  const int conc = smb_concurrency(n);
-  pcgrl_smb::k_smb_get_stats<<<(conc + SMB_THREADS - 1) / SMB_THREADS, SMB_THREADS, 0, (cudaStream_t)stream>>>(
-      maps, stats_out, n, width, height, solver_power, (uint32_t*)scratch, conc, PCGRL_MAX_STATS);
-  return cuda_rc(cudaGetLastError(), "pcgrl_smb_get_stats launch");
+  return smb_get_stats(&c, maps, stats_out, n, scratch, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host twins: the same entry points on HOST pointers, no GPU involved.  Implemented for the problems
+// whose step logic is scalar `__host__ __device__` code (smb); the bitboard problems return -2.
+// ------------------------------------------------------------------------------------------------
+static int cpu_supported(const pcgrl_config* cfg) {
+  if (!cfg) return fail(-1, "config is NULL");
+  int rc = pcgrl_config_validate(cfg);
+  if (rc) return rc;
+  if (cfg->problem != PCGRL_PROB_SMB) return fail(-2, "host twin not available for this problem (warp-cooperative bitboard kernels): use the CUDA entry point");
+  return 0;
+}
+struct HostWorkOwner {
+  pcgrl_smb::HostWork hw;
+  explicit HostWorkOwner(int power) { hw.heap = (pcgrl_smb::u64*)malloc(sizeof(pcgrl_smb::u64) * pcgrl_smb::heap_entries(power)); }
+  ~HostWorkOwner() { free(hw.heap); }
+};
+
+extern "C" int pcgrl_reset_cpu(const pcgrl_config* cfg, const pcgrl_buffers* b, const uint8_t* mask, int n) {
+  int rc = cpu_supported(cfg);
+  if (rc) return rc;
+  if (!b || n <= 0 || !b->scratch || b->scratch_bytes < pcgrl_scratch_bytes(cfg, n)) return fail(-1, "bad buffers / scratch too small");
+  HostWorkOwner w(cfg->solver_power);
+  if (!w.hw.heap) return fail(-1, "out of memory");
+  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power);
+  for (int e = 0; e < n; e++) {
+    if (mask && !mask[e]) continue;
+    pcgrl_smb::host_reset_env(cfg, b, e, w.hw, sc.touched + (size_t)e * pcgrl_smb::LEVEL_WORDS);
+    b->reward[e] = 0.0;
+    b->done[e] = 0;
+    for (int i = 0; i < PCGRL_MAX_STATS; i++) b->info_stats[(size_t)e * PCGRL_MAX_STATS + i] = (i < 8) ? b->stats[(size_t)e * PCGRL_MAX_STATS + i] : 0;
+  }
+  return 0;
+}
+
+extern "C" int pcgrl_step_cpu(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n) {
+  int rc = cpu_supported(cfg);
+  if (rc) return rc;
+  if (!b || !actions || n <= 0 || !b->scratch || b->scratch_bytes < pcgrl_scratch_bytes(cfg, n)) return fail(-1, "bad buffers / scratch too small");
+  HostWorkOwner w(cfg->solver_power);
+  if (!w.hw.heap) return fail(-1, "out of memory");
+  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power);
+  for (int e = 0; e < n; e++) pcgrl_smb::host_step_env(cfg, b, actions, e, w.hw, sc.touched + (size_t)e * pcgrl_smb::LEVEL_WORDS);
+  return 0;
+}
+
+extern "C" int pcgrl_get_stats_cpu(const pcgrl_config* cfg, const uint8_t* maps, int32_t* stats_out, int n) {
+  int rc = cpu_supported(cfg);
+  if (rc) return rc;
+  if (!maps || !stats_out || n <= 0) return fail(-1, "NULL argument");
+  HostWorkOwner w(cfg->solver_power);
+  if (!w.hw.heap) return fail(-1, "out of memory");
+  uint32_t touched[pcgrl_smb::LEVEL_WORDS];
+  const size_t cells = (size_t)cfg->width * cfg->height;
+  for (int e = 0; e < n; e++) {
+    int32_t st[8];
+    pcgrl_smb::host_get_stats(cfg, maps + (size_t)e * cells, touched, w.hw, st);
+    for (int i = 0; i < PCGRL_MAX_STATS; i++) stats_out[(size_t)e * PCGRL_MAX_STATS + i] = (i < 8) ? st[i] : 0;
+  }
+  return 0;
 }
 
 extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, const uint8_t* pos, void* out, int n,

@@ -1,72 +1,170 @@
-// pcgrl_smb.cuh -- SMBProblem.get_stats on the device (first piece: the stand-alone operator).
+// pcgrl_smb.cuh -- the smb problem: PcgrlEnv.reset / step for 114 x 14 Super Mario levels.
 //
-// Reference: gym_pcgrl/envs/probs/smb_prob.py:95-148 (_run_game, get_stats), probs/smb/engine.py (State, AStarAgent),
-// helper.py:37-62 (get_floor_dist), :74-103 (get_type_grouping), :115-133 (get_changes).
+// Reference: gym_pcgrl/envs/probs/smb_prob.py:9-185 (_run_game :95-124, get_stats :126-148, get_reward :150-172,
+// get_episode_over :174-175), probs/smb/engine.py (State :131-286, AStarAgent :105-129), helper.py:37-62
+// (get_floor_dist), :74-103 (get_type_grouping), :115-133 (get_changes), :310-352 (gen_random_map), the six
+// Representation.update methods (reps/*.py) and pcgrl_env.py:66-76,129-150.
 //
-// The 114 x 14 map does not fit the one-row-per-lane bitboards of the other problems, and its statistics are plain
-// scans plus an always-on A* play-through whose key space is tiny (x, y, airTime): so the mapping is ONE THREAD PER
-// MAP.  A thread keeps the level's solid cells as 4 x 32-bit words per row in shared memory, and its open list
-// (CPython heapq order on packed entries priority << 16 | node, as in pcgrl_solver.cuh), node store and visited
-// bitmap in a private slice of caller-owned scratch in HBM; 2048 searches are in flight per launch, the maps are
-// taken grid-stride.  Everything below is scalar `__host__ __device__` code: tests/test_smb_device_code_on_host.py
-// compiles this header with g++ and checks the very same functions against the reference's golden vectors on the
-// CPU; the GPU test only has to confirm the launch plumbing.
+// The 114 x 14 map does not fit the one-row-per-lane bitboards of the other problems, and its cost is not the map
+// scans but the always-on A* play-through (two passes of up to 10 000 iterations on every step that edits the map).
+// Design:
+//   * ONE WARP PER ENV, persistent CTAs pulling env indices from a global counter.  The warp stages the env's byte map
+//     in shared memory; everything sequential (Representation.update, the scans, the search loop) is scalar code run by
+//     lane 0, everything wide (map load, visited-set clears, building the solid bit rows) is done by the whole warp.
+//   * The A* open list is CPython's binary heap reproduced operation by operation (the result depends on its pop order
+//     under ties) on SELF-CONTAINED 64-bit entries: x, y, airTime, depth, jumps, last jump x and widest jump gap are
+//     packed in the entry itself, so there is no node store and no indirection; priority = (exit - x) + balance * depth
+//     is recomputed from the fields.  The first `fast_cap` entries (the top levels, touched by every pop) live in the
+//     warp's shared memory, the tail in a per-warp slice of HBM scratch.  The visited set is a 32 Kbit bitmap over
+//     (x, y, airTime) == State.getKey, also in shared memory.
+//   * SEARCH SKIPPING (exact): the search is a deterministic function of the solidity of the level cells it reads.  Every
+//     read is recorded in a per-env "touched" bitmap; a later edit that does not change the solidity of a touched cell
+//     cannot change the outcome, so jumps / jumps-dist / dist-win are carried over and the two A* passes are skipped.
+//     Random edits mostly fall outside the region the agent can reach, and half of the tile pairs have equal solidity.
+//   * All scalar pieces are `__host__ __device__`: the same functions are the host twins pcgrl_*_cpu (plumbing without a
+//     GPU) and are checked against the reference's golden vectors on the CPU (tests/test_smb_device_code_on_host.py).
 //
-// Limits: width <= 122, height <= 16, solver_power <= 16000 (node index fits 16 bits).
+// Limits (pcgrl_config_validate): width <= 122, 3 <= height <= 16, solver_power <= 16000 (depth / jumps fit 14 bits).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
+#include "../../include/pcgrl_b200.h"
+
 #ifdef __CUDACC__
 #define SMB_HD __host__ __device__ __forceinline__
+#define SMB_HDN __host__ __device__
 #else
 #define SMB_HD static inline
+#define SMB_HDN static
 #endif
 
 namespace pcgrl_smb {
 
-enum { T_EMPTY = 0, T_SOLID, T_ENEMY, T_BRICK, T_QUESTION, T_COIN, T_TUBE };
-enum { MAX_W = 122, MAX_H = 16, ROW_WORDS = 4, VISITED_WORDS = (MAX_H + 16) * 128 * 8 / 32, PRIO_BIAS = 256 };
+typedef unsigned long long u64;
 
+enum { T_EMPTY = 0, T_SOLID, T_ENEMY, T_BRICK, T_QUESTION, T_COIN, T_TUBE, NUM_TILES = 7 };
+enum { MAX_W = PCGRL_SMB_MAX_W, MAX_H = PCGRL_SMB_MAX_H, ROW_WORDS = 4, LEVEL_WORDS = MAX_H * ROW_WORDS,
+       VISITED_WORDS = 1024 /* 8 airTimes x 32 rows (y + 8) x 128 columns, one bit each */, MAX_POWER = 16000 };
+#define SMB_SOLID_TYPES ((1u << T_SOLID) | (1u << T_BRICK) | (1u << T_QUESTION) | (1u << T_TUBE)) /* smb_prob.py:96 " # ## #" */
+
+// ------------------------------------------------------------------------------------------------
+// MT19937 + numpy legacy RandomState (scalar; state = 624 key words + position, as everywhere in this repo)
+// ------------------------------------------------------------------------------------------------
+SMB_HDN void mt_twist(uint32_t* k) {
+  const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
+  int i;
+  uint32_t y;
+  for (i = 0; i < 624 - 397; i++) { y = (k[i] & UP) | (k[i + 1] & LO); k[i] = k[i + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+  for (; i < 623; i++) { y = (k[i] & UP) | (k[i + 1] & LO); k[i] = k[i - 227] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+  y = (k[623] & UP) | (k[0] & LO);
+  k[623] = k[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+}
+SMB_HD uint32_t mt_u32(uint32_t* st) {
+  uint32_t pos = st[624];
+  if (pos >= 624) { mt_twist(st); pos = 0; }
+  uint32_t y = st[pos];
+  st[624] = pos + 1;
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+SMB_HD double mt_double(uint32_t* st) {  // random_sample()
+  const uint32_t a = mt_u32(st) >> 5, b = mt_u32(st) >> 6;
+  return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+}
+SMB_HD int mt_randint(uint32_t* st, int n) {  // RandomState.randint(n): masked rejection, no draw when n == 1
+  const uint32_t rng = (uint32_t)(n - 1);
+  if (rng == 0) return 0;
+  uint32_t mask = rng, v;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  do { v = mt_u32(st) & mask; } while (v > rng);
+  return (int)v;
+}
+
+// helper.py:310-312 gen_random_map + :343-352 get_int_prob + RandomState.choice(p) on the per-env probabilities
+SMB_HDN void gen_random_map(uint32_t* rng, const double* tile_prob, int T, int cells, uint8_t* map, uint8_t* map2, uint8_t* map3) {
+  double p[PCGRL_MAX_TILES], cdf[PCGRL_MAX_TILES], total = 0.0, acc = 0.0;
+  for (int t = 0; t < T; t++) total += tile_prob[t];
+  for (int t = 0; t < T; t++) p[t] = tile_prob[t] / total;
+  for (int t = 0; t < T; t++) { acc += p[t]; cdf[t] = acc; }
+  for (int t = 0; t < T; t++) cdf[t] /= cdf[T - 1];
+  for (int i = 0; i < cells; i++) {
+    const double u = mt_double(rng);
+    int k = 0;
+    while (k < T && cdf[k] <= u) k++;  // searchsorted(side='right')
+    map[i] = (uint8_t)k;
+    if (map2) map2[i] = (uint8_t)k;
+    if (map3) map3[i] = (uint8_t)k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// level = solid bit rows (4 words per row, level width = W + 6) + the bitmap of cells the search has read
+// ------------------------------------------------------------------------------------------------
 struct Level {
   int width, height, exit_x;
   const uint32_t* solid;  // [height][ROW_WORDS]
+  uint32_t* touched;      // [height][ROW_WORDS]: every solidity read is recorded here
 };
 
-struct State {  // engine.py:159,187-195: player dict; jump_locs folded into (jumps, last_jump_x, max_gap)
-  int x, y, air, jumps, last_jump_x, max_gap;
-};
-
-struct Workspace {  // private slice of one search
-  uint32_t* heap;     // [3 * power + 8]  priority << 16 | node
-  uint32_t* nodes;    // [4 * power + 8][4]  x | (y + 8) << 8 | air << 16,  jumps | last_jump_x << 16,  max_gap | depth << 16,  -
-  uint32_t* visited;  // [VISITED_WORDS] bitmap over (y + 8, x, air)
-};
-
-SMB_HD size_t heap_words(int power) { return (size_t)3 * power + 8; }
-SMB_HD size_t node_words(int power) { return ((size_t)4 * power + 8) * 4; }
-SMB_HD size_t workspace_words(int power) { return ((heap_words(power) + node_words(power) + VISITED_WORDS + 3) / 4) * 4; }
-
-SMB_HD bool solid_at(const Level& L, int x, int y) { return (L.solid[y * ROW_WORDS + (x >> 5)] >> (x & 31)) & 1u; }
-SMB_HD bool movable(const Level& L, int x, int y) {  // engine.py:203-206
+SMB_HD bool solid_at(const Level& L, int x, int y) {
+  const int w = y * ROW_WORDS + (x >> 5);
+  const uint32_t bit = 1u << (x & 31);
+  L.touched[w] |= bit;
+  return (L.solid[w] & bit) != 0u;
+}
+SMB_HD bool movable(const Level& L, int x, int y) {  // engine.py:203-206 checkMovableLocation
   if (y < 0) return true;
   return !(x < 0 || x >= L.width || y >= L.height || solid_at(L, x, y));
 }
-SMB_HD bool st_win(const Level& L, const State& s) { return s.x >= L.exit_x; }
-SMB_HD bool st_lose(const Level& L, const State& s) { return s.y >= L.height; }
+
+// one row of the runnable level (smb_prob.py:97-115): "   " / " @ " / "###" + row + " | " / " # " / "###"
+SMB_HD void build_solid_row(const uint8_t* m, int w, int h, int y, uint32_t* solid) {
+  uint32_t r[ROW_WORDS] = {0u, 0u, 0u, 0u};
+  const bool floor_rows = y > h - 3;
+  for (int x = 0; x < w + 6; x++) {
+    bool s;
+    if (x < 3 || x >= 3 + w) s = floor_rows || (y == h - 3 && x == 3 + w + 1);
+    else s = (SMB_SOLID_TYPES >> m[y * w + x - 3]) & 1u;
+    if (s) r[x >> 5] |= 1u << (x & 31);
+  }
+  for (int k = 0; k < ROW_WORDS; k++) solid[y * ROW_WORDS + k] = r[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// search node == heap entry (64 bits):  x:7 | y+8:5 | airTime:3 | depth:14 | jumps:14 | last jump x:7 | widest gap:7
+// (engine.py:159 player dict; jump_locs folded into (jumps, last jump x, widest gap), smb_prob.py:140-146)
+// ------------------------------------------------------------------------------------------------
+struct State { int x, y, air, jumps, last_jump_x, max_gap; };
+
+SMB_HD u64 pack(const State& s, int depth) {
+  return (u64)(uint32_t)s.x | ((u64)(uint32_t)(s.y + 8) << 7) | ((u64)(uint32_t)s.air << 12) | ((u64)(uint32_t)depth << 15) |
+         ((u64)(uint32_t)s.jumps << 29) | ((u64)(uint32_t)s.last_jump_x << 43) | ((u64)(uint32_t)s.max_gap << 50);
+}
+SMB_HD int e_x(u64 e) { return (int)(e & 127u); }
+SMB_HD int e_y(u64 e) { return (int)((e >> 7) & 31u) - 8; }
+SMB_HD int e_air(u64 e) { return (int)((e >> 12) & 7u); }
+SMB_HD int e_depth(u64 e) { return (int)((e >> 15) & 0x3fffu); }
+SMB_HD int e_key(u64 e) { return (int)(e & 0x7fffu); }  // (x, y, airTime) == State.getKey (engine.py:248-249)
+SMB_HD State unpack(u64 e) {
+  State s;
+  s.x = e_x(e); s.y = e_y(e); s.air = e_air(e);
+  s.jumps = (int)((e >> 29) & 0x3fffu); s.last_jump_x = (int)((e >> 43) & 127u); s.max_gap = (int)((e >> 50) & 127u);
+  return s;
+}
 
 SMB_HD void st_update(const Level& L, State& s, int dir_x, int dir_y) {  // engine.py:208-246
-  if (st_win(L, s) || st_lose(L, s)) return;
-  dir_y = (dir_y < 0) ? -1 : 0;
+  if (s.x >= L.exit_x || s.y >= L.height) return;  // checkOver
   bool ground = false;
   if (s.y < L.height - 1 && s.y >= -1) ground = solid_at(L, s.x, s.y + 1);
   int nx = s.x, ny = s.y;
   if (dir_x != 0 && movable(L, nx + dir_x, ny)) nx += dir_x;
-  if (dir_y == -1) {
+  if (dir_y < 0) {
     if (ground && movable(L, nx, ny - 1)) {
       s.air = 5;
       s.jumps += 1;
-      if (s.x - s.last_jump_x > s.max_gap) s.max_gap = s.x - s.last_jump_x;  // smb_prob.py:141-145 on (old x, y)
+      if (s.x - s.last_jump_x > s.max_gap) s.max_gap = s.x - s.last_jump_x;  // jump_locs.append((x, y)) of the OLD position
       s.last_jump_x = s.x;
     }
   } else if (s.air > 0) {
@@ -85,173 +183,249 @@ SMB_HD void st_update(const Level& L, State& s, int dir_x, int dir_y) {  // engi
   s.y = ny;
 }
 
-SMB_HD void node_store(uint32_t* nodes, int i, const State& s, int depth) {
-  uint32_t* p = nodes + (size_t)i * 4;
-  p[0] = (uint32_t)s.x | ((uint32_t)(s.y + 8) << 8) | ((uint32_t)s.air << 16);
-  p[1] = (uint32_t)s.jumps | ((uint32_t)s.last_jump_x << 16);
-  p[2] = (uint32_t)s.max_gap | ((uint32_t)depth << 16);
-}
-SMB_HD void node_load(const uint32_t* nodes, int i, State& s, int& depth) {
-  const uint32_t* p = nodes + (size_t)i * 4;
-  s.x = (int)(p[0] & 0xffu); s.y = (int)((p[0] >> 8) & 0xffu) - 8; s.air = (int)((p[0] >> 16) & 0xffu);
-  s.jumps = (int)(p[1] & 0xffffu); s.last_jump_x = (int)(p[1] >> 16);
-  s.max_gap = (int)(p[2] & 0xffffu); depth = (int)(p[2] >> 16);
-}
+// The open list: element i of CPython's list sits in storage slot i + 1, so that the child pair (2i+1, 2i+2) is one
+// aligned 16-byte couple; slots below fast_cap are in `fast` (shared memory on the device), the rest in `slow`.
+struct Heap {
+  u64* fast;
+  u64* slow;
+  int fast_cap;  // even
+};
+SMB_HD u64 hget(const Heap& h, int i) { const int s = i + 1; return s < h.fast_cap ? h.fast[s] : h.slow[s - h.fast_cap]; }
+SMB_HD void hset(const Heap& h, int i, u64 v) { const int s = i + 1; if (s < h.fast_cap) h.fast[s] = v; else h.slow[s - h.fast_cap] = v; }
+SMB_HD int e_prio(u64 e, int exit_x, int balance) { return exit_x - e_x(e) + balance * e_depth(e); }  // Node.__lt__ (engine.py:52-53)
 
-// CPython heapq (Lib/heapq.py _siftdown / _siftup) on packed entries; Node.__lt__ compares h + balance * depth only
-#define SMB_HP(e) ((e) >> 16)
-SMB_HD void heap_siftdown(uint32_t* heap, int startpos, int pos) {
-  const uint32_t item = heap[pos];
+// Lib/heapq.py: heappush -> _siftdown(heap, 0, len-1); heappop -> _siftup(heap, 0) (which ends in a _siftdown)
+SMB_HD void heap_siftdown(const Heap& hp, int startpos, int pos, u64 item, int exit_x, int bal) {
+  const int pi = e_prio(item, exit_x, bal);
   while (pos > startpos) {
     const int parentpos = (pos - 1) >> 1;
-    const uint32_t parent = heap[parentpos];
-    if (SMB_HP(item) < SMB_HP(parent)) { heap[pos] = parent; pos = parentpos; continue; }
+    const u64 parent = hget(hp, parentpos);
+    if (pi < e_prio(parent, exit_x, bal)) { hset(hp, pos, parent); pos = parentpos; continue; }
     break;
   }
-  heap[pos] = item;
+  hset(hp, pos, item);
 }
-SMB_HD uint32_t heap_pop(uint32_t* heap, int& n) {
-  const uint32_t last = heap[--n];
+SMB_HD u64 heap_pop(const Heap& hp, int& n, int exit_x, int bal) {
+  const u64 last = hget(hp, --n);
   if (n == 0) return last;
-  const uint32_t ret = heap[0];
+  const u64 ret = hget(hp, 0);
   int pos = 0, childpos = 1;
   while (childpos < n) {
     const int rightpos = childpos + 1;
-    uint32_t child = heap[childpos];
+    u64 child = hget(hp, childpos);
     if (rightpos < n) {
-      const uint32_t right = heap[rightpos];
-      if (!(SMB_HP(child) < SMB_HP(right))) { childpos = rightpos; child = right; }
+      const u64 right = hget(hp, rightpos);
+      if (!(e_prio(child, exit_x, bal) < e_prio(right, exit_x, bal))) { childpos = rightpos; child = right; }
     }
-    heap[pos] = child;
+    hset(hp, pos, child);
     pos = childpos;
     childpos = 2 * pos + 1;
   }
-  heap[pos] = last;
-  heap_siftdown(heap, 0, pos);
+  heap_siftdown(hp, 0, pos, last, exit_x, bal);
   return ret;
 }
 
-// AStarAgent.getSolution (engine.py:105-129): returns the node index of the winning node or of the best node
-SMB_HD int astar(const Level& L, const State& s0, int balance, int max_iter, const Workspace& ws, bool& won) {
+// AStarAgent.getSolution (engine.py:105-129) on a CLEARED visited bitmap; returns true on a win; `result` = the winning
+// node, else the best node (lowest heuristic, then lowest cost).
+SMB_HDN bool astar_core(const Level& L, u64 root, int balance, int max_iter, const Heap& hp, uint32_t* visited, u64& result,
+                        int& iterations_out) {
   const int dirs_x[4] = {0, 1, 0, 1}, dirs_y[4] = {0, 0, -1, -1};  // engine.py:3
-  int nn = 0, nheap = 0, iterations = 0, best = -1, best_h = 0, best_depth = 0;
-  for (int i = 0; i < VISITED_WORDS; i++) ws.visited[i] = 0u;
-  node_store(ws.nodes, 0, s0, 0);
-  ws.heap[0] = ((uint32_t)((L.exit_x - s0.x) + PRIO_BIAS) << 16) | 0u;
-  nn = 1; nheap = 1;
-  won = false;
+  int nheap = 1, iterations = 0, best_h = 0, best_depth = 0;
+  bool have_best = false;
+  u64 best = root;
+  hset(hp, 0, root);
   while ((iterations < max_iter || max_iter <= 0) && nheap > 0) {
     iterations++;
-    const int cur = (int)(heap_pop(ws.heap, nheap) & 0xffffu);
-    State cs;
-    int depth;
-    node_load(ws.nodes, cur, cs, depth);
-    if (st_lose(L, cs)) continue;
-    if (st_win(L, cs)) { won = true; return cur; }
-    const int key = (((cs.y + 8) * 128 + cs.x) << 3) + cs.air;
+    const u64 cur = heap_pop(hp, nheap, L.exit_x, balance);
+    if (e_y(cur) >= L.height) continue;                                              // checkLose
+    if (e_x(cur) >= L.exit_x) { result = cur; iterations_out = iterations; return true; }  // checkWin
+    const int key = e_key(cur);
     const uint32_t bit = 1u << (key & 31);
-    if (!(ws.visited[key >> 5] & bit)) {
-      const int h = L.exit_x - cs.x;
-      if (best < 0 || h < best_h || (h == best_h && depth < best_depth)) { best = cur; best_h = h; best_depth = depth; }
-      ws.visited[key >> 5] |= bit;
-      for (int d = 0; d < 4; d++) {
-        State c = cs;
-        st_update(L, c, dirs_x[d], dirs_y[d]);
-        node_store(ws.nodes, nn, c, depth + 1);
-        ws.heap[nheap] = ((uint32_t)((L.exit_x - c.x) + balance * (depth + 1) + PRIO_BIAS) << 16) | (uint32_t)nn;
-        nheap++;
-        heap_siftdown(ws.heap, 0, nheap - 1);
-        nn++;
-      }
+    if (visited[key >> 5] & bit) continue;
+    const int h = L.exit_x - e_x(cur), depth = e_depth(cur);
+    if (!have_best || h < best_h || (h == best_h && depth < best_depth)) { best = cur; best_h = h; best_depth = depth; have_best = true; }
+    visited[key >> 5] |= bit;
+    const State cs = unpack(cur);
+    for (int d = 0; d < 4; d++) {
+      State c = cs;
+      st_update(L, c, dirs_x[d], dirs_y[d]);
+      heap_siftdown(hp, 0, nheap, pack(c, depth + 1), L.exit_x, balance);
+      nheap++;
     }
   }
-  return best;
+  result = best;
+  iterations_out = iterations;
+  return false;
 }
 
-// helper.py scans on the uint8 map
-SMB_HD int floor_dist(const uint8_t* m, int w, int h, unsigned from_types, unsigned floor_types) {  // :37-62
-  int result = 0;
-  for (int y = 0; y < h; y++)
-    for (int x = 0; x < w; x++) {
-      if (!((from_types >> m[y * w + x]) & 1u)) continue;
-      int dist = h - 1;
-      for (int dy = 0; dy < h; dy++) {
-        if (y + dy >= h) break;
-        if ((floor_types >> m[(y + dy) * w + x]) & 1u) { dist = dy - 1; break; }
-      }
-      result += dist;
-    }
-  return result;
+SMB_HD u64 root_state(int h) { const State s0 = {1, h - 3, 0, 0, 0, 0}; return pack(s0, 0); }
+
+// play statistics of the selected node -> st[5..7] (smb_prob.py:136-147)
+SMB_HD void play_stats(u64 node, bool won, int w, int exit_x, int32_t* st) {
+  const State s = unpack(node);
+  st[5] = s.jumps;
+  st[6] = (w - s.last_jump_x > s.max_gap) ? (w - s.last_jump_x) : s.max_gap;
+  st[7] = won ? 0 : (exit_x - s.x);
 }
 
-// SMBProblem.get_stats(map) -> st[0..7] = dist-floor, disjoint-tubes, enemies, empty, noise, jumps, jumps-dist, dist-win
-SMB_HD void get_stats_one(const uint8_t* m, int w, int h, int power, uint32_t* solid_words, const Workspace& ws, int32_t* st) {
-  int tubes = 0, enemies = 0, empty = 0, noise = 0;
+// ------------------------------------------------------------------------------------------------
+// helper.py scans on the uint8 map -> st[0..4] = dist-floor, disjoint-tubes, enemies, empty, noise
+// ------------------------------------------------------------------------------------------------
+SMB_HDN void scan_stats(const uint8_t* m, int w, int h, int32_t* st) {
+  const unsigned floor_types = (1u << T_SOLID) | (1u << T_BRICK) | (1u << T_QUESTION);  // "tube_left/right" never occur in the map
+  int dist_floor = 0, tubes = 0, enemies = 0, empty = 0, noise = 0;
   for (int y = 0; y < h; y++)
     for (int x = 0; x < w; x++) {
       const int t = m[y * w + x];
-      enemies += (t == T_ENEMY);
       empty += (t == T_EMPTY);
+      if (t == T_ENEMY) {  // helper.py:37-62 get_floor_dist(map, ["enemy"], floor types)
+        enemies++;
+        int dist = h - 1;
+        for (int dy = 0; y + dy < h; dy++)
+          if ((floor_types >> m[(y + dy) * w + x]) & 1u) { dist = dy - 1; break; }
+        dist_floor += dist;
+      }
       if (t == T_TUBE) {  // get_type_grouping(map, ["tube"], [(-1,0),(1,0)], 1, 1): helper.py:74-103
         const int nb = ((x >= 1 && m[y * w + x - 1] == T_TUBE) ? 1 : 0) + ((x + 1 < w && m[y * w + x + 1] == T_TUBE) ? 1 : 0);
         tubes += (nb == 1);
       }
-      if (x >= 1 && m[y * w + x - 1] != t) noise++;   // get_changes(map, False): helper.py:115-133
+      if (x >= 1 && m[y * w + x - 1] != t) noise++;    // get_changes(map, False): helper.py:115-133
       if (y >= 1 && m[(y - 1) * w + x] != t) noise++;  // get_changes(map, True)
     }
-  st[0] = floor_dist(m, w, h, 1u << T_ENEMY, (1u << T_SOLID) | (1u << T_BRICK) | (1u << T_QUESTION));
-  st[1] = tubes; st[2] = enemies; st[3] = empty; st[4] = noise;
-  // _run_game (smb_prob.py:95-124): "   " / " @ " / "###" + row + " | " / " # " / "###"
-  Level L;
-  L.width = w + 6; L.height = h; L.exit_x = w + 4; L.solid = solid_words;
-  for (int i = 0; i < h * ROW_WORDS; i++) solid_words[i] = 0u;
-  for (int y = 0; y < h; y++) {
-    uint32_t* row = solid_words + y * ROW_WORDS;
-    const bool floor_rows = y > h - 3;
-    for (int x = 0; x < L.width; x++) {
-      bool s;
-      if (x < 3 || x >= 3 + w) s = floor_rows || (y == h - 3 && x == 3 + w + 1);
-      else { const int t = m[y * w + x - 3]; s = (t == T_SOLID || t == T_BRICK || t == T_QUESTION || t == T_TUBE); }
-      if (s) row[x >> 5] |= 1u << (x & 31);
+  st[0] = dist_floor; st[1] = tubes; st[2] = enemies; st[3] = empty; st[4] = noise;
+}
+
+// helper.py:366-376 get_range_reward
+SMB_HD double range_reward(double nv, double ov, double low, double high) {
+  if (nv >= low && nv <= high && ov >= low && ov <= high) return 0.0;
+  if (ov <= high && nv <= high) return fmin(nv, low) - fmin(ov, low);
+  if (ov >= low && nv >= low) return fmax(ov, high) - fmax(nv, high);
+  if (nv > high && ov < low) return high - nv + ov - low;
+  if (nv < low && ov > high) return high - ov + nv - low;
+  return 0.0;
+}
+// smb_prob.py:150-172, terms summed left to right
+SMB_HD double get_reward(const pcgrl_config& cfg, const int32_t* n, const int32_t* o) {
+  const double* w = cfg.reward_weight;
+  const int32_t* ip = cfg.iparam;
+  const double INF = HUGE_VAL;
+  return range_reward(n[0], o[0], 0, 0) * w[0] + range_reward(n[1], o[1], 0, 0) * w[1] +
+         range_reward(n[2], o[2], ip[1], ip[2]) * w[2] + range_reward(n[3], o[3], ip[0], INF) * w[3] +
+         range_reward(n[4], o[4], 0, 0) * w[4] + range_reward(n[5], o[5], ip[3], INF) * w[5] +
+         range_reward(n[6], o[6], 0, 0) * w[6] + range_reward(n[7], o[7], 0, 0) * w[7];
+}
+SMB_HD bool episode_over(const int32_t* n) { return n[7] <= 0; }  // smb_prob.py:174-175
+
+// ------------------------------------------------------------------------------------------------
+// Representation.update on the byte map (the six representations; reps/*.py, cited in include/pcgrl_b200.h)
+// ------------------------------------------------------------------------------------------------
+struct Edit {
+  int change;            // number of cells whose tile changed
+  int hx, hy;            // heat-map cell (pcgrl_env.py:137)
+  int cell, tile;        // single-cell edit (delta transport)
+  bool multi;            // a 3x3 stamp ran
+  bool solidity_touched; // some changed cell switched between solid / non-solid AND the last search had read it
+};
+
+SMB_HD void write_cell(const pcgrl_config& cfg, uint8_t* m, uint8_t* m2, const uint32_t* touched, int x, int y, int t, Edit& ed) {
+  const int W = cfg.width, old = m[y * W + x];
+  if (old == t) return;
+  ed.change++;
+  m[y * W + x] = (uint8_t)t;
+  if (m2) m2[y * W + x] = (uint8_t)t;
+  if ((((SMB_SOLID_TYPES >> old) ^ (SMB_SOLID_TYPES >> t)) & 1u) && ((touched[y * ROW_WORDS + ((x + 3) >> 5)] >> ((x + 3) & 31)) & 1u))
+    ed.solidity_touched = true;
+}
+SMB_HD void turtle_move(const pcgrl_config& cfg, int a, int& x, int& y) {  // turtle_rep.py:101-125
+  const int W = cfg.width, H = cfg.height;
+  const bool warp = (cfg.flags & PCGRL_FLAG_WARP) != 0;
+  x += (a == 0) ? -1 : (a == 1) ? 1 : 0;
+  if (x < 0) x = warp ? x + W : 0;
+  if (x >= W) x = warp ? x - W : W - 1;
+  y += (a == 2) ? -1 : (a == 3) ? 1 : 0;
+  if (y < 0) y = warp ? y + H : 0;
+  if (y >= H) y = warp ? y - H : H - 1;
+}
+// m = working copy of the map (shared memory on the device), m2 = the env's map in HBM (or NULL on the host)
+SMB_HDN Edit apply_action(const pcgrl_config& cfg, const int32_t* act, uint8_t* m, uint8_t* m2, const uint32_t* touched,
+                          uint32_t* rng, int& x, int& y) {
+  const int W = cfg.width, H = cfg.height, rep = cfg.representation;
+  Edit ed;
+  ed.change = 0; ed.multi = false; ed.solidity_touched = false; ed.tile = 0;
+  int wx = x, wy = y, newt = -1, stamp = -2;  // stamp: -2 none, -1 per-cell values (narrowmulti), >= 0 one value
+  if (rep == PCGRL_REP_NARROW) {
+    if (act[0] > 0) newt = (act[0] - 1) & 7;
+  } else if (rep == PCGRL_REP_TURTLE) {
+    if (act[0] >= 4) newt = (act[0] - 4) & 7;
+    else if (act[0] >= 0) turtle_move(cfg, act[0], x, y);
+    wx = x; wy = y;
+  } else if (rep == PCGRL_REP_WIDE) {
+    wx = act[0] < 0 ? 0 : (act[0] >= W ? W - 1 : act[0]);
+    wy = act[1] < 0 ? 0 : (act[1] >= H ? H - 1 : act[1]);
+    newt = act[2] & 7;
+  } else if (rep == PCGRL_REP_NARROWCAST) {
+    if (act[0] == 1) newt = act[1] & 7;
+    else if (act[0] == 2) stamp = act[1] & 7;
+  } else if (rep == PCGRL_REP_NARROWMULTI) {
+    stamp = -1;
+  } else {  // PCGRL_REP_TURTLECAST
+    if (act[0] >= 0 && act[0] < 4) turtle_move(cfg, act[0], x, y);
+    else if (act[0] == 4) newt = act[1] & 7;
+    else if (act[0] == 5) stamp = act[1] & 7;
+    wx = x; wy = y;
+  }
+  if (stamp != -2) {  // 3x3 block centred on the cursor, clipped to the map (narrow_cast_rep.py:43-48 etc.)
+    ed.multi = true;
+    for (int k = 0; k < 9; k++) {
+      const int cx = x + (k % 3) - 1, cy = y + (k / 3) - 1;
+      int t = stamp;
+      if (stamp == -1) t = (act[k] > 0) ? ((act[k] - 1) & 7) : -1;
+      if (cx >= 0 && cx < W && cy >= 0 && cy < H && t >= 0) write_cell(cfg, m, m2, touched, cx, cy, t, ed);
     }
   }
-  State s0 = {1, h - 3, 0, 0, 0, 0};
-  bool won;
-  int sol = astar(L, s0, 1, power, ws, won);
-  if (!won) sol = astar(L, s0, 0, power, ws, won);
-  State ss;
-  int depth;
-  node_load(ws.nodes, sol, ss, depth);
-  st[5] = ss.jumps;
-  st[6] = (w - ss.last_jump_x > ss.max_gap) ? (w - ss.last_jump_x) : ss.max_gap;  // smb_prob.py:140-146
-  st[7] = won ? 0 : (L.exit_x - ss.x);
-}
-
-}  // namespace pcgrl_smb
-
-#ifdef __CUDACC__
-namespace pcgrl_smb {
-
-#define SMB_THREADS 64
-#define SMB_MAX_CONCURRENCY 2048
-
-__global__ void __launch_bounds__(SMB_THREADS) k_smb_get_stats(const uint8_t* __restrict__ maps, int32_t* stats_out, int n, int w,
-                                                               int h, int power, uint32_t* scratch, int concurrency,
-                                                               int out_stride) {
-  __shared__ uint32_t solid_s[SMB_THREADS][MAX_H * ROW_WORDS];
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= concurrency) return;
-  uint32_t* base = scratch + (size_t)tid * workspace_words(power);
-  Workspace ws;
-  ws.heap = base;
-  ws.nodes = base + heap_words(power);
-  ws.visited = ws.nodes + node_words(power);
-  for (int i = tid; i < n; i += concurrency) {
-    int32_t st[8];
-    get_stats_one(maps + (size_t)i * w * h, w, h, power, solid_s[threadIdx.x], ws, st);
-    for (int k = 0; k < out_stride; k++) stats_out[(size_t)i * out_stride + k] = (k < 8) ? st[k] : 0;
+  if (newt >= 0) {
+    write_cell(cfg, m, m2, touched, wx, wy, newt, ed);
+    ed.tile = newt;
   }
+  ed.cell = wy * W + wx;
+  if (rep == PCGRL_REP_NARROW || rep == PCGRL_REP_NARROWCAST || rep == PCGRL_REP_NARROWMULTI) {
+    if (cfg.flags & PCGRL_FLAG_RANDOM_TILE) {  // narrow_rep.py:104-106
+      x = mt_randint(rng, W);
+      y = mt_randint(rng, H);
+    } else {                                   // :107-113
+      x += 1;
+      if (x >= W) { x = 0; y += 1; if (y >= H) y = 0; }
+    }
+    ed.hx = x; ed.hy = y;
+  } else if (rep == PCGRL_REP_WIDE) {
+    ed.hx = wx; ed.hy = wy;
+  } else {
+    ed.hx = x; ed.hy = y;
+  }
+  return ed;
+}
+
+SMB_HD size_t heap_entries(int power) { return ((size_t)3 * power + 16) & ~(size_t)1; }  // one pop, <= four pushes per iteration
+
+// _run_game + the play part of get_stats on the host: both passes, everything in `slow` memory
+SMB_HDN void run_game_scalar(const uint8_t* m, int w, int h, int power, uint32_t* solid, uint32_t* touched, uint32_t* visited,
+                             u64* heap_mem, int32_t* st, long* iterations) {
+  Level L;
+  L.width = w + 6; L.height = h; L.exit_x = w + 4; L.solid = solid; L.touched = touched;
+  for (int i = 0; i < LEVEL_WORDS; i++) touched[i] = 0u;
+  for (int y = 0; y < h; y++) build_solid_row(m, w, h, y, solid);
+  Heap hp;
+  hp.fast = heap_mem; hp.slow = heap_mem; hp.fast_cap = 1 << 30;
+  u64 node;
+  int it1 = 0, it2 = 0;
+  for (int i = 0; i < VISITED_WORDS; i++) visited[i] = 0u;
+  bool won = astar_core(L, root_state(h), 1, power, hp, visited, node, it1);
+  if (!won) {
+    for (int i = 0; i < VISITED_WORDS; i++) visited[i] = 0u;
+    won = astar_core(L, root_state(h), 0, power, hp, visited, node, it2);
+  }
+  play_stats(node, won, w, L.exit_x, st);
+  if (iterations) *iterations += it1 + it2;
 }
 
 }  // namespace pcgrl_smb
-#endif

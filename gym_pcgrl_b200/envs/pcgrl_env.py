@@ -135,10 +135,14 @@ class BatchedPcgrlEnv:
         if mask is not None:
             m = torch.as_tensor(mask, device=self._dev).to(torch.uint8).contiguous()
         self.native_config
-        with torch.cuda.device(self._dev):
-            _native.check(_native.lib().pcgrl_reset(self._cfg_ref, C.byref(self._cbufs),
-                                                    None if m is None else m.data_ptr(), self.num_envs,
-                                                    _native.stream_ptr(self._dev)), "pcgrl_reset")
+        if self._host:
+            _native.check(_native.lib().pcgrl_reset_cpu(self._cfg_ref, C.byref(self._cbufs),
+                                                        None if m is None else m.data_ptr(), self.num_envs), "pcgrl_reset_cpu")
+        else:
+            with torch.cuda.device(self._dev):
+                _native.check(_native.lib().pcgrl_reset(self._cfg_ref, C.byref(self._cbufs),
+                                                        None if m is None else m.data_ptr(), self.num_envs,
+                                                        _native.stream_ptr(self._dev)), "pcgrl_reset")
         self._prob.reset(self._prob.stats_from_rows(self._tens["start_stats"]))
         self._info_cache["max_iterations"], self._info_cache["max_changes"] = self._max_iterations, self._max_changes
         return self._obs_cache
@@ -158,6 +162,9 @@ class BatchedPcgrlEnv:
             a = torch.as_tensor(actions).to(device=dev, dtype=torch.int32).contiguous()
         if a.numel() != self.num_envs * self._adim:
             raise ValueError("actions must have shape [%d%s]" % (self.num_envs, ",%d" % self._adim if self._adim > 1 else ""))
+        if self._host:
+            _native.check(_native.lib().pcgrl_step_cpu(self._cfg_ref, self._bufs_ref, a.data_ptr(), self.num_envs), "pcgrl_step_cpu")
+            return self._obs_cache, self._reward_view, self._done_view, self._info_cache
         if torch.cuda.current_device() != dev.index:
             with torch.cuda.device(dev):
                 return self.step(a)
@@ -184,6 +191,12 @@ class BatchedPcgrlEnv:
             done_out = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self._dev)
         if reward_out.numel() < T * self.num_envs or done_out.numel() < T * self.num_envs:
             raise ValueError("reward_out / done_out must hold [T,%d] entries" % self.num_envs)
+        if self._host:
+            for t in range(T):
+                _, r, d, _ = self.step(a[t])
+                reward_out[t].copy_(r)
+                done_out[t].copy_(d.view(torch.uint8))
+            return reward_out, done_out.view(torch.bool)
         with torch.cuda.device(self._dev):
             _native.check(_native.lib().pcgrl_rollout(C.byref(self._cfg), C.byref(self._cbufs), a.data_ptr(),
                                                       reward_out.data_ptr(), done_out.data_ptr(), T, self.num_envs,
@@ -267,11 +280,18 @@ class BatchedPcgrlEnv:
         cfg = self.native_config
         if self._tens is not None:
             return
-        self._dev = _native.require_cuda(self.device)
+        self._host = torch.device(self.device).type == "cpu"
         _native.validate(cfg)
-        with torch.cuda.device(self._dev):
+        if self._host:
+            # host twin (pcgrl_*_cpu): explicit device="cpu", only for the problems that have one -- never a fallback
+            self._dev = torch.device("cpu")
             self._tens, self._cbufs = _native.alloc_buffers(cfg, self.num_envs, self._dev)
-            self._d_actions = torch.zeros(self.num_envs * self._adim, dtype=torch.int32, device=self._dev)
+            self._d_actions = torch.zeros(self.num_envs * self._adim, dtype=torch.int32)
+        else:
+            self._dev = _native.require_cuda(self.device)
+            with torch.cuda.device(self._dev):
+                self._tens, self._cbufs = _native.alloc_buffers(cfg, self.num_envs, self._dev)
+                self._d_actions = torch.zeros(self.num_envs * self._adim, dtype=torch.int32, device=self._dev)
         self._bufs = self._tens
         self._fn_step_host = _native.lib().pcgrl_step_host
         self._fn_step = _native.lib().pcgrl_step
@@ -399,6 +419,7 @@ class PcgrlEnv:
     metadata = {'render.modes': []}
 
     def __init__(self, prob="binary", rep="narrow", device="cuda"):
+        # device="cpu" selects the host twin (pcgrl_*_cpu) for the problems that have one
         self._batched = BatchedPcgrlEnv(prob, rep, num_envs=1, device=device, auto_reset=False)
         self._prob = self._batched._prob
         self._rep = self._batched._rep

@@ -1,8 +1,8 @@
-"""PROBLEMS registry (same keys as gym_pcgrl/envs/probs/__init__.py:9-16; "smb" is out of scope,
-SURVEY.md 2 row 4b)."""
+"""PROBLEMS registry (same keys as gym_pcgrl/envs/probs/__init__.py:9-16)."""
 from .binary_prob import BinaryProblem
 from .ddave_prob import DDaveProblem
 from .mdungeon_prob import MDungeonProblem
+from .smb_prob import SMBProblem
 from .sokoban_prob import SokobanProblem
 from .zelda_prob import ZeldaProblem
 
@@ -11,5 +11,6 @@ PROBLEMS = {
     "ddave": DDaveProblem,
     "mdungeon": MDungeonProblem,
     "sokoban": SokobanProblem,
+    "smb": SMBProblem,
     "zelda": ZeldaProblem,
 }

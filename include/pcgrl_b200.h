@@ -237,17 +237,30 @@ int pcgrl_action_map(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const i
                      int32_t* actions_out, int n, void* stream);
 
 /*
- * smb (first piece): the stand-alone SMBProblem.get_stats operator
- * (gym_pcgrl/envs/probs/smb_prob.py:126-148 incl. the A* play-through of _run_game :95-124 and probs/smb/engine.py).
+ * smb (gym_pcgrl/envs/probs/smb_prob.py, probs/smb/engine.py).  The smb ENVIRONMENT runs through the
+ * generic entry points above with cfg->problem = PCGRL_PROB_SMB (byte map, width <= 122, 3 <= height <= 16, solver_power
+ * <= 16000; max_changes = 319 at the default size, hence PCGRL_FLAG_HEAT_U16).  The two functions below are the
+ * stand-alone SMBProblem.get_stats operator without a config:
  *   maps [n][height][width] u8 (tiles: empty, solid, enemy, brick, question, coin, tube) ->
  *   stats_out [n][PCGRL_MAX_STATS] i32: dist-floor, disjoint-tubes, enemies, empty, noise, jumps, jumps-dist, dist-win.
- * One thread per map; scratch = pcgrl_smb_scratch_bytes(n, solver_power) bytes of caller-owned device memory
- * (open lists, node stores and visited bitmaps of the searches in flight).  width <= 122, height <= 16,
- * 1 <= solver_power <= 16000.  The batched smb environment (reset / step) is not implemented yet.
+ * scratch = pcgrl_smb_scratch_bytes(n, solver_power) bytes of caller-owned device memory (== pcgrl_scratch_bytes of an smb
+ * config): per-env bitmaps of the level cells the last search read + the tails of the A* open lists of the resident warps.
  */
 size_t pcgrl_smb_scratch_bytes(int n, int solver_power);
 int pcgrl_smb_get_stats(const uint8_t* maps, int32_t* stats_out, int n, int width, int height, int solver_power,
                         void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Host twins: the same operations on HOST pointers, computed on the calling CPU thread by the very
+ * scalar `__host__ __device__` functions the kernels run -- for plumbing / CI without a GPU (BASELINE config 1 style
+ * single-env runs).  They are separate, explicitly named entry points: the CUDA entry points above never fall back to
+ * them.  Available for the problems whose step logic is scalar code (smb); for the warp-cooperative bitboard problems
+ * they return -2 with an explanatory pcgrl_last_error().  pcgrl_buffers.scratch must hold pcgrl_scratch_bytes() bytes of
+ * host memory.
+ */
+int pcgrl_reset_cpu(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const uint8_t* mask_or_null, int n);
+int pcgrl_step_cpu(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* actions, int n);
+int pcgrl_get_stats_cpu(const pcgrl_config* cfg, const uint8_t* maps, int32_t* stats_out, int n);
 
 #ifdef __cplusplus
 }

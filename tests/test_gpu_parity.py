@@ -180,6 +180,15 @@ BATCH_CASES = [
     ("binary-turtlecast-v0", dict(warp=True, width=9, height=12, change_percentage=0.5), 128, 150),
     ("sokoban-turtlecast-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 64, 60),
     ("mdungeon-narrowmulti-v0", {}, 64, 60),
+    # smb (row f3): byte map, warp per env, always-on A* with exact search skipping
+    ("smb-narrow-v0", {}, 96, 40),
+    ("smb-wide-v0", dict(width=40, height=10, change_percentage=0.3), 300, 120),
+    ("smb-turtle-v0", dict(width=30, height=9, change_percentage=0.4, warp=True), 128, 200),
+    ("smb-narrowcast-v0", dict(width=24, height=8, change_percentage=0.3), 128, 100),
+    ("smb-narrowmulti-v0", dict(width=30, height=10, change_percentage=0.3, random_tile=False, random_start=False), 64, 100),
+    ("smb-turtlecast-v0", dict(width=122, height=16, change_percentage=0.01), 40, 60),       # the size limits
+    ("smb-wide-v0", dict(width=30, height=8, change_percentage=0.5,
+                         probs={"empty": 0.55, "solid": 0.3, "enemy": 0.03, "brick": 0.04, "question": 0.02, "coin": 0.02, "tube": 0.04}), 256, 100),
 ]
 
 
@@ -379,6 +388,7 @@ ROLLOUT_CASES = [
     ("sokoban-wide-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 260, 40),
     ("mdungeon-turtle-v0", {}, 192, 40),
     ("ddave-narrow-v0", {}, 130, 40),
+    ("smb-narrow-v0", dict(width=40, height=10, change_percentage=0.3), 200, 48),
 ]
 
 
@@ -521,6 +531,8 @@ HOST_CASES = [
     ("mdungeon-narrow-v0", {}, 64, 60),
     ("zelda-narrowmulti-v0", {}, 96, 60),          # multi-cell edits: whole-map records
     ("binary-turtlecast-v0", dict(width=10, height=10, change_percentage=0.4), 96, 120),
+    ("smb-narrow-v0", dict(width=60, height=12, change_percentage=0.5), 64, 80),       # uint16 heat map (360 changes) in the delta records
+    ("smb-narrowcast-v0", dict(width=30, height=8, change_percentage=0.2), 96, 80),
 ]
 
 
@@ -672,8 +684,8 @@ def test_step_is_cuda_graph_capturable(env_id):
 
 
 def test_smb_get_stats_matches_reference_golden_and_oracle(capsys):
-    """pcgrl_smb_get_stats (one thread per map, A* play-through inline) against the reference's golden vectors and
-    against the smb oracle on a batch larger than the 2048 searches in flight (grid-stride path)."""
+    """pcgrl_smb_get_stats (one warp per map, persistent CTAs) against the reference's golden vectors and against the smb
+    oracle on a batch larger than the resident warps (work-counter path)."""
     import time
     import torch
     from oracle import smb as smb_oracle
@@ -696,3 +708,36 @@ def test_smb_get_stats_matches_reference_golden_and_oracle(capsys):
     np.testing.assert_array_equal(t2n(got)[:, :8], smb_oracle.get_stats(maps, power))
     with capsys.disabled():
         print("\n[smb] pcgrl_smb_get_stats: %d maps 114x14 in %.2f ms (%.3e maps/s)" % (len(maps), dt * 1e3, len(maps) / dt))
+
+
+def test_smb_more_envs_than_resident_warps_and_tiny_power():
+    """5000 tiny smb envs (> SMB_MAX_SLOTS resident warps: the persistent kernels loop over the work counter) with a
+    12-iteration search cap; rollout + single steps + partial reset against the oracle."""
+    import torch
+    n = 5000
+    env = util.host_env("smb-wide-v0", dict(width=9, height=5, change_percentage=0.5), num_envs=n, device="cuda")
+    env._prob._solver_power = 12
+    env._cfg = None
+    states = np.stack([util.randomstate_words(i) for i in range(n)])
+    env.set_rng_states(states)
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    ref.set_rng_states(states)
+    env.reset()
+    ref.reset()
+    assert_state_equal(env, ref, 8, "smb tiny reset", True)
+    arng = np.random.RandomState(3)
+    acts = np.stack([random_actions(env, arng, n) for _ in range(20)])
+    rew, done = env.rollout(torch.from_numpy(acts[:12]).cuda())
+    for k in range(12):
+        ref.step(acts[k])
+        np.testing.assert_array_equal(t2n(rew[k]), ref["reward"], err_msg="step %d" % k)
+        np.testing.assert_array_equal(t2n(done[k]).astype(np.uint8), ref["done"], err_msg="step %d" % k)
+    assert_state_equal(env, ref, 8, "smb tiny rollout", True)
+    mask = (arng.random_sample(n) < 0.3).astype(np.uint8)
+    env.reset(torch.from_numpy(mask))
+    ref.reset(mask)
+    for k in range(12, 20):
+        env.step(torch.from_numpy(acts[k]).cuda())
+        ref.step(acts[k])
+    assert_state_equal(env, ref, 8, "smb tiny steps", True)
+    np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"])

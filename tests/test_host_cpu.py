@@ -15,9 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_registry_and_spaces():
-    assert set(PROBLEMS) == {"binary", "ddave", "mdungeon", "sokoban", "zelda"}
+    assert set(PROBLEMS) == {"binary", "ddave", "mdungeon", "sokoban", "zelda", "smb"}   # gym_pcgrl/envs/probs/__init__.py:9-16
     assert set(REPRESENTATIONS) == {"narrow", "turtle", "wide", "narrowcast", "narrowmulti", "turtlecast"}
-    assert len(pkg.REGISTRY) == 30 and "zelda-turtle-v0" in pkg.REGISTRY and "sokoban-narrowmulti-v0" in pkg.REGISTRY
+    assert len(pkg.REGISTRY) == 36 and "zelda-turtle-v0" in pkg.REGISTRY and "sokoban-narrowmulti-v0" in pkg.REGISTRY
+    smb = BatchedPcgrlEnv("smb", "narrow")
+    assert smb.observation_space["map"].shape == (14, 114) and smb._max_changes == 319 and smb.action_space.n == 8
+    assert smb.observation_space["heatmap"].dtype == np.uint16 and (smb.native_config.flags & _abi.FLAG_HEAT_U16)
     assert BatchedPcgrlEnv("zelda", "narrowmulti").action_space.nvec.tolist() == [9] * 9
     assert BatchedPcgrlEnv("binary", "narrowcast").action_space.nvec.tolist() == [3, 2]
     assert BatchedPcgrlEnv("ddave", "turtlecast").action_space.nvec.tolist() == [6, 7]

@@ -15,7 +15,7 @@
 //     under ties) on SELF-CONTAINED 64-bit entries: x, y, airTime, depth, jumps, last jump x and widest jump gap are
 //     packed in the entry itself, so there is no node store and no indirection; priority = (exit - x) + balance * depth
 //     is recomputed from the fields.  The first `fast_cap` entries (the top levels, touched by every pop) live in the
-//     warp's shared memory, the tail in a per-warp slice of HBM scratch.  The visited set is a 32 Kbit bitmap over
+//     warp's shared memory, the tail in a per-warp slice of HBM scratch.  The visited set is a 16 Kbit bitmap over
 //     (x, y, airTime) == State.getKey, also in shared memory.
 //   * SEARCH SKIPPING (exact): the search is a deterministic function of the solidity of the level cells it reads.  Every
 //     read is recorded in a per-env "touched" bitmap; a later edit that does not change the solidity of a touched cell
@@ -46,7 +46,7 @@ typedef unsigned long long u64;
 
 enum { T_EMPTY = 0, T_SOLID, T_ENEMY, T_BRICK, T_QUESTION, T_COIN, T_TUBE, NUM_TILES = 7 };
 enum { MAX_W = PCGRL_SMB_MAX_W, MAX_H = PCGRL_SMB_MAX_H, ROW_WORDS = 4, LEVEL_WORDS = MAX_H * ROW_WORDS,
-       VISITED_WORDS = 1024 /* 8 airTimes x 32 rows (y + 8) x 128 columns, one bit each */, MAX_POWER = 16000 };
+       VISITED_WORDS = 512 /* 6 airTimes x 21 rows (-5 <= y <= 15) x 128 columns, one bit each (504 words) */, MAX_POWER = 16000 };
 #define SMB_SOLID_TYPES ((1u << T_SOLID) | (1u << T_BRICK) | (1u << T_QUESTION) | (1u << T_TUBE)) /* smb_prob.py:96 " # ## #" */
 
 // ------------------------------------------------------------------------------------------------
@@ -146,7 +146,13 @@ SMB_HD int e_x(u64 e) { return (int)(e & 127u); }
 SMB_HD int e_y(u64 e) { return (int)((e >> 7) & 31u) - 8; }
 SMB_HD int e_air(u64 e) { return (int)((e >> 12) & 7u); }
 SMB_HD int e_depth(u64 e) { return (int)((e >> 15) & 0x3fffu); }
-SMB_HD int e_key(u64 e) { return (int)(e & 0x7fffu); }  // (x, y, airTime) == State.getKey (engine.py:248-249)
+// (x, y, airTime) == State.getKey (engine.py:248-249) as a dense bit index.  A state that reaches the visited test has
+// 0 <= airTime <= 5 and -5 <= y < height <= 16: a jump needs ground (y >= -1) and rises at most four rows (:224-236).
+SMB_HD int e_key(u64 e) {
+  int row = (int)((e >> 7) & 31u) - 3;
+  row = row < 0 ? 0 : (row > 20 ? 20 : row);
+  return (((int)((e >> 12) & 7u) * 21 + row) << 7) | (int)(e & 127u);
+}
 SMB_HD State unpack(u64 e) {
   State s;
   s.x = e_x(e); s.y = e_y(e); s.air = e_air(e);

@@ -9,7 +9,6 @@
 namespace pcgrl_smb {
 
 #define SMB_WPB 4             /* env warps per CTA */
-#define SMB_MAX_SLOTS 4144    /* resident env warps per launch: 148 SMs x 28 */
 #define SMB_HEADER_BYTES 256
 
 // scratch: [header: work counter][touched bitmaps, LEVEL_WORDS words per env][slow heap, heap_entries(power) per slot]
@@ -19,9 +18,13 @@ struct Scratch {
   u64* heap;
   size_t heap_stride;
 };
-static inline int smb_slots(int n) {
-  int s = (n + SMB_WPB - 1) / SMB_WPB * SMB_WPB;
-  return s < SMB_MAX_SLOTS ? s : SMB_MAX_SLOTS;
+static inline int smb_ctas_cap() {  // resident CTAs per SM (tuning knob PCGRL_SMB_CTAS_PER_SM=1..10, read once)
+  static const int cap = [] { const char* v = getenv("PCGRL_SMB_CTAS_PER_SM"); const int k = v ? atoi(v) : 0; return (k >= 1 && k <= 10) ? k : 5; }();
+  return cap;
+}
+static inline int smb_slots(int n) {  // resident env warps of one launch (B200: 148 SMs)
+  const int s = (n + SMB_WPB - 1) / SMB_WPB * SMB_WPB, most = 148 * smb_ctas_cap() * SMB_WPB;
+  return s < most ? s : most;
 }
 static inline size_t scratch_bytes(int n, int power) {
   return SMB_HEADER_BYTES + sizeof(uint32_t) * LEVEL_WORDS * (size_t)n + sizeof(u64) * heap_entries(power) * (size_t)smb_slots(n);
@@ -59,6 +62,7 @@ __device__ __forceinline__ void warp_clear_visited(uint32_t* visited, int lane) 
   uint4* v = reinterpret_cast<uint4*>(visited);
 #pragma unroll
   for (int k = 0; k < VISITED_WORDS / 4 / 32; k++) v[k * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+  static_assert(VISITED_WORDS % 128 == 0, "one uint4 per lane per round");
 }
 
 // _run_game (smb_prob.py:95-124) for the map staged in A.map: lane 0 writes st[5..7].  Rebuilds the touched bitmap.
@@ -316,7 +320,10 @@ static inline Launch launch_plan(const pcgrl_config* cfg, int n, int sm_count) {
   int ctas = slots / SMB_WPB;
   int ctas_per_sm = (ctas + sm_count - 1) / sm_count;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 7) ctas_per_sm = 7;
+  // A search is one dependent instruction chain on lane 0 (~0.6 us per iteration): throughput comes from resident
+  // warps hiding each other's latencies, not from a larger shared-memory slice per search.  Measured on B200
+  // (tools/bench_smb.py, 8192 maps): 2 / 3 / 5 / 7 / 10 CTAs per SM -> 1.9 / 2.5 / 3.3 / 3.5 / 3.3 e5 maps/s.
+  if (ctas_per_sm > smb_ctas_cap()) ctas_per_sm = smb_ctas_cap();
   const int budget = (227 * 1024 - 1024 * ctas_per_sm) / ctas_per_sm / SMB_WPB;  // bytes per warp (1 KB per CTA reserved by the driver)
   int fast_cap = (budget - arena_fixed_bytes(cells)) / 8;
   const int full = (int)heap_entries(cfg->solver_power);
@@ -328,7 +335,8 @@ static inline Launch launch_plan(const pcgrl_config* cfg, int n, int sm_count) {
   L.fast_cap = fast_cap;
   L.per_warp_bytes = (8 * fast_cap + arena_fixed_bytes(cells) + 15) & ~15;
   L.smem = (size_t)L.per_warp_bytes * SMB_WPB;
-  L.grid = ctas;
+  L.grid = ctas < sm_count * ctas_per_sm ? ctas : sm_count * ctas_per_sm;
+  if (L.grid > slots / SMB_WPB) L.grid = slots / SMB_WPB;  // one slow-heap slice per resident warp
   return L;
 }
 #endif  // __CUDACC__

@@ -711,7 +711,7 @@ def test_smb_get_stats_matches_reference_golden_and_oracle(capsys):
 
 
 def test_smb_more_envs_than_resident_warps_and_tiny_power():
-    """5000 tiny smb envs (> SMB_MAX_SLOTS resident warps: the persistent kernels loop over the work counter) with a
+    """5000 tiny smb envs (more than the 2960 resident warps: the persistent kernels loop over the work counter) with a
     12-iteration search cap; rollout + single steps + partial reset against the oracle."""
     import torch
     n = 5000

@@ -26,6 +26,7 @@ using namespace pcgrl;
 // kernels
 // ------------------------------------------------------------------------------------------------
 #define WPB PCGRL_WARPS_PER_BLOCK
+#define PCGRL_PACKED_MIN_T 8 /* shorter fragments do not amortise the packed kernel's per-env prologue */
 
 template <int N>
 __device__ __forceinline__ void load_row(const int32_t* __restrict__ src, int* dst) {
@@ -43,6 +44,8 @@ __device__ __forceinline__ void store_info_counters(int32_t* info_row, int itera
   if (lane == PCGRL_INFO_ITERATION) info_row[PCGRL_INFO_ITERATION] = iteration;
   if (lane == PCGRL_INFO_CHANGES) info_row[PCGRL_INFO_CHANGES] = changes;
 }
+
+#include "pcgrl_packed.cuh"
 
 template <int PROB>
 __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
@@ -878,6 +881,21 @@ extern "C" int pcgrl_reset(const pcgrl_config* cfg, const pcgrl_buffers* b, cons
 template <int PROB>
 static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                          uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
+  if constexpr (PROB == PCGRL_PROB_BINARY) {
+    // Rollouts of maps with at most 16 (8) rows: two (four) envs per warp, decoupled in time (pcgrl_packed.cuh).
+    // PCGRL_PACKED=0 keeps the one-env-per-warp kernel (A/B comparison); single steps always use it.
+    static const bool packed = !(getenv("PCGRL_PACKED") && atoi(getenv("PCGRL_PACKED")) == 0);
+    if (packed && !sg.base && T >= PCGRL_PACKED_MIN_T && cfg->height <= 16 && cfg->representation <= PCGRL_REP_WIDE) {
+      if (cfg->height <= 8) {
+        const int epc = PACKED_WPB * 4;
+        k_rollout_packed_binary<8><<<(n + epc - 1) / epc, 32 * PACKED_WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n);
+      } else {
+        const int epc = PACKED_WPB * 2;
+        k_rollout_packed_binary<16><<<(n + epc - 1) / epc, 32 * PACKED_WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n);
+      }
+      return cuda_rc(cudaGetLastError(), "pcgrl_rollout (packed) launch");
+    }
+  }
   k_rollout<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg);
   return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
 }

@@ -450,6 +450,45 @@ class Bench:
             out.append((time.perf_counter() - t0) * 1e3)
         return out, rio, ncalls * chunk
 
+    # -- asynchronous grouped stepping (opt-in API): every env group keeps one step in flight on its own stream
+    def time_e2e_async(self, wl, n, K, groups, seed):
+        from gym_pcgrl_b200 import AsyncGroupedEnv
+        torch = self.torch
+        env = AsyncGroupedEnv(wl["prob"], wl["rep"], num_envs=n, groups=groups, device=self.dev, seed=0, env_offset=self.rank * n)
+        if wl["kwargs"]:
+            env.adjust_param(**wl["kwargs"])
+            env.adjust_param(**wl["kwargs"])
+        env.reset()
+        m = env.per_group
+        acts = torch.from_numpy(host_actions(env.envs[0], (K + 4) * groups, m, seed)).pin_memory()   # [(K+4)*groups, m(, k)]
+        base, stride = acts.data_ptr(), acts.stride(0) * 4
+
+        def send(g, t):
+            env.io[g].struct.actions = base + (t * groups + g) * stride
+            env.send(g)
+
+        for t in range(4):          # warm-up, synchronous
+            for g in range(groups):
+                send(g, t)
+            while any(env.in_flight):
+                env.recv(wait=True)
+        self.barrier()
+        step = [4] * groups
+        t0 = time.perf_counter()
+        for g in range(groups):
+            send(g, step[g])
+        remaining = groups * K
+        while remaining:
+            for g in env.recv(wait=True):
+                remaining -= 1
+                step[g] += 1
+                if step[g] < K + 4:
+                    send(g, step[g])
+        self.barrier()
+        dt = (time.perf_counter() - t0) * 1e3
+        env.check_status()
+        return dt
+
     # -- shard invariance on hardware: 1024 GLOBAL envs split over the ranks must give the same per-env results at any N
     def shard_check(self):
         torch = self.torch
@@ -512,7 +551,12 @@ class Bench:
                 step_ms = e0.elapsed_time(e1)
                 e2e_ms, io, _ = self.time_e2e(env, 48, 2, "delta", 99 + self.rank)
                 env.check_status()
-                red = self.max_over_ranks([float(np.median(per_region)), step_ms, float(np.median(e2e_ms))])
+                async_ms = None
+                if wl["prob"] in ("sokoban", "ddave", "mdungeon", "smb"):   # a batch step waits for its slowest search
+                    del io
+                    io = None
+                    async_ms = self.time_e2e_async(wl, n, 48, 16, 1999 + self.rank)
+                red = self.max_over_ranks([float(np.median(per_region)), step_ms, float(np.median(e2e_ms)), async_ms or 0.0])
                 tot = n * self.world
                 W, H = env._prob._width, env._prob._height
                 out[name] = {"envs_per_gpu": n, "map": "%dx%d" % (W, H),
@@ -520,6 +564,9 @@ class Bench:
                              "e2e": tot * 48 / (red[2] * 1e-3), "unit": "env-steps/s",
                              "hbm_frac": tot / self.world * Ks * algorithmic_bytes_per_env_step(W, H) / (red[0] * 1e-3) / 1e9 / measured_peak()[0],
                              "wall_s": time.perf_counter() - t_wall}
+                if async_ms:
+                    out[name]["e2e_async_groups"] = tot * 48 / (red[3] * 1e-3)
+                    out[name]["e2e_async_api"] = "AsyncGroupedEnv: 16 env groups, one pcgrl_step_host_begin/_end step in flight each"
                 del env, io
             except Exception as ex:
                 out[name] = {"error": repr(ex)[:300]}
@@ -541,8 +588,13 @@ def main():
     ap.add_argument("--only-rollout", action="store_true", help="time the open-loop rollout only (ncu runs)")
     ap.add_argument("--repeats", type=int, default=0, help="override the number of timed regions")
     ap.add_argument("--workload", default="binary-narrow-16x16", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU (experiments; the headline uses the workload's own)")
     args = ap.parse_args()
     select_workload(args.workload)
+    if args.envs > 0:
+        global WORKLOAD_NAME
+        WORKLOAD["envs_per_gpu"] = args.envs
+        WORKLOAD_NAME = "%s, %d envs/GPU (override), random-action rollout, auto-reset" % (args.workload, args.envs)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

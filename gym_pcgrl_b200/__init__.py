@@ -4,6 +4,7 @@ Public surface (mirrors gym_pcgrl): ``PcgrlEnv`` (single env, classic gym API), 
 (N lock-step envs, CUDA tensors), ``PROBLEMS`` / ``REPRESENTATIONS`` registries and ``make(id)`` for
 the ``"{problem}-{representation}-v0"`` ids (gym_pcgrl/__init__.py:6-12).
 """
+from .async_env import AsyncGroupedEnv
 from .envs.pcgrl_env import BatchedPcgrlEnv, HostRolloutIO, HostStepIO, PcgrlEnv
 from .envs.probs import PROBLEMS
 from .envs.reps import REPRESENTATIONS
@@ -22,4 +23,4 @@ def make(env_id, num_envs=None, **kwargs):
     return BatchedPcgrlEnv(spec["prob"], spec["rep"], num_envs=num_envs, **kwargs)
 
 
-__all__ = ["PcgrlEnv", "BatchedPcgrlEnv", "HostStepIO", "HostRolloutIO", "PROBLEMS", "REPRESENTATIONS", "REGISTRY", "make"]
+__all__ = ["PcgrlEnv", "BatchedPcgrlEnv", "AsyncGroupedEnv", "HostStepIO", "HostRolloutIO", "PROBLEMS", "REPRESENTATIONS", "REGISTRY", "make"]

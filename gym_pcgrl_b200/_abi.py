@@ -80,6 +80,7 @@ class PcgrlHostIO(C.Structure):
         ("reward", C.c_void_p), ("done", C.c_void_p), ("info_stats", C.c_void_p),
         ("d_staging", C.c_void_p), ("h_staging", C.c_void_p), ("staging_bytes", C.c_size_t),
         ("mode", C.c_int32), ("synced", C.c_int32), ("reset_base", C.c_int64), ("change_base", C.c_int64),
+        ("pending", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("PCGRL_B200_LIB") or os.path.join(_HERE, "csrc", "libp
 EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pcgrl_scratch_bytes",
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
            "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host",
-           "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats", "pcgrl_reset_cpu", "pcgrl_step_cpu", "pcgrl_get_stats_cpu"]
+           "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats", "pcgrl_reset_cpu", "pcgrl_step_cpu", "pcgrl_get_stats_cpu",
+           "pcgrl_step_host_begin", "pcgrl_step_host_end"]
 
 _lib = None
 
@@ -53,6 +54,10 @@ def lib():
         L.pcgrl_seed.argtypes = [C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int, C.c_void_p]
         L.pcgrl_step_host.restype = C.c_int
         L.pcgrl_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_step_host_begin.restype = C.c_int
+        L.pcgrl_step_host_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pcgrl_step_host_end.restype = C.c_int
+        L.pcgrl_step_host_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.pcgrl_rollout_host.restype = C.c_int
         L.pcgrl_rollout_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_int, C.c_void_p]

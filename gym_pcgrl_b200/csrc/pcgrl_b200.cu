@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   uint32_t row = (uint32_t)e;
   for (int t = 0; t < T; t++, row += (uint32_t)n) {
     const int32_t* act = actions + (size_t)(row * (uint32_t)adim);
+    if (t + 2 < T)  // the action rows of the next steps are independent of the state: pull them towards L1 now
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)((row + 2u * (uint32_t)n) * (uint32_t)adim)));
     iteration++;  // pcgrl_env.py:130
     int old[NS];
 #pragma unroll
@@ -883,8 +885,11 @@ static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
                          uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   if constexpr (PROB == PCGRL_PROB_BINARY) {
     // Rollouts of maps with at most 16 (8) rows: two (four) envs per warp, decoupled in time (pcgrl_packed.cuh).
-    // PCGRL_PACKED=0 keeps the one-env-per-warp kernel (A/B comparison); single steps always use it.
-    static const bool packed = !(getenv("PCGRL_PACKED") && atoi(getenv("PCGRL_PACKED")) == 0);
+    // OPT-IN (PCGRL_PACKED=1): bit-exact, but measured SLOWER than one env per warp on B200 at every batch size
+    // (binary-narrow 16x16, 128 steps per launch: 6.2e8 vs 9.3e8 env-steps/s at 4096 envs, 9.0e8 vs 1.35e9 at 65536;
+    // profiles/r02_summary.md): the per-group state machine costs ~15 instructions per wave against 10.5, a packed
+    // pass lasts as long as its slower env, and half as many warps hide less latency.  Kept for A/B runs.
+    static const bool packed = getenv("PCGRL_PACKED") && atoi(getenv("PCGRL_PACKED")) == 1;
     if (packed && !sg.base && T >= PCGRL_PACKED_MIN_T && cfg->height <= 16 && cfg->representation <= PCGRL_REP_WIDE) {
       if (cfg->height <= 8) {
         const int epc = PACKED_WPB * 4;
@@ -1131,9 +1136,13 @@ extern "C" size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n) {
   return staging_layout(n, staging_slots(n), cfg->width * cfg->height).total;
 }
 
-extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, pcgrl_host_io* io,
-                               int n, void* stream) {
+// pcgrl_step_host = pcgrl_step_host_begin (enqueue: actions in, step kernels, results towards pinned host memory) +
+// pcgrl_step_host_end (wait for / poll the stream, then patch the host arrays).  io->pending carries the state between
+// the two: 0 idle, 1 delta transport in flight, 2 full copies in flight.
+extern "C" int pcgrl_step_host_begin(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, pcgrl_host_io* io,
+                                     int n, void* stream) {
   if (!io || !io->actions || !io->reward || !io->done || !d_actions) return fail(-1, "NULL host io pointer");
+  if (io->pending) return fail(-1, "pcgrl_step_host_begin: the previous step of this io block has not been ended");
   int rc = check_common(cfg, b, n);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1142,8 +1151,6 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   const bool wide = cfg->representation == PCGRL_REP_WIDE;
   const bool delta = io->mode == 1;
   const size_t hb = (size_t)heat_bytes(*cfg);
-  uint8_t* const heat8 = (uint8_t*)io->heatmap;
-  uint16_t* const heat16 = (uint16_t*)io->heatmap;
   if (delta && (!io->d_staging || !io->h_staging || io->staging_bytes < pcgrl_host_staging_bytes(cfg, n)))
     return fail(-1, "mode 1 needs d_staging / h_staging of pcgrl_host_staging_bytes() bytes");
   HT_BEGIN();
@@ -1170,60 +1177,8 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
     cudaMemcpyAsync(io->h_staging, io->d_staging, L.total, cudaMemcpyDeviceToHost, s);
     if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
     HT(2);
-    rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
-    if (rc) return rc;
-    HT(3);
-    // reward / done / cursor arrive in their final layout; the observation arrays are patched from the change list
-    const uint8_t* hs = (const uint8_t*)io->h_staging;
-    const uint32_t total_resets = ((const uint32_t*)hs)[0], total_changes = ((const uint32_t*)hs)[1];
-    memcpy(io->reward, hs + L.reward_off, sizeof(double) * (size_t)n);
-    memcpy(io->done, hs + L.done_off, (size_t)n);
-    const uint8_t* hpos = hs + L.pos_off;
-    if (io->pos && !wide) memcpy(io->pos, hpos, 2 * (size_t)n);
-    const ChangeRecord* rec = (const ChangeRecord*)(hs + L.rec_off);
-    const uint8_t* slots = hs + L.slot_off;
-    uint32_t nchg = total_changes - (uint32_t)io->change_base;
-    if (nchg > (uint32_t)n) nchg = (uint32_t)n;
-    bool overflow = false;
-    const uint32_t PF = 8;  // the records scatter over the 2 x n x H x W host arrays: fetch the target lines ahead
-    for (uint32_t k = 0; k < nchg; k++) {
-      if (k + PF < nchg) {
-        const ChangeRecord& f = rec[k + PF];
-        const size_t fe = f.env_kind & 0xffffffu;
-        if (fe < (size_t)n) {
-          if (io->map) __builtin_prefetch(io->map + fe * cells + f.cell, 1);
-          if (io->heatmap) __builtin_prefetch(heat8 + hb * (fe * cells + (wide ? (size_t)f.cell : (size_t)hpos[2 * fe + 1] * cfg->width + hpos[2 * fe])), 1);
-        }
-      }
-      const ChangeRecord r = rec[k];
-      const size_t e = r.env_kind & 0xffffffu;
-      const uint32_t kind = r.env_kind >> 24;
-      if (e >= (size_t)n) continue;
-      if (kind == PCGRL_REC_RESET) {
-        if (r.slot == 0xFF) overflow = true;
-        else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
-        if (io->heatmap) memset(heat8 + hb * e * cells, 0, hb * cells);
-      } else {
-        if (kind == PCGRL_REC_MULTI) {
-          if (r.slot == 0xFF) overflow = true;
-          else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
-        } else if (io->map) {
-          io->map[e * cells + r.cell] = r.tile;
-        }
-        if (io->heatmap) {
-          const size_t hi = e * cells + (wide ? (size_t)r.cell : (size_t)hpos[2 * e + 1] * cfg->width + hpos[2 * e]);
-          if (hb == 2) heat16[hi] += 1; else heat8[hi] += 1;
-        }
-      }
-    }
-    io->reset_base = (int64_t)total_resets;
-    io->change_base = (int64_t)total_changes;
-    HT(4);
-    if (overflow && io->map) {  // more whole-map updates than staging slots in one step: fetch the whole map batch
-      cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
-      rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host (map refetch)");
-    }
-    return rc;
+    io->pending = 1;
+    return 0;
   }
 
   // full copies (mode 0, or the first / re-arming call of mode 1)
@@ -1236,9 +1191,94 @@ extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, 
   cudaMemcpyAsync(io->reward, b->reward, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->done, b->done, (size_t)n, cudaMemcpyDeviceToHost, s);
   if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
-  rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
-  if (delta && rc == 0) { io->synced = 1; io->reset_base = 0; io->change_base = 0; }
+  io->pending = 2;
+  return 0;
+}
+
+extern "C" int pcgrl_step_host_end(const pcgrl_config* cfg, const pcgrl_buffers* b, pcgrl_host_io* io, int n, void* stream,
+                                   int wait) {
+  if (!cfg || !b || !io) return fail(-1, "NULL argument");
+  if (!io->pending) return fail(-1, "pcgrl_step_host_end: no step in flight on this io block");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!wait) {
+    const cudaError_t q = cudaStreamQuery(s);
+    if (q == cudaErrorNotReady) return 1;  // still running: call again (nothing was consumed)
+    if (q != cudaSuccess) return cuda_rc(q, "pcgrl_step_host_end");
+  }
+  HT_BEGIN();
+  int rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host");
+  if (rc) return rc;
+  HT(3);
+  const size_t cells = (size_t)cfg->width * cfg->height;
+  const bool wide = cfg->representation == PCGRL_REP_WIDE;
+  const size_t hb = (size_t)heat_bytes(*cfg);
+  uint8_t* const heat8 = (uint8_t*)io->heatmap;
+  uint16_t* const heat16 = (uint16_t*)io->heatmap;
+  if (io->pending == 2) {
+    io->pending = 0;
+    if (io->mode == 1) { io->synced = 1; io->reset_base = 0; io->change_base = 0; }
+    return 0;
+  }
+  io->pending = 0;
+  const StagingLayout L = staging_layout(n, staging_slots(n), (int)cells);
+  // reward / done / cursor arrive in their final layout; the observation arrays are patched from the change list
+  const uint8_t* hs = (const uint8_t*)io->h_staging;
+  const uint32_t total_resets = ((const uint32_t*)hs)[0], total_changes = ((const uint32_t*)hs)[1];
+  memcpy(io->reward, hs + L.reward_off, sizeof(double) * (size_t)n);
+  memcpy(io->done, hs + L.done_off, (size_t)n);
+  const uint8_t* hpos = hs + L.pos_off;
+  if (io->pos && !wide) memcpy(io->pos, hpos, 2 * (size_t)n);
+  const ChangeRecord* rec = (const ChangeRecord*)(hs + L.rec_off);
+  const uint8_t* slots = hs + L.slot_off;
+  uint32_t nchg = total_changes - (uint32_t)io->change_base;
+  if (nchg > (uint32_t)n) nchg = (uint32_t)n;
+  bool overflow = false;
+  const uint32_t PF = 8;  // the records scatter over the 2 x n x H x W host arrays: fetch the target lines ahead
+  for (uint32_t k = 0; k < nchg; k++) {
+    if (k + PF < nchg) {
+      const ChangeRecord& f = rec[k + PF];
+      const size_t fe = f.env_kind & 0xffffffu;
+      if (fe < (size_t)n) {
+        if (io->map) __builtin_prefetch(io->map + fe * cells + f.cell, 1);
+        if (io->heatmap) __builtin_prefetch(heat8 + hb * (fe * cells + (wide ? (size_t)f.cell : (size_t)hpos[2 * fe + 1] * cfg->width + hpos[2 * fe])), 1);
+      }
+    }
+    const ChangeRecord r = rec[k];
+    const size_t e = r.env_kind & 0xffffffu;
+    const uint32_t kind = r.env_kind >> 24;
+    if (e >= (size_t)n) continue;
+    if (kind == PCGRL_REC_RESET) {
+      if (r.slot == 0xFF) overflow = true;
+      else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
+      if (io->heatmap) memset(heat8 + hb * e * cells, 0, hb * cells);
+    } else {
+      if (kind == PCGRL_REC_MULTI) {
+        if (r.slot == 0xFF) overflow = true;
+        else if (io->map) memcpy(io->map + e * cells, slots + (size_t)r.slot * cells, cells);
+      } else if (io->map) {
+        io->map[e * cells + r.cell] = r.tile;
+      }
+      if (io->heatmap) {
+        const size_t hi = e * cells + (wide ? (size_t)r.cell : (size_t)hpos[2 * e + 1] * cfg->width + hpos[2 * e]);
+        if (hb == 2) heat16[hi] += 1; else heat8[hi] += 1;
+      }
+    }
+  }
+  io->reset_base = (int64_t)total_resets;
+  io->change_base = (int64_t)total_changes;
+  HT(4);
+  if (overflow && io->map) {  // more whole-map updates than staging slots in one step: fetch the whole map batch
+    cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
+    rc = cuda_rc(cudaStreamSynchronize(s), "pcgrl_step_host (map refetch)");
+  }
   return rc;
+}
+
+extern "C" int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, pcgrl_host_io* io,
+                               int n, void* stream) {
+  const int rc = pcgrl_step_host_begin(cfg, b, d_actions, io, n, stream);
+  if (rc) return rc;
+  return pcgrl_step_host_end(cfg, b, io, n, stream, 1);
 }
 
 extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* b, int32_t* d_actions, double* d_reward,

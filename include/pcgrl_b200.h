@@ -194,10 +194,26 @@ typedef struct pcgrl_host_io {
   int32_t synced;         /* in/out, mode 1: host arrays are in sync with the device state */
   int64_t reset_base;     /* in/out, mode 1: running counters of staged whole-map updates / change records */
   int64_t change_base;    /*                 (library-maintained)                                            */
+  int32_t pending;        /* library-maintained: a pcgrl_step_host_begin of this block awaits its _end (init 0) */
+  int32_t reserved;
 } pcgrl_host_io;
 size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n);
 int pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions,
                     pcgrl_host_io* io, int n, void* stream);
+/*
+ * The same call split in two, for asynchronous vector-env bindings (the step_async / step_wait pair of the reference's
+ * SubprocVecEnv, utils.py:60-71 -- here per ENV GROUP: a caller that shards its batch over several pcgrl_buffers +
+ * streams keeps every group in flight and serves whichever finishes first, so one env stuck in a capped A* search
+ * (solver problems, smb) delays its own group only):
+ *   pcgrl_step_host_begin  enqueues everything on `stream` and returns at once;
+ *   pcgrl_step_host_end    wait != 0: blocks until the step is complete; wait == 0: returns 1 if it is still running
+ *                          (call again later), else completes it.  On return 0 the host arrays hold the step's results.
+ * pcgrl_step_host(...) == begin + end(wait = 1).  One step per io block may be in flight.
+ */
+int pcgrl_step_host_begin(const pcgrl_config* cfg, const pcgrl_buffers* bufs, int32_t* d_actions,
+                          pcgrl_host_io* io, int n, void* stream);
+int pcgrl_step_host_end(const pcgrl_config* cfg, const pcgrl_buffers* bufs, pcgrl_host_io* io, int n,
+                        void* stream, int wait);
 
 /*
  * pcgrl_rollout_host: T consecutive PcgrlEnv.step calls on HOST buffers in one call -- the open-loop form of the

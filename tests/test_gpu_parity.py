@@ -743,58 +743,71 @@ def test_smb_more_envs_than_resident_warps_and_tiny_power():
     np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"])
 
 
-PACKED_CASES = [
-    # (env id, kwargs, n envs, T, rounds) -- binary rollouts with T >= 8 run k_rollout_packed_binary<16 | 8>
-    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 513, 128, 3),
-    ("binary-narrow-v0", {}, 300, 400, 2),                                            # 14x14 default, long: MT19937 twists inside
-    ("binary-turtle-v0", dict(width=11, height=11, change_percentage=0.2), 129, 96, 2),
-    ("binary-wide-v0", dict(width=16, height=16, change_percentage=0.1), 64, 64, 3),
-    ("binary-narrow-v0", dict(width=8, height=8, change_percentage=0.3), 257, 200, 2),     # four envs per warp
-    ("binary-wide-v0", dict(width=20, height=7, change_percentage=0.3), 70, 80, 2),
-    ("binary-narrow-v0", dict(width=3, height=2, change_percentage=0.5, random_tile=False), 19, 50, 2),
-    ("binary-turtle-v0", dict(width=32, height=16, change_percentage=0.05, warp=True), 33, 120, 2),
-    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2, random_start=False, random_probs=False), 7, 64, 3),
-    ("binary-narrow-v0", dict(width=12, height=9, change_percentage=0.2), 1, 40, 2),
+def test_packed_rollout_kernel_matches_oracle():
+    """The opt-in multi-env-per-warp rollout kernel (csrc/pcgrl_packed.cuh, PCGRL_PACKED=1 -- read once per process,
+    hence the child pytest run): tests/gpu_packed_cases.py against the oracle."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PCGRL_PACKED="1")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "gpu_packed_cases.py"), "-x", "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1200)
+    assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+ASYNC_GROUP_CASES = [
+    ("sokoban-wide-v0", dict(probs={"empty": 0.7, "solid": 0.1, "player": 0.07, "crate": 0.065, "target": 0.065}), 256, 8, 40),
+    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.2), 192, 4, 60),
+    ("smb-narrow-v0", dict(width=40, height=10, change_percentage=0.3), 96, 6, 40),
 ]
 
 
-@pytest.mark.parametrize("case", PACKED_CASES, ids=["%s-%d" % (c[0], i) for i, c in enumerate(PACKED_CASES)])
-def test_packed_rollout_matches_oracle(case):
-    """The multi-env-per-warp rollout kernel (run-ahead + packed wave engine, csrc/pcgrl_packed.cuh) against the oracle:
-    every step's reward / done, the complete state after each fragment, the RNG streams at the end."""
+@pytest.mark.parametrize("case", ASYNC_GROUP_CASES, ids=[c[0] for c in ASYNC_GROUP_CASES])
+def test_async_grouped_env_equals_synchronous_batch(case):
+    """AsyncGroupedEnv (pcgrl_step_host_begin / _end, one stream per env group, groups served in completion order):
+    every env must see exactly the results it gets in one synchronous batch -- only the batching differs."""
     import torch
-    env_id, kwargs, n, T, rounds = case
-    env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
-    states = np.stack([util.randomstate_words(4000 + i) for i in range(n)])
-    env.set_rng_states(states)
-    env.reset()
-    ref = oracle.OracleEnv(env.native_config, n, threads=8)
-    ref.set_rng_states(states)
-    ref.reset()
-    wide = env_id.split("-")[1] == "wide"
-    arng = np.random.RandomState(21)
-    ndone = 0
-    for rnd in range(rounds):
-        acts = np.stack([random_actions(env, arng, n) for _ in range(T)])
-        rew, done = env.rollout(torch.from_numpy(acts).cuda())
-        rew, done = t2n(rew), t2n(done).astype(np.uint8)
-        for k in range(T):
-            ref.step(acts[k])
-            ctx = "%s round %d step %d" % (env_id, rnd, k)
-            np.testing.assert_array_equal(rew[k], ref["reward"], err_msg=ctx + " reward")
-            np.testing.assert_array_equal(done[k], ref["done"], err_msg=ctx + " done")
-            ndone += int(ref["done"].sum())
-        assert_state_equal(env, ref, 2, "%s round %d" % (env_id, rnd), wide)
-        np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, :3], ref["info_stats"][:, :3])
-        np.testing.assert_array_equal(t2n(env._tens["info_stats"])[:, 14:], ref["info_stats"][:, 14:])
-        np.testing.assert_array_equal(t2n(env._tens["reward"]), ref["reward"])
-        np.testing.assert_array_equal(t2n(env._tens["done"]), ref["done"])
-        # a few single steps in between: the one-env-per-warp kernel continues from the packed kernel's state
-        for k in range(3):
-            a = random_actions(env, arng, n)
-            env.step(torch.from_numpy(a).cuda())
-            ref.step(a)
-        assert_state_equal(env, ref, 2, "%s round %d + steps" % (env_id, rnd), wide)
-    np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"], err_msg="rng state")
-    np.testing.assert_array_equal(t2n(env._tens["tile_prob"]), ref["tile_prob"], err_msg="tile_prob")
-    assert ndone > 0 or n < 8
+    from gym_pcgrl_b200 import AsyncGroupedEnv
+    env_id, kwargs, n, groups, steps = case
+    prob, rep = env_id.split("-")[:2]
+    states = np.stack([util.randomstate_words(8000 + i) for i in range(n)])
+    sync = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
+    sync.set_rng_states(states)
+    sync.reset()
+    aenv = AsyncGroupedEnv(prob, rep, num_envs=n, groups=groups, device="cuda", seed=0, with_info=True)
+    if kwargs:
+        aenv.adjust_param(**kwargs)
+        aenv.adjust_param(**kwargs)
+    aenv.set_rng_states(states)
+    aenv.reset()
+    m = aenv.per_group
+    arng = np.random.RandomState(31)
+    acts = np.stack([random_actions(sync, arng, n) for _ in range(steps)])        # action of env i at ITS step t
+    # reference results from the synchronous batch
+    want = []
+    for t in range(steps):
+        obs, r, d, info = sync.step(torch.from_numpy(acts[t]).cuda())
+        want.append((t2n(obs["map"]).copy(), t2n(obs["heatmap"]).copy(), t2n(r).copy(), t2n(d).copy(), t2n(sync._tens["info_stats"]).copy()))
+    step = [0] * groups
+    order = list(range(groups))
+    arng.shuffle(order)
+    for g in order:                                                                 # groups start in a scrambled order
+        aenv.send(g, acts[0, g * m:(g + 1) * m])
+    served = 0
+    while served < groups * steps:
+        for g in aenv.recv(wait=True):
+            t = step[g]
+            sl = slice(g * m, (g + 1) * m)
+            io = aenv.io[g]
+            ctx = "%s group %d step %d" % (env_id, g, t)
+            np.testing.assert_array_equal(io.map.numpy(), want[t][0][sl], err_msg=ctx)
+            np.testing.assert_array_equal(io.heatmap.numpy(), want[t][1][sl], err_msg=ctx)
+            np.testing.assert_array_equal(io.reward.numpy(), want[t][2][sl], err_msg=ctx)
+            np.testing.assert_array_equal(io.done.numpy().astype(bool), want[t][3][sl], err_msg=ctx)
+            np.testing.assert_array_equal(io.info_stats.numpy(), want[t][4][sl], err_msg=ctx)
+            served += 1
+            step[g] += 1
+            if step[g] < steps:
+                aenv.send(g, acts[step[g], sl])
+    assert not any(aenv.in_flight) and all(s == steps for s in step)
+    aenv.check_status()

@@ -418,15 +418,20 @@ class Bench:
         for t in range(8):
             io.struct.actions = base + t * stride
             env.step_host(io)
+        # wall clock: the K-step region is run `per` times inside one barrier bracket (the NCCL barrier itself costs about
+        # as much as one step, so a bracket around a single 20-step region would charge it to the steps); ms per REGION
+        per = max(1, min(R, 400 // max(1, K)))
         out = []
-        for r in range(R):
+        for r in range(max(3, R // per)):
             self.barrier()
             t0 = time.perf_counter()
-            for t in range(K):
-                io.struct.actions = base + (8 + t) * stride
-                env.step_host(io)
+            for rep in range(per):
+                for t in range(K):
+                    io.struct.actions = base + (8 + t) * stride
+                    env.step_host(io)
+            t1 = time.perf_counter()
             self.barrier()
-            out.append((time.perf_counter() - t0) * 1e3)
+            out.append((t1 - t0) * 1e3 / per)
         return out, io, float(io.reward.sum())
 
     def time_e2e_rollout(self, env, K, chunk, R, seed):
@@ -439,15 +444,18 @@ class Bench:
         base, stride = acts_h.data_ptr(), acts_h.stride(0) * 4 * chunk
         rio.struct.actions = base
         env.rollout_host(rio)
+        per = max(1, min(R, 400 // max(1, K)))
         out = []
-        for r in range(R):
+        for r in range(max(3, R // per)):
             self.barrier()
             t0 = time.perf_counter()
-            for c in range(ncalls):
-                rio.struct.actions = base + (1 + c) * stride
-                env.rollout_host(rio)
+            for rep in range(per):
+                for c in range(ncalls):
+                    rio.struct.actions = base + (1 + c) * stride
+                    env.rollout_host(rio)
+            t1 = time.perf_counter()
             self.barrier()
-            out.append((time.perf_counter() - t0) * 1e3)
+            out.append((t1 - t0) * 1e3 / per)
         return out, rio, ncalls * chunk
 
     # -- asynchronous grouped stepping (opt-in API): every env group keeps one step in flight on its own stream

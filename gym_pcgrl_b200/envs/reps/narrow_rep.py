@@ -32,4 +32,26 @@ class NarrowRepresentation(Representation):
         })
 
     def get_observation(self):
+        if self._env is None:
+            return self._cursor_observation()
         return OrderedDict({"pos": self._env._bufs["pos"], "map": self._env._bufs["map"]})
+
+    def update(self, action):
+        """narrow_rep.py:99-114 on batched tensors (plugin path): write tile a-1 at the cursor, then move the cursor
+        (random, or raster scan); the returned (x, y) is the cursor AFTER the move."""
+        import torch
+        m, x, y = self._plugin_tensors()
+        n, h, w = m.shape
+        a = torch.as_tensor(action, device=m.device).reshape(n).long()
+        idx = torch.arange(n, device=m.device)
+        change = self._write_tile(idx, x, y, (a - 1).clamp(min=0), a > 0)
+        if self._random_tile:
+            self._x = torch.randint(0, w, (n,), generator=self._gen, device=m.device)
+            self._y = torch.randint(0, h, (n,), generator=self._gen, device=m.device)
+        else:
+            nx = x + 1
+            wrap = nx >= w
+            ny = torch.where(wrap, y + 1, y)
+            self._x = torch.where(wrap, torch.zeros_like(nx), nx)
+            self._y = torch.where(ny >= h, torch.zeros_like(ny), ny)
+        return change, self._x, self._y

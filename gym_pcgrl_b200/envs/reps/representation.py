@@ -18,6 +18,8 @@ class Representation:
         self._random = None
         self._seed = None
         self._env = None
+        self._x = self._y = None    # cursor tensors [N] on the plugin path
+        self._gen = None            # torch generator of the plugin env
         self.seed()
 
     def seed(self, seed=None):
@@ -52,9 +54,30 @@ class Representation:
         raise NotImplementedError('get_observation is not implemented')
 
     def update(self, action):
-        """Applying an action outside PcgrlEnv.step is not offered: the tile write is fused with
-        get_stats / get_reward in the step kernel (csrc/pcgrl_step.cuh)."""
-        raise NotImplementedError('update runs inside the fused step kernel; call env.step(actions)')
+        """Batched ``update(actions) -> (change [N], x [N], y [N])`` on the plugin path (envs/plugin_env.py); edits
+        ``self._map``.  Inside ``BatchedPcgrlEnv`` the built-in representations never get here: their tile write is
+        fused with get_stats / get_reward in the step kernel.  Subclasses of the base class must implement it
+        (representation.py:102-103)."""
+        raise NotImplementedError('update is not implemented')
+
+    # -- helpers for the torch implementations of the built-in representations (plugin path only)
+    def _plugin_tensors(self):
+        if self._env is not None:
+            raise NotImplementedError('update runs inside the fused step kernel; call env.step(actions)')
+        return self._map, self._x, self._y
+
+    def _write_tile(self, idx, x, y, tile, active):
+        """map[i, y[i], x[i]] = tile[i] where active[i]; returns change [N] (0 / 1)."""
+        import torch
+        m = self._map
+        old = m[idx, y, x]
+        change = active & (old != tile.to(m.dtype))
+        m[idx[change], y[change], x[change]] = tile[change].to(m.dtype)
+        return change.to(torch.int64)
+
+    def _cursor_observation(self):
+        import torch
+        return {"pos": torch.stack([self._x, self._y], dim=1).to(torch.uint8), "map": self._map}
 
     def render(self, lvl_image, tile_size, border_size):
         return lvl_image

@@ -33,4 +33,25 @@ class TurtleRepresentation(Representation):
         })
 
     def get_observation(self):
+        if self._env is None:
+            return self._cursor_observation()
         return OrderedDict({"pos": self._env._bufs["pos"], "map": self._env._bufs["map"]})
+
+    def update(self, action):
+        """turtle_rep.py:101-129 on batched tensors (plugin path): actions 0..3 move the cursor (clamp or wrap), an
+        action >= 4 writes tile a-4 at the cursor."""
+        import torch
+        m, x, y = self._plugin_tensors()
+        n, h, w = m.shape
+        a = torch.as_tensor(action, device=m.device).reshape(n).long()
+        dx = torch.tensor([d[0] for d in self._dirs] + [0], device=m.device)[a.clamp(max=4)]
+        dy = torch.tensor([d[1] for d in self._dirs] + [0], device=m.device)[a.clamp(max=4)]
+        nx, ny = x + dx, y + dy
+        if self._warp:
+            nx, ny = nx % w, ny % h
+        else:
+            nx, ny = nx.clamp(0, w - 1), ny.clamp(0, h - 1)
+        self._x, self._y = nx, ny
+        idx = torch.arange(n, device=m.device)
+        change = self._write_tile(idx, nx, ny, (a - 4).clamp(min=0), a >= 4)
+        return change, self._x, self._y

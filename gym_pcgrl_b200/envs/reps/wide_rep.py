@@ -17,4 +17,16 @@ class WideRepresentation(Representation):
         })
 
     def get_observation(self):
+        if self._env is None:
+            return {"map": self._map}
         return {"map": self._env._bufs["map"]}
+
+    def update(self, action):
+        """wide_rep.py:67-70 on batched tensors (plugin path): write action[2] at (x = action[0], y = action[1])."""
+        import torch
+        m, _, _ = self._plugin_tensors()
+        n = m.shape[0]
+        a = torch.as_tensor(action, device=m.device).reshape(n, 3).long()
+        idx = torch.arange(n, device=m.device)
+        change = self._write_tile(idx, a[:, 0], a[:, 1], a[:, 2], torch.ones(n, dtype=torch.bool, device=m.device))
+        return change, a[:, 0], a[:, 1]

@@ -811,3 +811,56 @@ def test_async_grouped_env_equals_synchronous_batch(case):
                 aenv.send(g, acts[step[g], sl])
     assert not any(aenv.in_flight) and all(s == steps for s in step)
     aenv.check_status()
+
+
+def test_plugin_path_builtin_problem_with_user_representation():
+    """A user-defined Representation driving a BUILT-IN problem on the plugin path (envs/plugin_env.py): the statistics
+    come from the native pcgrl_get_stats operator on the plugin's CUDA maps; checked against the oracle's get_stats and a
+    numpy restatement of the step bookkeeping."""
+    import torch
+    from gym_pcgrl_b200 import PluginBatchedEnv, spaces
+    from gym_pcgrl_b200._config import build_config
+    from gym_pcgrl_b200.envs.reps.representation import Representation
+
+    class RowPaint(Representation):
+        name = "rowpaint"
+
+        def get_action_space(self, width, height, num_tiles):
+            return spaces.MultiDiscrete([height, num_tiles])
+
+        def get_observation_space(self, width, height, num_tiles):
+            return spaces.Dict({"map": spaces.Box(low=0, high=num_tiles - 1, dtype=np.uint8, shape=(height, width))})
+
+        def get_observation(self):
+            return {"map": self._map}
+
+        def update(self, action):            # paint three cells of row action[0] starting at the cursor column
+            n, h, w = self._map.shape
+            a = torch.as_tensor(action, device=self._map.device).reshape(n, 2).long()
+            idx = torch.arange(n, device=self._map.device)
+            change = torch.zeros(n, dtype=torch.int64, device=self._map.device)
+            for k in range(3):
+                change += self._write_tile(idx, (self._x + k) % w, a[:, 0], a[:, 1], torch.ones(n, dtype=torch.bool, device=self._map.device))
+            self._x = (self._x + 3) % w
+            return change, self._x, a[:, 0]
+
+    n = 64
+    env = PluginBatchedEnv("zelda", RowPaint, num_envs=n, device="cuda", seed=5, auto_reset=False)
+    env.adjust_param(width=11, height=16, change_percentage=0.2)
+    env.adjust_param(width=11, height=16, change_percentage=0.2)
+    obs = env.reset()
+    cfg = build_config(env._prob, __import__("gym_pcgrl_b200").REPRESENTATIONS["wide"](), 1, 1, auto_reset=False)
+    names = env._prob.stat_names
+    rng = np.random.RandomState(1)
+    prev_stats = oracle.get_stats(cfg, t2n(obs["map"]), threads=4)[:, :7]
+    for t in range(25):
+        a = np.stack([rng.randint(16, size=n), rng.randint(8, size=n)], axis=1)
+        obs, reward, done, info = env.step(a)
+        want = oracle.get_stats(cfg, t2n(obs["map"]), threads=4)[:, :7]
+        got = np.stack([t2n(env._rep_stats[k]) for k in names], axis=1)
+        np.testing.assert_array_equal(got, want, err_msg="step %d" % t)
+        # zelda_prob.py:124-142 through the torch mirror of get_range_reward == the oracle's reward on the same stats pair
+        new_d = {k: torch.from_numpy(want[:, i]) for i, k in enumerate(names)}
+        old_d = {k: torch.from_numpy(prev_stats[:, i]) for i, k in enumerate(names)}
+        np.testing.assert_array_equal(t2n(reward), env._prob.get_reward(new_d, old_d).numpy(), err_msg="reward %d" % t)
+        prev_stats = want

@@ -1339,25 +1339,40 @@ static int cpu_supported(const pcgrl_config* cfg) {
   if (!cfg) return fail(-1, "config is NULL");
   int rc = pcgrl_config_validate(cfg);
   if (rc) return rc;
-  if (cfg->problem != PCGRL_PROB_SMB) return fail(-2, "host twin not available for this problem (warp-cooperative bitboard kernels): use the CUDA entry point");
+  if (cfg->problem != PCGRL_PROB_SMB && cfg->problem != PCGRL_PROB_BINARY && cfg->problem != PCGRL_PROB_ZELDA)
+    return fail(-2, "host twin not available for this problem (GPU search kernels): use the CUDA entry point");
   return 0;
 }
 struct HostWorkOwner {
   pcgrl_smb::HostWork hw;
-  explicit HostWorkOwner(int power) { hw.heap = (pcgrl_smb::u64*)malloc(sizeof(pcgrl_smb::u64) * pcgrl_smb::heap_entries(power)); }
+  explicit HostWorkOwner(const pcgrl_config* cfg) {
+    memset(&hw, 0, sizeof(hw));
+    hw.heap = (pcgrl_smb::u64*)malloc(sizeof(pcgrl_smb::u64) * pcgrl_smb::heap_entries(cfg->problem == PCGRL_PROB_SMB ? cfg->solver_power : 1));
+  }
   ~HostWorkOwner() { free(hw.heap); }
 };
+// per-env "touched" bitmap: smb keeps it in the scratch buffer, the other problems have none
+static uint32_t* host_touched(const pcgrl_config* cfg, const pcgrl_buffers* b, pcgrl_smb::HostWork& hw, int n, int e) {
+  if (cfg->problem != PCGRL_PROB_SMB) return hw.no_touch;
+  return pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power).touched + (size_t)e * pcgrl_smb::LEVEL_WORDS;
+}
+static int host_buffers_ok(const pcgrl_config* cfg, const pcgrl_buffers* b, int n) {
+  if (!b || n <= 0) return fail(-1, "bad buffers");
+  const size_t need = pcgrl_scratch_bytes(cfg, n);
+  if (need && (!b->scratch || b->scratch_bytes < need)) return fail(-1, "scratch buffer too small: see pcgrl_scratch_bytes()");
+  return 0;
+}
 
 extern "C" int pcgrl_reset_cpu(const pcgrl_config* cfg, const pcgrl_buffers* b, const uint8_t* mask, int n) {
   int rc = cpu_supported(cfg);
   if (rc) return rc;
-  if (!b || n <= 0 || !b->scratch || b->scratch_bytes < pcgrl_scratch_bytes(cfg, n)) return fail(-1, "bad buffers / scratch too small");
-  HostWorkOwner w(cfg->solver_power);
+  rc = host_buffers_ok(cfg, b, n);
+  if (rc) return rc;
+  HostWorkOwner w(cfg);
   if (!w.hw.heap) return fail(-1, "out of memory");
-  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power);
   for (int e = 0; e < n; e++) {
     if (mask && !mask[e]) continue;
-    pcgrl_smb::host_reset_env(cfg, b, e, w.hw, sc.touched + (size_t)e * pcgrl_smb::LEVEL_WORDS);
+    pcgrl_smb::host_reset_env(cfg, b, e, w.hw, host_touched(cfg, b, w.hw, n, e));
     b->reward[e] = 0.0;
     b->done[e] = 0;
     for (int i = 0; i < PCGRL_MAX_STATS; i++) b->info_stats[(size_t)e * PCGRL_MAX_STATS + i] = (i < 8) ? b->stats[(size_t)e * PCGRL_MAX_STATS + i] : 0;
@@ -1368,11 +1383,12 @@ extern "C" int pcgrl_reset_cpu(const pcgrl_config* cfg, const pcgrl_buffers* b, 
 extern "C" int pcgrl_step_cpu(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int n) {
   int rc = cpu_supported(cfg);
   if (rc) return rc;
-  if (!b || !actions || n <= 0 || !b->scratch || b->scratch_bytes < pcgrl_scratch_bytes(cfg, n)) return fail(-1, "bad buffers / scratch too small");
-  HostWorkOwner w(cfg->solver_power);
+  if (!actions) return fail(-1, "actions is NULL");
+  rc = host_buffers_ok(cfg, b, n);
+  if (rc) return rc;
+  HostWorkOwner w(cfg);
   if (!w.hw.heap) return fail(-1, "out of memory");
-  pcgrl_smb::Scratch sc = pcgrl_smb::scratch_view(b->scratch, n, cfg->solver_power);
-  for (int e = 0; e < n; e++) pcgrl_smb::host_step_env(cfg, b, actions, e, w.hw, sc.touched + (size_t)e * pcgrl_smb::LEVEL_WORDS);
+  for (int e = 0; e < n; e++) pcgrl_smb::host_step_env(cfg, b, actions, e, w.hw, host_touched(cfg, b, w.hw, n, e));
   return 0;
 }
 
@@ -1380,15 +1396,11 @@ extern "C" int pcgrl_get_stats_cpu(const pcgrl_config* cfg, const uint8_t* maps,
   int rc = cpu_supported(cfg);
   if (rc) return rc;
   if (!maps || !stats_out || n <= 0) return fail(-1, "NULL argument");
-  HostWorkOwner w(cfg->solver_power);
+  HostWorkOwner w(cfg);
   if (!w.hw.heap) return fail(-1, "out of memory");
   uint32_t touched[pcgrl_smb::LEVEL_WORDS];
   const size_t cells = (size_t)cfg->width * cfg->height;
-  for (int e = 0; e < n; e++) {
-    int32_t st[8];
-    pcgrl_smb::host_get_stats(cfg, maps + (size_t)e * cells, touched, w.hw, st);
-    for (int i = 0; i < PCGRL_MAX_STATS; i++) stats_out[(size_t)e * PCGRL_MAX_STATS + i] = (i < 8) ? st[i] : 0;
-  }
+  for (int e = 0; e < n; e++) pcgrl_smb::host_get_stats(cfg, maps + (size_t)e * cells, touched, w.hw, stats_out + (size_t)e * PCGRL_MAX_STATS);
   return 0;
 }
 

@@ -456,7 +456,7 @@ __device__ __forceinline__ int floor_dist(uint32_t from, uint32_t floor_m, int H
 }
 
 // G/helper.py:366-376 get_range_reward in fp64 (bounds may be +-inf)
-__device__ __forceinline__ double range_reward(double nv, double ov, double low, double high) {
+__host__ __device__ __forceinline__ double range_reward(double nv, double ov, double low, double high) {
   if (nv >= low && nv <= high && ov >= low && ov <= high) return 0.0;
   if (ov <= high && nv <= high) return fmin(nv, low) - fmin(ov, low);
   if (ov >= low && nv >= low) return fmax(ov, high) - fmax(nv, high);

@@ -1,6 +1,8 @@
 // pcgrl_problems.cuh -- Problem.get_stats / get_reward / get_episode_over on bitboards, one warp per env.
 // Reference: gym_pcgrl/envs/probs/{binary,zelda,sokoban,ddave,mdungeon}_prob.py (cited per function).
 #pragma once
+#include <math.h>
+
 #include "pcgrl_device.cuh"
 
 namespace pcgrl {
@@ -98,10 +100,10 @@ __device__ __noinline__ void map_stats_shared(const Board& b, const pcgrl_config
 // Problem.get_reward: fp64, terms summed left to right exactly as the reference writes them
 // (compiled with -fmad=false so no product is fused into the adds).
 template <int PROB>
-__device__ __forceinline__ double problem_reward(const pcgrl_config& cfg, const int* n, const int* o) {
+__host__ __device__ __forceinline__ double problem_reward(const pcgrl_config& cfg, const int* n, const int* o) {
   const double* w = cfg.reward_weight;
   const int32_t* ip = cfg.iparam;
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const double INF = HUGE_VAL;
   if (PROB == PCGRL_PROB_BINARY) {  // binary_prob.py:98-106
     // get_range_reward on integers is exact in int32: (regions, 1, 1) follows helper.py:366-376 case by case and
     // (path, inf, inf) always takes the second case, min(new, inf) - min(old, inf) = new - old; the two products and
@@ -141,7 +143,7 @@ __device__ __forceinline__ double problem_reward(const pcgrl_config& cfg, const 
 
 // Problem.get_episode_over
 template <int PROB>
-__device__ __forceinline__ bool problem_over(const pcgrl_config& cfg, const int* n, const int* start) {
+__host__ __device__ __forceinline__ bool problem_over(const pcgrl_config& cfg, const int* n, const int* start) {
   const int32_t* ip = cfg.iparam;
   if (PROB == PCGRL_PROB_BINARY) return n[0] == 1 && n[1] - start[1] >= ip[0];   // binary_prob.py:119-120
   if (PROB == PCGRL_PROB_ZELDA) return n[5] >= ip[1] && n[6] >= ip[2];            // zelda_prob.py:155-156

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include "pcgrl_env.cuh"
+#include "pcgrl_host_twin.cuh"
 #include "pcgrl_smb.cuh"
 
 namespace pcgrl_smb {
@@ -346,12 +347,32 @@ static inline Launch launch_plan(const pcgrl_config* cfg, int n, int sm_count) {
 // ------------------------------------------------------------------------------------------------
 struct HostWork {
   uint32_t solid[LEVEL_WORDS], visited[VISITED_WORDS];
+  uint32_t no_touch[32 * ROW_WORDS + 8];  // all-zero "touched" bitmap for the problems without search skipping
   u64* heap;
 };
 
+static inline int host_nstats(const pcgrl_config* cfg) {
+  return cfg->problem == PCGRL_PROB_BINARY ? 2 : cfg->problem == PCGRL_PROB_ZELDA ? 7 : 8;
+}
+// Problem.get_stats: smb = scans + A* play-through (this file), binary / zelda = host bitboards (pcgrl_host_twin.cuh)
 static inline void host_get_stats(const pcgrl_config* cfg, const uint8_t* map, uint32_t* touched, HostWork& hw, int32_t* st) {
-  scan_stats(map, cfg->width, cfg->height, st);
-  run_game_scalar(map, cfg->width, cfg->height, cfg->solver_power, hw.solid, touched, hw.visited, hw.heap, st, nullptr);
+  for (int i = 0; i < PCGRL_MAX_STATS; i++) st[i] = 0;
+  if (cfg->problem == PCGRL_PROB_SMB) {
+    scan_stats(map, cfg->width, cfg->height, st);
+    run_game_scalar(map, cfg->width, cfg->height, cfg->solver_power, hw.solid, touched, hw.visited, hw.heap, st, nullptr);
+  } else {
+    pcgrl_host::get_stats(cfg, map, st);
+  }
+}
+static inline double host_reward(const pcgrl_config* cfg, const int32_t* n, const int32_t* o) {
+  if (cfg->problem == PCGRL_PROB_BINARY) return pcgrl::problem_reward<PCGRL_PROB_BINARY>(*cfg, n, o);
+  if (cfg->problem == PCGRL_PROB_ZELDA) return pcgrl::problem_reward<PCGRL_PROB_ZELDA>(*cfg, n, o);
+  return get_reward(*cfg, n, o);
+}
+static inline bool host_over(const pcgrl_config* cfg, const int32_t* n, const int32_t* start) {
+  if (cfg->problem == PCGRL_PROB_BINARY) return pcgrl::problem_over<PCGRL_PROB_BINARY>(*cfg, n, start);
+  if (cfg->problem == PCGRL_PROB_ZELDA) return pcgrl::problem_over<PCGRL_PROB_ZELDA>(*cfg, n, start);
+  return episode_over(n);
 }
 
 static inline void host_reset_env(const pcgrl_config* cfg, const pcgrl_buffers* b, int e, HostWork& hw, uint32_t* touched) {
@@ -359,58 +380,68 @@ static inline void host_reset_env(const pcgrl_config* cfg, const pcgrl_buffers* 
   uint8_t* map = b->map + (size_t)e * cells;
   uint8_t* smap = b->start_map + (size_t)e * cells;
   uint32_t* rng_rep = b->rng + (size_t)e * 2 * PCGRL_MT_WORDS;
-  if ((cfg->flags & PCGRL_FLAG_RANDOM_START) || !b->start_valid[e]) {
-    gen_random_map(rng_rep, b->tile_prob + (size_t)e * PCGRL_MAX_TILES, cfg->num_tiles, cells, map, smap, nullptr);
+  double* tp = b->tile_prob + (size_t)e * PCGRL_MAX_TILES;
+  if ((cfg->flags & PCGRL_FLAG_RANDOM_START) || !b->start_valid[e]) {  // representation.py:40-45
+    gen_random_map(rng_rep, tp, cfg->num_tiles, cells, map, smap, nullptr);
     b->start_valid[e] = 1;
   } else {
     memcpy(map, smap, (size_t)cells);
   }
-  if (cfg->representation != PCGRL_REP_WIDE) {
+  if (cfg->representation != PCGRL_REP_WIDE) {  // narrow_rep.py:30-31, turtle_rep.py:32-33
     b->pos[2 * e] = (uint8_t)mt_randint(rng_rep, W);
     b->pos[2 * e + 1] = (uint8_t)mt_randint(rng_rep, H);
   }
-  int32_t st[8];
+  int32_t st[PCGRL_MAX_STATS];
   host_get_stats(cfg, map, touched, hw, st);
   for (int i = 0; i < S; i++) {
-    const int32_t v = (i < 8) ? st[i] : 0;
-    b->stats[(size_t)e * S + i] = v;
-    b->start_stats[(size_t)e * S + i] = v;
+    b->stats[(size_t)e * S + i] = st[i];
+    b->start_stats[(size_t)e * S + i] = st[i];  // problem.py:45-46
+  }
+  if (cfg->problem == PCGRL_PROB_BINARY && (cfg->flags & PCGRL_FLAG_RANDOM_PROBS)) {  // binary_prob.py:68-72 (problem stream)
+    tp[0] = mt_double(rng_rep + PCGRL_MT_WORDS);
+    tp[1] = 1 - tp[0];
   }
   const size_t hb = (cfg->flags & PCGRL_FLAG_HEAT_U16) ? 2 : 1;
-  memset((uint8_t*)b->heatmap + hb * (size_t)e * cells, 0, hb * (size_t)cells);
+  memset((uint8_t*)b->heatmap + hb * (size_t)e * cells, 0, hb * (size_t)cells);  // pcgrl_env.py:72
   b->iteration[e] = 0;
   b->changes[e] = 0;
 }
 
 static inline void host_step_env(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, int e, HostWork& hw,
                                  uint32_t* touched) {
-  const int W = cfg->width, H = cfg->height, cells = W * H, S = PCGRL_MAX_STATS;
+  const int W = cfg->width, H = cfg->height, cells = W * H, S = PCGRL_MAX_STATS, NS = host_nstats(cfg);
   const int adim = cfg->representation == PCGRL_REP_WIDE ? 3 : (cfg->representation == PCGRL_REP_NARROWCAST || cfg->representation == PCGRL_REP_TURTLECAST) ? 2
                    : cfg->representation == PCGRL_REP_NARROWMULTI ? 9 : 1;
   uint8_t* map = b->map + (size_t)e * cells;
   int32_t* st = b->stats + (size_t)e * S;
-  int32_t old[8];
-  for (int i = 0; i < 8; i++) old[i] = st[i];
+  int32_t old[PCGRL_MAX_STATS];
+  for (int i = 0; i < S; i++) old[i] = st[i];
   int x = 0, y = 0;
   if (cfg->representation != PCGRL_REP_WIDE) { x = b->pos[2 * e]; y = b->pos[2 * e + 1]; }
-  b->iteration[e] += 1;
+  b->iteration[e] += 1;  // pcgrl_env.py:130
   const Edit ed = apply_action(*cfg, actions + (size_t)e * adim, map, nullptr, touched, b->rng + (size_t)e * 2 * PCGRL_MT_WORDS, x, y);
   if (cfg->representation != PCGRL_REP_WIDE) { b->pos[2 * e] = (uint8_t)x; b->pos[2 * e + 1] = (uint8_t)y; }
-  if (ed.change > 0) {
+  if (ed.change > 0) {  // :135-138
     b->changes[e] += ed.change;
     const size_t hi = (size_t)e * cells + (size_t)ed.hy * W + ed.hx;
     if (cfg->flags & PCGRL_FLAG_HEAT_U16) ((uint16_t*)b->heatmap)[hi] += 1; else ((uint8_t*)b->heatmap)[hi] += 1;
-    int32_t ns[8];
-    scan_stats(map, W, H, ns);
-    if (ed.solidity_touched) run_game_scalar(map, W, H, cfg->solver_power, hw.solid, touched, hw.visited, hw.heap, ns, nullptr);
-    else { ns[5] = st[5]; ns[6] = st[6]; ns[7] = st[7]; }
-    for (int i = 0; i < 8; i++) st[i] = ns[i];
+    int32_t ns[PCGRL_MAX_STATS];
+    if (cfg->problem == PCGRL_PROB_SMB && !ed.solidity_touched) {  // exact search skipping (pcgrl_smb.cuh)
+      for (int i = 0; i < S; i++) ns[i] = 0;
+      scan_stats(map, W, H, ns);
+      ns[5] = st[5]; ns[6] = st[6]; ns[7] = st[7];
+    } else {
+      host_get_stats(cfg, map, touched, hw, ns);
+    }
+    for (int i = 0; i < S; i++) st[i] = ns[i];
   }
-  b->reward[e] = (ed.change > 0) ? get_reward(*cfg, st, old) : 0.0;
-  const bool done = episode_over(st) || b->changes[e] >= cfg->max_changes || b->iteration[e] >= cfg->max_iterations;
+  b->reward[e] = (ed.change > 0) ? host_reward(cfg, st, old) : 0.0;  // :142
+  const bool done = host_over(cfg, st, b->start_stats + (size_t)e * S) || b->changes[e] >= cfg->max_changes ||
+                    b->iteration[e] >= cfg->max_iterations;            // :143
   b->done[e] = done ? 1 : 0;
   int32_t* info = b->info_stats + (size_t)e * S;
-  for (int i = 0; i < S; i++) info[i] = (i < 8) ? st[i] : 0;
+  for (int i = 0; i < S; i++) info[i] = (i < NS) ? st[i] : 0;
+  if (cfg->problem == PCGRL_PROB_BINARY) info[2] = st[1] - b->start_stats[(size_t)e * S + 1];  // binary_prob.py:137 "path-imp"
   info[PCGRL_INFO_ITERATION] = b->iteration[e];
   info[PCGRL_INFO_CHANGES] = b->changes[e];
   if (done && (cfg->flags & PCGRL_FLAG_AUTO_RESET)) host_reset_env(cfg, b, e, hw, touched);

@@ -135,10 +135,3 @@ def test_smb_host_twin_batched_matches_oracle(case):
         ndone += int(ref["done"].sum())
     np.testing.assert_array_equal(env._tens["rng"].numpy().view(np.uint32), ref["rng"])
     assert ndone > 0
-
-
-def test_host_twin_is_explicit_and_refuses_bitboard_problems():
-    """device="cpu" is an explicit choice; problems without a host twin fail loudly instead of falling back."""
-    env = PcgrlEnv("binary", "narrow", device="cpu")
-    with pytest.raises(_native.NativeError, match="host twin not available"):
-        env.reset()

@@ -189,74 +189,90 @@ SMB_HD void st_update(const Level& L, State& s, int dir_x, int dir_y) {  // engi
   s.y = ny;
 }
 
-// The open list: element i of CPython's list sits in storage slot i + 1, so that the child pair (2i+1, 2i+2) is one
-// aligned 16-byte couple; slots below fast_cap are in `fast` (shared memory on the device), the rest in `slow`.
+// The open list: element i of CPython's list sits in storage slot i + 1 (a 1-based heap: parent s / 2, children 2s and
+// 2s + 1), so that a child pair is one aligned 16-byte couple; slots below fast_cap are in `fast` (shared memory on the
+// device), the rest in `slow`.  The sift loops work on local copies of the three fields (HeapRef) -- the accessors were
+// 47 % of the kernel's instructions while they re-read the struct through a reference (profiles/r02_summary.md).
 struct Heap {
   u64* fast;
   u64* slow;
   int fast_cap;  // even
 };
-SMB_HD u64 hget(const Heap& h, int i) { const int s = i + 1; return s < h.fast_cap ? h.fast[s] : h.slow[s - h.fast_cap]; }
-SMB_HD void hset(const Heap& h, int i, u64 v) { const int s = i + 1; if (s < h.fast_cap) h.fast[s] = v; else h.slow[s - h.fast_cap] = v; }
-SMB_HD int e_prio(u64 e, int exit_x, int balance) { return exit_x - e_x(e) + balance * e_depth(e); }  // Node.__lt__ (engine.py:52-53)
+struct HeapRef {
+  u64* fast;
+  u64* slow_biased;  // slow - fast_cap: slot s >= fast_cap lives at slow_biased[s]
+  int cap;
+};
+SMB_HD HeapRef heap_ref(const Heap& h) { HeapRef r; r.fast = h.fast; r.slow_biased = h.slow - h.fast_cap; r.cap = h.fast_cap; return r; }
+SMB_HD u64* slot(const HeapRef& h, int s) { return (s < h.cap ? h.fast : h.slow_biased) + s; }
+// priority of Node.__lt__ (engine.py:52-53): (exit - x) + balance * depth -- both fields sit in the low word of the entry
+SMB_HD int e_prio(u64 e, int exit_x, int balance) {
+  const uint32_t lo = (uint32_t)e;
+  return exit_x - (int)(lo & 127u) + balance * (int)((lo >> 15) & 0x3fffu);
+}
 
 // Lib/heapq.py: heappush -> _siftdown(heap, 0, len-1); heappop -> _siftup(heap, 0) (which ends in a _siftdown)
-SMB_HD void heap_siftdown(const Heap& hp, int startpos, int pos, u64 item, int exit_x, int bal) {
+SMB_HD void heap_siftdown(const HeapRef& h, int s, u64 item, int exit_x, int bal) {  // s = slot of the hole (1-based)
   const int pi = e_prio(item, exit_x, bal);
-  while (pos > startpos) {
-    const int parentpos = (pos - 1) >> 1;
-    const u64 parent = hget(hp, parentpos);
-    if (pi < e_prio(parent, exit_x, bal)) { hset(hp, pos, parent); pos = parentpos; continue; }
+  while (s > 1) {
+    const int ps = s >> 1;
+    const u64 parent = *slot(h, ps);
+    if (pi < e_prio(parent, exit_x, bal)) { *slot(h, s) = parent; s = ps; continue; }
     break;
   }
-  hset(hp, pos, item);
+  *slot(h, s) = item;
 }
-SMB_HD u64 heap_pop(const Heap& hp, int& n, int exit_x, int bal) {
-  const u64 last = hget(hp, --n);
+SMB_HD u64 heap_pop(const HeapRef& h, int& n, int exit_x, int bal) {  // n = number of entries (slots 1..n)
+  const u64 last = *slot(h, n);
+  n--;
   if (n == 0) return last;
-  const u64 ret = hget(hp, 0);
-  int pos = 0, childpos = 1;
-  while (childpos < n) {
-    const int rightpos = childpos + 1;
-    u64 child = hget(hp, childpos);
-    if (rightpos < n) {
-      const u64 right = hget(hp, rightpos);
-      if (!(e_prio(child, exit_x, bal) < e_prio(right, exit_x, bal))) { childpos = rightpos; child = right; }
+  const u64 ret = h.fast[1];
+  int s = 1, c = 2;
+  while (c <= n) {
+    const u64* pair = slot(h, c);  // c is even and fast_cap is even: both children are in the same region
+    u64 child = pair[0];
+    if (c < n) {
+      const u64 right = pair[1];
+      if (!(e_prio(child, exit_x, bal) < e_prio(right, exit_x, bal))) { c++; child = right; }
     }
-    hset(hp, pos, child);
-    pos = childpos;
-    childpos = 2 * pos + 1;
+    *slot(h, s) = child;
+    s = c;
+    c = 2 * s;
   }
-  heap_siftdown(hp, 0, pos, last, exit_x, bal);
+  heap_siftdown(h, s, last, exit_x, bal);
   return ret;
 }
 
 // AStarAgent.getSolution (engine.py:105-129) on a CLEARED visited bitmap; returns true on a win; `result` = the winning
 // node, else the best node (lowest heuristic, then lowest cost).
-SMB_HDN bool astar_core(const Level& L, u64 root, int balance, int max_iter, const Heap& hp, uint32_t* visited, u64& result,
+SMB_HDN bool astar_core(const Level& level, u64 root, int balance, int max_iter, const Heap& hp, uint32_t* visited, u64& result,
                         int& iterations_out) {
-  const int dirs_x[4] = {0, 1, 0, 1}, dirs_y[4] = {0, 0, -1, -1};  // engine.py:3
+  const Level L = level;  // local copies: the loop must not re-read the structs through the references
+  const HeapRef h = heap_ref(hp);
+  const int exit_x = L.exit_x, height = L.height;
   int nheap = 1, iterations = 0, best_h = 0, best_depth = 0;
   bool have_best = false;
   u64 best = root;
-  hset(hp, 0, root);
+  h.fast[1] = root;
   while ((iterations < max_iter || max_iter <= 0) && nheap > 0) {
     iterations++;
-    const u64 cur = heap_pop(hp, nheap, L.exit_x, balance);
-    if (e_y(cur) >= L.height) continue;                                              // checkLose
-    if (e_x(cur) >= L.exit_x) { result = cur; iterations_out = iterations; return true; }  // checkWin
+    const u64 cur = heap_pop(h, nheap, exit_x, balance);
+    if (e_y(cur) >= height) continue;                                              // checkLose
+    if (e_x(cur) >= exit_x) { result = cur; iterations_out = iterations; return true; }  // checkWin
     const int key = e_key(cur);
     const uint32_t bit = 1u << (key & 31);
-    if (visited[key >> 5] & bit) continue;
-    const int h = L.exit_x - e_x(cur), depth = e_depth(cur);
-    if (!have_best || h < best_h || (h == best_h && depth < best_depth)) { best = cur; best_h = h; best_depth = depth; have_best = true; }
-    visited[key >> 5] |= bit;
+    const uint32_t seen = visited[key >> 5];
+    if (seen & bit) continue;
+    const int hh = exit_x - e_x(cur), depth = e_depth(cur);
+    if (!have_best || hh < best_h || (hh == best_h && depth < best_depth)) { best = cur; best_h = hh; best_depth = depth; have_best = true; }
+    visited[key >> 5] = seen | bit;
     const State cs = unpack(cur);
-    for (int d = 0; d < 4; d++) {
+#pragma unroll
+    for (int d = 0; d < 4; d++) {  // engine.py:3 directions (0,0) (1,0) (0,-1) (1,-1)
       State c = cs;
-      st_update(L, c, dirs_x[d], dirs_y[d]);
-      heap_siftdown(hp, 0, nheap, pack(c, depth + 1), L.exit_x, balance);
+      st_update(L, c, d & 1, (d & 2) ? -1 : 0);
       nheap++;
+      heap_siftdown(h, nheap, pack(c, depth + 1), exit_x, balance);
     }
   }
   result = best;

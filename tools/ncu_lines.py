@@ -62,6 +62,8 @@ def main():
     # pick the SASS function whose mangled name contains the kernel substring and instantiation
     inst = re.search(r"<\(int\)(\d+)>", b["name"])
     cands = [f for f in funcs if ksub in f and (inst is None or ("ILi%sE" % inst.group(1)) in f) and not f.startswith("_ZN") or (ksub in f and inst and ("ILi%sE" % inst.group(1)) in f)]
+    if not cands:   # namespaced kernels (pcgrl_smb::...)
+        cands = [f for f in funcs if ksub in f]
     fn = funcs[cands[0]]
     per_line = collections.defaultdict(lambda: [0, 0])
     total_i = total_s = 0

@@ -16,7 +16,7 @@ EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pc
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
            "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host",
            "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats", "pcgrl_reset_cpu", "pcgrl_step_cpu", "pcgrl_get_stats_cpu",
-           "pcgrl_step_host_begin", "pcgrl_step_host_end"]
+           "pcgrl_step_host_begin", "pcgrl_step_host_end", "pcgrl_render"]
 
 _lib = None
 
@@ -78,6 +78,8 @@ def lib():
         L.pcgrl_step_cpu.argtypes = [C.POINTER(_abi.PcgrlConfig), C.POINTER(_abi.PcgrlBuffers), C.c_void_p, C.c_int]
         L.pcgrl_get_stats_cpu.restype = C.c_int
         L.pcgrl_get_stats_cpu.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_int]
+        L.pcgrl_render.restype = C.c_int
+        L.pcgrl_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
         L.pcgrl_host_staging_bytes.restype = C.c_size_t
         L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:
@@ -192,4 +194,21 @@ def get_stats(prob, maps):
                                     status.data_ptr(), stream_ptr(dev)), "pcgrl_get_stats")
     if int(status[0].item()) != 0:
         raise NativeError("pcgrl_get_stats hit a device capacity limit (status=%s)" % status.tolist())
+    return out
+
+
+def render(prob, maps, pos=None):
+    """pcgrl_render: batched PcgrlEnv.render(mode='rgb_array') -> uint8 CUDA tensor [N, Hpx, Wpx, 3]."""
+    import torch
+    dev = require_cuda(maps.device)
+    maps = maps.to(torch.uint8).contiguous()
+    n, h, w = maps.shape
+    atlas = torch.as_tensor(prob.get_graphics()).to(device=dev, dtype=torch.uint8).contiguous()
+    tiles = prob.get_tile_types()
+    ts, (bw, bh) = int(prob._tile_size), prob._border_size
+    out = torch.empty((n, (h + 2 * bh) * ts, (w + 2 * bw) * ts, 3), dtype=torch.uint8, device=dev)
+    p = None if pos is None else pos.to(torch.uint8).contiguous()
+    with torch.cuda.device(dev):
+        check(lib().pcgrl_render(maps.data_ptr(), None if p is None else p.data_ptr(), atlas.data_ptr(), out.data_ptr(), n, h, w,
+                                 len(tiles), int(bw), int(bh), tiles.index(prob._border_tile), ts, stream_ptr(dev)), "pcgrl_render")
     return out

@@ -1430,6 +1430,20 @@ extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, con
   return cuda_rc(cudaGetLastError(), "pcgrl_obs_image launch");
 }
 
+extern "C" int pcgrl_render(const uint8_t* maps, const uint8_t* pos_or_null, const uint8_t* atlas, uint8_t* out, int n,
+                            int height, int width, int num_tiles, int border_w, int border_h, int border_tile, int tile_size,
+                            void* stream) {
+  if (!maps || !atlas || !out) return fail(-1, "NULL argument");
+  if (n <= 0 || height <= 0 || width <= 0) return fail(-1, "n, height, width must be > 0");
+  if (tile_size < 4 || (tile_size & 3)) return fail(-1, "tile_size must be a positive multiple of 4");
+  if (num_tiles < 1 || border_tile < 0 || border_tile >= num_tiles || border_w < 0 || border_h < 0) return fail(-1, "bad tile / border arguments");
+  const size_t quads = (size_t)n * (height + 2 * border_h) * tile_size * ((size_t)(width + 2 * border_w) * tile_size / 4);
+  unsigned blocks = (unsigned)((quads + 255) / 256 < 148u * 16u ? (quads + 255) / 256 : 148u * 16u);
+  k_render<<<blocks ? blocks : 1, 256, 0, (cudaStream_t)stream>>>(maps, pos_or_null, (const uint32_t*)atlas, (uint32_t*)out, n, height, width,
+                                                                 border_w, border_h, border_tile, tile_size);
+  return cuda_rc(cudaGetLastError(), "pcgrl_render launch");
+}
+
 extern "C" int pcgrl_action_map(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* flat_actions,
                                 int32_t* actions_out, int n, void* stream) {
   if (!cfg || !b || !flat_actions || !actions_out) return fail(-1, "NULL argument");

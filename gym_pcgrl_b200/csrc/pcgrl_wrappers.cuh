@@ -112,4 +112,38 @@ __global__ void k_action_map(const int32_t* __restrict__ flat, const uint8_t* __
   }
 }
 
+// PcgrlEnv.render (pcgrl_env.py:160-173) = Problem.render (probs/problem.py:134-156: a border of `border_tile`, every
+// map tile pasted as a tile_size x tile_size sprite) + the cursor frame of the narrow / turtle representations
+// (reps/narrow_rep.py:126-140: a 2-pixel red frame on the cursor tile) + convert("RGB"), for the whole batch:
+//   maps [n][H][W] u8, atlas [num_tiles][ts][ts][4] RGBA u8  ->  out [n][(H + 2 bh) ts][(W + 2 bw) ts][3] RGB u8.
+// HBM-write bound: one thread produces four horizontal pixels (12 bytes, three aligned 32-bit stores; ts % 4 == 0).
+__global__ void __launch_bounds__(256) k_render(const uint8_t* __restrict__ maps, const uint8_t* __restrict__ pos,
+                                                const uint32_t* __restrict__ atlas, uint32_t* __restrict__ out, int n, int H,
+                                                int W, int bw, int bh, int border_tile, int ts) {
+  const int wpx = (W + 2 * bw) * ts, hpx = (H + 2 * bh) * ts, quads = wpx >> 2;
+  const size_t total = (size_t)n * hpx * quads;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    const int qx = (int)(q % quads);
+    const size_t rest = q / quads;
+    const int py = (int)(rest % hpx), e = (int)(rest / hpx);
+    const int px = qx << 2, tx = px / ts - bw, ty = py / ts - bh, sx = px % ts, sy = py % ts;
+    const bool inside = tx >= 0 && tx < W && ty >= 0 && ty < H;
+    const int tile = inside ? (int)maps[((size_t)e * H + ty) * W + tx] : border_tile;
+    const uint4 rgba = *reinterpret_cast<const uint4*>(atlas + ((size_t)tile * ts + sy) * ts + sx);  // four RGBA pixels
+    uint32_t p[4] = {rgba.x, rgba.y, rgba.z, rgba.w};
+    if (pos && inside && tx == (int)pos[2 * e] && ty == (int)pos[2 * e + 1]) {
+      const bool edge_row = sy < 2 || sy >= ts - 2;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (edge_row || sx + k < 2 || sx + k >= ts - 2) p[k] = 0xff0000ffu;  // (255, 0, 0, 255) little-endian RGBA
+    }
+    // RGBA x 4 -> RGB x 4 = 12 bytes
+    const uint32_t w0 = (p[0] & 0xffffffu) | ((p[1] & 0xffu) << 24);
+    const uint32_t w1 = ((p[1] >> 8) & 0xffffu) | ((p[2] & 0xffffu) << 16);
+    const uint32_t w2 = ((p[2] >> 16) & 0xffu) | ((p[3] & 0xffffffu) << 8);
+    uint32_t* o = out + q * 3;
+    o[0] = w0; o[1] = w1; o[2] = w2;
+  }
+}
+
 }  // namespace pcgrl

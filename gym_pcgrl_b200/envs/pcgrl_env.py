@@ -233,8 +233,14 @@ class BatchedPcgrlEnv:
     def observation(self):
         return self._observation()
 
-    def render(self, mode='human'):
-        raise NotImplementedError("rendering is out of scope of the B200 hot path (SURVEY.md 2, row 7)")
+    def render(self, mode='rgb_array'):
+        """pcgrl_env.py:160-173 for the whole batch, on the GPU: RGB uint8 tensor [N, Hpx, Wpx, 3] (level + border +
+        the cursor frame of the cursor representations).  There is no window: mode='human' is not offered."""
+        if mode != 'rgb_array':
+            raise NotImplementedError("only mode='rgb_array' (a CUDA image batch) is offered")
+        if self._tens is None:
+            raise RuntimeError("call reset() before render()")
+        return self._prob.render(self._tens["map"], None if self._rep.name == "wide" else self._tens["pos"])
 
     def close(self):
         self._tens = None
@@ -466,8 +472,8 @@ class PcgrlEnv:
         return self._obs(obs), (int(r) if r == int(r) and self._prob.name in ("binary", "zelda") else r), \
             bool(done[0].item()), info
 
-    def render(self, mode='human'):
-        return self._batched.render(mode)
+    def render(self, mode='rgb_array'):
+        return self._batched.render(mode)[0].cpu().numpy()
 
     def close(self):
         self._batched.close()

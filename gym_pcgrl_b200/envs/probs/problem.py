@@ -151,8 +151,23 @@ class Problem:
     def get_debug_info(self, new_stats, old_stats):
         return {k: new_stats[k] for k in self.stat_names}
 
-    def render(self, map):
-        raise NotImplementedError("rendering is out of scope of the B200 hot path (SURVEY.md 2, row 7)")
+    def get_graphics(self):
+        """RGBA sprite atlas uint8 [num_tiles, tile_size, tile_size, 4].  Default = the grey levels of the reference's
+        base class (problem.py:137-141); assign ``self._graphics`` (same shape) to use real sprites."""
+        import numpy as np
+        if getattr(self, "_graphics", None) is None:
+            tiles = self.get_tile_types()
+            g = np.zeros((len(tiles), self._tile_size, self._tile_size, 4), np.uint8)
+            for i in range(len(tiles)):
+                g[i, :, :, :3] = int(i * 255 / len(tiles))
+                g[i, :, :, 3] = 255
+            self._graphics = g
+        return self._graphics
+
+    def render(self, maps, pos=None):
+        """Batched Problem.render (problem.py:134-156) on the GPU: uint8 CUDA maps [N,H,W] -> RGB uint8 [N,Hpx,Wpx,3]."""
+        from ... import _native
+        return _native.render(self, maps, pos)
 
 
 def _as_tensor(v):

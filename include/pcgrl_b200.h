@@ -253,6 +253,16 @@ int pcgrl_action_map(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const i
                      int32_t* actions_out, int n, void* stream);
 
 /*
+ * Batched PcgrlEnv.render(mode="rgb_array") (pcgrl_env.py:160-173 = Problem.render, probs/problem.py:134-156, + the cursor
+ * frame of the cursor representations, reps/narrow_rep.py:126-140, + convert("RGB")) -- SURVEY.md 8f row f4, no PIL:
+ *   maps [n][height][width] u8, pos [n][2] (x, y) or NULL (no cursor frame), atlas [num_tiles][ts][ts][4] RGBA u8 (16-byte
+ *   aligned) -> out [n][(height + 2 border_h) ts][(width + 2 border_w) ts][3] RGB u8.  tile_size ts % 4 == 0.
+ */
+int pcgrl_render(const uint8_t* maps, const uint8_t* pos_or_null, const uint8_t* atlas, uint8_t* out, int n,
+                 int height, int width, int num_tiles, int border_w, int border_h, int border_tile, int tile_size,
+                 void* stream);
+
+/*
  * smb (gym_pcgrl/envs/probs/smb_prob.py, probs/smb/engine.py).  The smb ENVIRONMENT runs through the
  * generic entry points above with cfg->problem = PCGRL_PROB_SMB (byte map, width <= 122, 3 <= height <= 16, solver_power
  * <= 16000; max_changes = 319 at the default size, hence PCGRL_FLAG_HEAT_U16).  The two functions below are the

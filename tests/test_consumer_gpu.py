@@ -18,7 +18,7 @@ def _numpy_render(m, pos, atlas, bw, bh, border_tile, ts):
             tile = m[y - bh, x - bw] if inside else border_tile
             img[y * ts:(y + 1) * ts, x * ts:(x + 1) * ts] = atlas[tile]
     if pos is not None:
-        x0, y0 = (pos[0] + bw) * ts, (pos[1] + bh) * ts
+        x0, y0 = (int(pos[0]) + bw) * ts, (int(pos[1]) + bh) * ts
         frame = np.zeros((ts, ts), bool)
         frame[:2, :] = frame[-2:, :] = frame[:, :2] = frame[:, -2:] = True
         img[y0:y0 + ts, x0:x0 + ts][frame] = (255, 0, 0, 255)

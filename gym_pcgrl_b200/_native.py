@@ -16,7 +16,8 @@ EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pc
            "pcgrl_reset", "pcgrl_step", "pcgrl_rollout", "pcgrl_get_stats", "pcgrl_seed", "pcgrl_step_host",
            "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host",
            "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats", "pcgrl_reset_cpu", "pcgrl_step_cpu", "pcgrl_get_stats_cpu",
-           "pcgrl_step_host_begin", "pcgrl_step_host_end", "pcgrl_render"]
+           "pcgrl_step_host_begin", "pcgrl_step_host_end", "pcgrl_render",
+           "pcgrl_linear_bf16", "pcgrl_linear_last_error"]
 
 _lib = None
 
@@ -80,6 +81,9 @@ def lib():
         L.pcgrl_get_stats_cpu.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_void_p, C.c_void_p, C.c_int]
         L.pcgrl_render.restype = C.c_int
         L.pcgrl_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+        L.pcgrl_linear_bf16.restype = C.c_int
+        L.pcgrl_linear_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.pcgrl_linear_last_error.restype = C.c_char_p
         L.pcgrl_host_staging_bytes.restype = C.c_size_t
         L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:
@@ -212,3 +216,22 @@ def render(prob, maps, pos=None):
         check(lib().pcgrl_render(maps.data_ptr(), None if p is None else p.data_ptr(), atlas.data_ptr(), out.data_ptr(), n, h, w,
                                  len(tiles), int(bw), int(bh), tiles.index(prob._border_tile), ts, stream_ptr(dev)), "pcgrl_render")
     return out
+
+
+def linear_bf16(x, weight, bias=None, relu=True):
+    """pcgrl_linear_bf16 (csrc/pcgrl_linear.cu, tcgen05 + TMEM + TMA): relu(x @ weight.T + bias) -> float32 [M, N].
+    x [M, K] and weight [N, K] are converted to contiguous bf16 if they are not already."""
+    import torch
+    dev = require_cuda(x.device)
+    xb = x.to(torch.bfloat16).contiguous()
+    wb = weight.to(device=dev, dtype=torch.bfloat16).contiguous()
+    m, k = xb.shape
+    n = wb.shape[0]
+    b = None if bias is None else bias.to(device=dev, dtype=torch.float32).contiguous()
+    y = torch.empty((m, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib().pcgrl_linear_bf16(xb.data_ptr(), wb.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), m, n, k,
+                                     1 if relu else 0, stream_ptr(dev))
+    if rc:
+        raise NativeError("pcgrl_linear_bf16 failed (rc=%d): %s" % (rc, lib().pcgrl_linear_last_error().decode()))
+    return y

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libpcgrl_b200.so")
-SOURCES = ["pcgrl_b200.cu"]
+SOURCES = ["pcgrl_b200.cu", "pcgrl_linear.cu"]
 import glob  # noqa: E402
 
 

@@ -1,0 +1,232 @@
+// pcgrl_linear.cu -- the one dense contraction next to the hot path: the 512-unit fully connected
+// layer of the reference's Cnn1 / Cnn2 feature extractors (model.py:15,23: fc1 over the flattened conv features),
+//   Y[M, N] = relu(X[M, K] . W[N, K]^T + b),  M = envs, K = 4*4*64 = 1024, N = 512 for the default policy,
+// as a hand-written sm_100a kernel: TMA (cp.async.bulk.tensor) stages 128 x 64 bf16 tiles of X and W in shared memory with
+// the 128-byte swizzle, ONE elected thread issues tcgen05.mma (cta_group::1, kind::f16, 128 x 128 x 16) accumulating in
+// TMEM, four epilogue warps read the accumulator back with tcgen05.ld, add the bias, apply the ReLU and store fp32.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (a warp may
+// only touch TMEM lanes [32 * (warp_id % 4), +32), so warps 2, 3, 4, 5 cover lane quarters 2, 3, 0, 1).
+// Pipelines: full[s] / empty[s] mbarriers between TMA and MMA over 4 smem stages; tmem_full between MMA and epilogue.
+// One 128 x 128 output tile per CTA (grid = N/128 x M/128: 4 x 32 = 128 CTAs for the default policy at 4096 envs).
+//
+// Descriptor encodings follow the public CUTLASS definitions (cute/arch/mma_sm100_desc.hpp: UMMA::SmemDescriptor,
+// UMMA::InstrDescriptor); every wait is bounded and traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace pcgrl_linear {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16, STAGES = 4, THREADS = 192;
+constexpr int TILE_A_BYTES = BLOCK_M * BLOCK_K * 2, TILE_B_BYTES = BLOCK_N * BLOCK_K * 2;
+constexpr int SMEM_BYTES = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr uint32_t TMEM_COLS = 128;  // fp32 accumulator: 128 lanes x 128 columns
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); spin++) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();  // a protocol bug must surface as a launch error, never as a hung GPU
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms stacked along M/N every 1024 bytes
+__device__ __forceinline__ uint64_t umma_smem_desc(const void* tile) {
+  const uint64_t addr = (uint64_t)((smem_u32(tile) >> 4) & 0x3FFFu);
+  const uint64_t sbo = (uint64_t)((8 * BLOCK_K * 2) >> 4);  // stride byte offset: 1024 B between 8-row groups
+  return addr | (0ull << 16) /* LBO unused: one swizzle atom along K */ | (sbo << 32) | (1ull << 46) /* version: sm_100 */ |
+         (2ull << 61) /* LayoutType::SWIZZLE_128B */;
+}
+// UMMA instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t INSTR_DESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(INSTR_DESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` once all MMAs issued so far have completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int M, int N,
+                                                            int K, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128: 1024-B aligned
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * TILE_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (TILE_A_BYTES + TILE_B_BYTES));
+  uint64_t* full = bars;                 // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);  // passes at once during the first trip round the ring
+        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+        tma_load_2d(smem_a + s * TILE_A_BYTES, &map_x, &full[s], kb * BLOCK_K, m0);
+        tma_load_2d(smem_b + s * TILE_B_BYTES, &map_w, &full[s], kb * BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: one thread drives the tensor core for the CTA =====
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        mbar_wait(&full[s], (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + s * TILE_B_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; k++)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {  // ===== epilogue: TMEM -> registers -> bias + ReLU -> global =====
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, +32)
+    const int row = m0 + quarter * 32 + lane;       // accumulator row m <-> TMEM lane m (M = 128, cta_group::1)
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        float* out = y + (size_t)row * N + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o;
+          float* of = &o.x;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int col = n0 + c0 + j + q;
+            float f = __uint_as_float(v[j + q]) + ((bias && col < N) ? bias[col] : 0.0f);
+            of[q] = relu ? fmaxf(f, 0.0f) : f;
+          }
+          if (n0 + c0 + j + 3 < N) *reinterpret_cast<float4*>(out + j) = o;
+          else for (int q = 0; q < 4; q++) if (n0 + c0 + j + q < N) out[j + q] = of[q];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major bf16 [rows, K] -> 2-D tensor map with a {BLOCK_K, 128} box and the 128-byte swizzle (zero fill out of bounds)
+static int make_map(CUtensorMap* map, const void* base, int rows, int K) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -2;
+}
+
+}  // namespace pcgrl_linear
+
+static thread_local char g_linear_err[256] = "";
+extern "C" const char* pcgrl_linear_last_error(void) { return g_linear_err; }
+
+// Y[M,N] (fp32, row-major) = act(X[M,K] . W[N,K]^T + bias[N]); X, W bf16 row-major device pointers (16-byte aligned,
+// K % 8 == 0); bias may be NULL; relu != 0 applies max(., 0).  Enqueues on `stream`; 0 = OK.
+extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, float* y, int M, int N, int K, int relu,
+                                 void* stream) {
+  using namespace pcgrl_linear;
+  if (!x_bf16 || !w_bf16 || !y) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
+  if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & 3)) { snprintf(g_linear_err, sizeof(g_linear_err), "need M, N, K > 0, K %% 8 == 0, N %% 4 == 0"); return -1; }
+  if (((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)y) & 15) { snprintf(g_linear_err, sizeof(g_linear_err), "pointers must be 16-byte aligned"); return -1; }
+  CUtensorMap mx, mw;
+  if (make_map(&mx, x_bf16, M, K) || make_map(&mw, w_bf16, N, K)) { snprintf(g_linear_err, sizeof(g_linear_err), "cuTensorMapEncodeTiled failed"); return -1; }
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(k_linear_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "smem opt-in: %s", cudaGetErrorString(ce)); return (int)ce; }
+    configured = true;
+  }
+  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M);
+  k_linear_bf16<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+  return 0;
+}

@@ -8,6 +8,7 @@ order ActionMap unravels flat actions in, wrappers.py:139-141).  Layers run thro
 the one hand-written contraction of this repo is csrc/pcgrl_linear.cu (opt-in for the 512-unit layer of Cnn1 / Cnn2).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -38,11 +39,16 @@ class _CnnBase(nn.Module):
             raise ValueError("observation %s is too small for three VALID 3x3 convolutions" % (obs_shape,))
         self.fc1 = _ortho(nn.Linear(h * w * 64, 512), math.sqrt(2))
         self.out_features = 512
+        # inference through the hand-written tcgen05 kernel (csrc/pcgrl_linear.cu); training keeps the autograd layer
+        self.use_tcgen05_fc = os.environ.get("PCGRL_TCGEN05_FC", "0") == "1"
 
     def forward(self, obs):                                   # obs: [N, H, W, C] any dtype
         x = obs.permute(0, 3, 1, 2).float()
         x = F.relu(self.c3(F.relu(self.c2(F.relu(self.c1(x))))))
         x = x.permute(0, 2, 3, 1).flatten(1)                  # conv_to_fc: (h, w, c) order
+        if self.use_tcgen05_fc and x.is_cuda and not torch.is_grad_enabled():
+            from . import _native
+            return _native.linear_bf16(x, self.fc1.weight, self.fc1.bias, relu=True)
         return F.relu(self.fc1(x))
 
 

@@ -288,6 +288,17 @@ int pcgrl_reset_cpu(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const ui
 int pcgrl_step_cpu(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* actions, int n);
 int pcgrl_get_stats_cpu(const pcgrl_config* cfg, const uint8_t* maps, int32_t* stats_out, int n);
 
+/*
+ * The dense contraction next to the path: the fully connected layer of the reference's policy
+ * feature extractors (model.py:15,23 `linear(layer_3, 'fc1', n_hidden=512)` + ReLU) as a tcgen05 / TMEM / TMA kernel.
+ *   y[M][N] (f32) = act(x[M][K] . w[N][K]^T + bias[N]);  x, w: bf16 row-major device pointers, 16-byte aligned, K % 8 == 0,
+ *   N % 4 == 0; bias may be NULL; relu != 0 applies max(., 0).  Only enqueues on `stream`.  Text of a failure:
+ *   pcgrl_linear_last_error().
+ */
+int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, float* y, int M, int N, int K,
+                      int relu, void* stream);
+const char* pcgrl_linear_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,7 +109,7 @@ def test_native_library_builds_loads_and_exports_every_symbol():
     lib = _native.lib()
     assert lib.pcgrl_abi_version() == _abi.ABI_VERSION
     header = open(os.path.join(ROOT, "include", "pcgrl_b200.h")).read()
-    declared = set(re.findall(r"\b(pcgrl_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(pcgrl_[a-z0-9_]+)\s*\(", header))
     declared -= {"pcgrl_last_error"} if False else set()
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for name in declared:

@@ -7,8 +7,10 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (a warp may
 // only touch TMEM lanes [32 * (warp_id % 4), +32), so warps 2, 3, 4, 5 cover lane quarters 2, 3, 0, 1).
-// Pipelines: full[s] / empty[s] mbarriers between TMA and MMA over 4 smem stages; tmem_full between MMA and epilogue.
-// One 128 x 128 output tile per CTA (grid = N/128 x M/128: 4 x 32 = 128 CTAs for the default policy at 4096 envs).
+// Pipelines: full[s] / empty[s] mbarriers between TMA and MMA over 4 smem stages; tmem_full[a] / tmem_empty[a] between MMA
+// and epilogue over 2 accumulator stages.
+// Persistent CTAs (one per SM) loop over 128 x 128 output tiles; the accumulator is double-buffered in TMEM so the epilogue of
+// one tile overlaps the main loop of the next (128 tiles = 128 CTAs for the default policy at 4096 envs).
 //
 // Descriptor encodings follow the public CUTLASS definitions (cute/arch/mma_sm100_desc.hpp: UMMA::SmemDescriptor,
 // UMMA::InstrDescriptor); every wait is bounded and traps instead of hanging the GPU.
@@ -22,8 +24,8 @@ namespace pcgrl_linear {
 
 constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16, STAGES = 4, THREADS = 192;
 constexpr int TILE_A_BYTES = BLOCK_M * BLOCK_K * 2, TILE_B_BYTES = BLOCK_N * BLOCK_K * 2;
-constexpr int SMEM_BYTES = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr uint32_t TMEM_COLS = 128;  // fp32 accumulator: 128 lanes x 128 columns
+constexpr int SMEM_BYTES = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /* alignment slack */ + 1024 /* barriers, TMEM slot, bias */;
+constexpr uint32_t TMEM_COLS = 256;  // two fp32 accumulator stages of 128 lanes x 128 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -77,6 +79,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: CTA b works on output tiles b, b + gridDim.x, ... (tile = m_block * tiles_n + n_block, so the CTAs that share
+// an X tile run at the same time and it is read from HBM once).  The accumulator is double-buffered in TMEM (2 x 128
+// columns): the epilogue of tile i overlaps the TMA / MMA main loop of tile i + 1.
 __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constant__ CUtensorMap map_x,
                                                             const __grid_constant__ CUtensorMap map_w,
                                                             const float* __restrict__ bias, float* __restrict__ y, int M, int N,
@@ -86,18 +95,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * TILE_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (TILE_A_BYTES + TILE_B_BYTES));
-  uint64_t* full = bars;                 // [STAGES] TMA -> MMA
-  uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* full = bars;                       // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + STAGES;             // [STAGES] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [2] MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // [BLOCK_N] bias of the current n-block (epilogue warps)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
+  const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N, tiles_m = (M + BLOCK_M - 1) / BLOCK_M, num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
@@ -110,63 +123,86 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);  // passes at once during the first trip round the ring
-        mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
-        tma_load_2d(smem_a + s * TILE_A_BYTES, &map_x, &full[s], kb * BLOCK_K, m0);
-        tma_load_2d(smem_b + s * TILE_B_BYTES, &map_w, &full[s], kb * BLOCK_K, n0);
+    if (lane == 0) {  // ===== TMA producer: one ring of smem stages across all tiles of this CTA =====
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);  // passes at once during the first trip round the ring
+          mbar_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+          tma_load_2d(smem_a + s * TILE_A_BYTES, &map_x, &full[s], kb * BLOCK_K, m0);
+          tma_load_2d(smem_b + s * TILE_B_BYTES, &map_w, &full[s], kb * BLOCK_K, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer: one thread drives the tensor core for the CTA =====
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % STAGES;
-        mbar_wait(&full[s], (kb / STAGES) & 1);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
+        const int as = lt & 1;
+        mbar_wait(&tmem_empty[as], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + s * TILE_B_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + s * TILE_B_BYTES);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; k++)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-          umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
-        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tmem_full[as]);  // accumulator of this tile complete
       }
-      umma_commit(tmem_full);    // accumulator complete
     }
-  } else {  // ===== epilogue: TMEM -> registers -> bias + ReLU -> global =====
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int quarter = warp & 3;                   // TMEM lanes [32 * quarter, +32)
-    const int row = m0 + quarter * 32 + lane;       // accumulator row m <-> TMEM lane m (M = 128, cta_group::1)
+  } else {  // ===== epilogue (warps 2-5): TMEM -> registers -> bias + ReLU -> global =====
+    const int quarter = warp & 3;  // TMEM lanes [32 * quarter, +32)
+    const int et = threadIdx.x - 64;  // 0..127
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N, as = lt & 1;
+      // stage this n-block's bias while the main loop of the tile is still running
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of bias_s are done
+      bias_s[et] = (bias && n0 + et < N) ? bias[n0 + et] : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[as], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + quarter * 32 + lane;  // accumulator row m <-> TMEM lane m (M = 128, cta_group::1)
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
-        float* out = y + (size_t)row * N + n0 + c0;
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= BLOCK_N) {  // last read of this accumulator stage: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty[as]);
+        }
+        if (row < M) {
+          float* out = y + (size_t)row * N + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          float* of = &o.x;
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            float* of = &o.x;
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int col = n0 + c0 + j + q;
-            float f = __uint_as_float(v[j + q]) + ((bias && col < N) ? bias[col] : 0.0f);
-            of[q] = relu ? fmaxf(f, 0.0f) : f;
+            for (int q = 0; q < 4; q++) {
+              const float f = __uint_as_float(v[j + q]) + bias_s[c0 + j + q];
+              of[q] = relu ? fmaxf(f, 0.0f) : f;
+            }
+            if (n0 + c0 + j + 3 < N) *reinterpret_cast<float4*>(out + j) = o;
+            else for (int q = 0; q < 4; q++) if (n0 + c0 + j + q < N) out[j + q] = of[q];
           }
-          if (n0 + c0 + j + 3 < N) *reinterpret_cast<float4*>(out + j) = o;
-          else for (int q = 0; q < 4; q++) if (n0 + c0 + j + q < N) out[j + q] = of[q];
         }
       }
     }
@@ -224,8 +260,10 @@ extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const f
     if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "smem opt-in: %s", cudaGetErrorString(ce)); return (int)ce; }
     configured = true;
   }
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M);
-  k_linear_bf16<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
+  static thread_local int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count < 1) sm_count = 148; }
+  const int tiles = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M);
+  k_linear_bf16<<<tiles < sm_count ? tiles : sm_count, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
   return 0;

@@ -22,10 +22,12 @@
 
 namespace pcgrl_linear {
 
-constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16, STAGES = 4, THREADS = 192;
-constexpr int TILE_A_BYTES = BLOCK_M * BLOCK_K * 2, TILE_B_BYTES = BLOCK_N * BLOCK_K * 2;
-constexpr int SMEM_BYTES = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /* alignment slack */ + 1024 /* barriers, TMEM slot, bias */;
-constexpr uint32_t TMEM_COLS = 256;  // two fp32 accumulator stages of 128 lanes x 128 columns
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16, STAGES = 4, THREADS = 192;
+constexpr int TILE_A_BYTES = BLOCK_M * BLOCK_K * 2;
+// BLOCK_N is a template parameter: 128 (more tiles: small problems fill the 148 SMs) or 256 (one third less operand
+// traffic per flop: large problems).  TMEM holds two fp32 accumulator stages of 128 lanes x BLOCK_N columns.
+template <int BN> __host__ __device__ constexpr int tile_b_bytes() { return BN * BLOCK_K * 2; }
+template <int BN> __host__ __device__ constexpr int smem_bytes() { return STAGES * (TILE_A_BYTES + tile_b_bytes<BN>()) + 1024 /* alignment slack */ + 2048 /* barriers, TMEM slot, bias */; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -65,14 +67,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const void* tile) {
          (2ull << 61) /* LayoutType::SWIZZLE_128B */;
 }
 // UMMA instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t INSTR_DESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+template <int BN> __host__ __device__ constexpr uint32_t instr_desc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(INSTR_DESC), "r"(accumulate)
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar` once all MMAs issued so far have completed
@@ -86,6 +90,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Persistent: CTA b works on output tiles b, b + gridDim.x, ... (tile = m_block * tiles_n + n_block, so the CTAs that share
 // an X tile run at the same time and it is read from HBM once).  The accumulator is double-buffered in TMEM (2 x 128
 // columns): the epilogue of tile i overlaps the TMA / MMA main loop of tile i + 1.
+template <int BLOCK_N>
 __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constant__ CUtensorMap map_x,
                                                             const __grid_constant__ CUtensorMap map_w,
                                                             const float* __restrict__ bias, float* __restrict__ y, int M, int N,
@@ -93,6 +98,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128: 1024-B aligned
   uint8_t* smem_a = smem;
+  constexpr int TILE_B_BYTES = tile_b_bytes<BLOCK_N>();
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   uint8_t* smem_b = smem + STAGES * TILE_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (TILE_A_BYTES + TILE_B_BYTES));
   uint64_t* full = bars;                       // [STAGES] TMA -> MMA
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
           const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + s * TILE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (kb | k) ? 1u : 0u);
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), instr_desc<BLOCK_N>(), (kb | k) ? 1u : 0u);
           umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
         umma_commit(&tmem_full[as]);  // accumulator of this tile complete
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
       const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N, as = lt & 1;
       // stage this n-block's bias while the main loop of the tile is still running
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of bias_s are done
-      bias_s[et] = (bias && n0 + et < N) ? bias[n0 + et] : 0.0f;
+      for (int c = et; c < BLOCK_N; c += 128) bias_s[c] = (bias && n0 + c < N) ? bias[n0 + c] : 0.0f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tmem_full[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -228,12 +235,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // row-major bf16 [rows, K] -> 2-D tensor map with a {BLOCK_K, 128} box and the 128-byte swizzle (zero fill out of bounds)
-static int make_map(CUtensorMap* map, const void* base, int rows, int K) {
+static int make_map(CUtensorMap* map, const void* base, int rows, int K, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, 128u};
+  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1u, 1u};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -2;
@@ -252,18 +259,23 @@ extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const f
   if (!x_bf16 || !w_bf16 || !y) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
   if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & 3)) { snprintf(g_linear_err, sizeof(g_linear_err), "need M, N, K > 0, K %% 8 == 0, N %% 4 == 0"); return -1; }
   if (((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)y) & 15) { snprintf(g_linear_err, sizeof(g_linear_err), "pointers must be 16-byte aligned"); return -1; }
-  CUtensorMap mx, mw;
-  if (make_map(&mx, x_bf16, M, K) || make_map(&mw, w_bf16, N, K)) { snprintf(g_linear_err, sizeof(g_linear_err), "cuTensorMapEncodeTiled failed"); return -1; }
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(k_linear_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "smem opt-in: %s", cudaGetErrorString(ce)); return (int)ce; }
-    configured = true;
-  }
   static thread_local int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count < 1) sm_count = 148; }
-  const int tiles = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + BLOCK_M - 1) / BLOCK_M);
-  k_linear_bf16<<<tiles < sm_count ? tiles : sm_count, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const bool wide = (N >= 256) && tiles_m * ((N + 255) / 256) >= sm_count;  // enough 128 x 256 tiles to fill every SM
+  const int bn = wide ? 256 : 128;
+  CUtensorMap mx, mw;
+  if (make_map(&mx, x_bf16, M, K, BLOCK_M) || make_map(&mw, w_bf16, N, K, bn)) { snprintf(g_linear_err, sizeof(g_linear_err), "cuTensorMapEncodeTiled failed"); return -1; }
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t c1 = cudaFuncSetAttribute(k_linear_bf16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>());
+    cudaError_t c2 = cudaFuncSetAttribute(k_linear_bf16<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>());
+    if (c1 != cudaSuccess || c2 != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "smem opt-in: %s", cudaGetErrorString(c1 != cudaSuccess ? c1 : c2)); return (int)(c1 != cudaSuccess ? c1 : c2); }
+    configured = true;
+  }
+  const int tiles = tiles_m * ((N + bn - 1) / bn), grid = tiles < sm_count ? tiles : sm_count;
+  if (wide) k_linear_bf16<256><<<grid, THREADS, smem_bytes<256>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
+  else k_linear_bf16<128><<<grid, THREADS, smem_bytes<128>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
   return 0;

@@ -5,7 +5,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-CASES = [(4096, 512, 1024, True), (128, 128, 64, False), (300, 132, 200, True), (1, 4, 8, False), (1000, 512, 3136, True)]
+CASES = [(4096, 512, 1024, True), (128, 128, 64, False), (300, 132, 200, True), (1, 4, 8, False), (1000, 512, 3136, True),
+         # enough 128 x 256 tiles to fill the SMs: the BLOCK_N = 256 instantiation (full and ragged in M and N)
+         (32768, 512, 256, True), (20001, 300, 136, False)]
 
 
 @pytest.mark.parametrize("m,n,k,relu", CASES)

@@ -93,8 +93,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constant__ CUtensorMap map_x,
                                                             const __grid_constant__ CUtensorMap map_w,
-                                                            const float* __restrict__ bias, float* __restrict__ y, int M, int N,
-                                                            int K, int relu) {
+                                                            const float* __restrict__ bias, void* __restrict__ y_out, int M, int N,
+                                                            int K, int relu, int out_bf16) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128: 1024-B aligned
   uint8_t* smem_a = smem;
@@ -197,18 +197,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
           mbar_arrive(&tmem_empty[as]);
         }
         if (row < M) {
-          float* out = y + (size_t)row * N + n0 + c0;
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            float* of = &o.x;
+          for (int j = 0; j < 32; j++) {
+            const float t = __uint_as_float(v[j]) + bias_s[c0 + j];
+            f[j] = relu ? fmaxf(t, 0.0f) : t;
+          }
+          if (out_bf16) {  // bf16 activations for the next layer (N % 8 == 0): 16-byte stores of eight values
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(y_out) + (size_t)row * N + n0 + c0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const float f = __uint_as_float(v[j + q]) + bias_s[c0 + j + q];
-              of[q] = relu ? fmaxf(f, 0.0f) : f;
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + c0 + j + 7 < N) {
+                uint4 o;
+                uint32_t* ow = &o.x;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  const __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 2 * q], f[j + 2 * q + 1]);
+                  ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
+                }
+                *reinterpret_cast<uint4*>(out + j) = o;
+              } else {
+                for (int q = 0; q < 8; q++) if (n0 + c0 + j + q < N) out[j + q] = __float2bfloat16_rn(f[j + q]);
+              }
             }
-            if (n0 + c0 + j + 3 < N) *reinterpret_cast<float4*>(out + j) = o;
-            else for (int q = 0; q < 4; q++) if (n0 + c0 + j + q < N) out[j + q] = of[q];
+          } else {
+            float* out = reinterpret_cast<float*>(y_out) + (size_t)row * N + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + c0 + j + 3 < N) *reinterpret_cast<float4*>(out + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              else for (int q = 0; q < 4; q++) if (n0 + c0 + j + q < N) out[j + q] = f[j + q];
+            }
           }
         }
       }
@@ -217,6 +235,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// im2col for NHWC activations: out[m][k] (bf16, k = (kh * KW + kw) * C + c, zero beyond 9C up to Kpad) for output pixel
+// m = (n * Ho + oy) * Wo + ox; input uint8 (observations) or bf16 (activations).  One thread per 8 consecutive k (16-byte
+// store); when C % 8 == 0 the eight values are one 16-byte load.  conv(x) = im2col(x) . W^T then runs on k_linear_bf16.
+template <typename InT>
+__global__ void __launch_bounds__(256) k_im2col(const InT* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int H, int W, int C,
+                                                int KS, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int chunks = Kpad >> 3;
+  const size_t total = (size_t)n * Ho * Wo * chunks;
+  const int Kreal = KS * KS * C;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(t % chunks);
+    const size_t m = t / chunks;
+    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), e = (int)(m / ((size_t)Wo * Ho));
+    const int k0 = ch << 3;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    __nv_bfloat16* ov = reinterpret_cast<__nv_bfloat16*>(&o);
+    bool done = false;
+    if (sizeof(InT) == 2 && (C & 7) == 0 && k0 < Kreal) {  // eight channels of one tap: a single 16-byte load
+      const int tap = k0 / C, c = k0 - tap * C, ky = tap / KS, kx = tap - ky * KS;
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        o = *reinterpret_cast<const uint4*>(in + (((size_t)e * H + iy) * W + ix) * C + c);
+      done = true;
+    }
+    if (!done) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int k = k0 + q;
+        float val = 0.0f;
+        if (k < Kreal) {
+          const int tap = k / C, c = k - tap * C, ky = tap / KS, kx = tap - ky * KS;
+          const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = (float)in[(((size_t)e * H + iy) * W + ix) * C + c];
+        }
+        ov[q] = __float2bfloat16_rn(val);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + m * Kpad + k0) = o;
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -251,13 +310,14 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int K, int box
 static thread_local char g_linear_err[256] = "";
 extern "C" const char* pcgrl_linear_last_error(void) { return g_linear_err; }
 
-// Y[M,N] (fp32, row-major) = act(X[M,K] . W[N,K]^T + bias[N]); X, W bf16 row-major device pointers (16-byte aligned,
-// K % 8 == 0); bias may be NULL; relu != 0 applies max(., 0).  Enqueues on `stream`; 0 = OK.
-extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, float* y, int M, int N, int K, int relu,
-                                 void* stream) {
+// Y[M,N] (row-major, fp32 or bf16) = act(X[M,K] . W[N,K]^T + bias[N]); X, W bf16 row-major device pointers (16-byte aligned,
+// K % 8 == 0; N % 4 == 0 for fp32 output, N % 8 == 0 for bf16 output); bias may be NULL; relu != 0 applies max(., 0).
+// Enqueues on `stream`; 0 = OK.
+extern "C" int pcgrl_linear_bf16_ex(const void* x_bf16, const void* w_bf16, const float* bias, void* y, int M, int N, int K, int relu,
+                                    int out_bf16, void* stream) {
   using namespace pcgrl_linear;
   if (!x_bf16 || !w_bf16 || !y) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
-  if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & 3)) { snprintf(g_linear_err, sizeof(g_linear_err), "need M, N, K > 0, K %% 8 == 0, N %% 4 == 0"); return -1; }
+  if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & (out_bf16 ? 7 : 3))) { snprintf(g_linear_err, sizeof(g_linear_err), "need M, N, K > 0, K %% 8 == 0, N %% 4 == 0 (fp32 out) or N %% 8 == 0 (bf16 out)"); return -1; }
   if (((uintptr_t)x_bf16 | (uintptr_t)w_bf16 | (uintptr_t)y) & 15) { snprintf(g_linear_err, sizeof(g_linear_err), "pointers must be 16-byte aligned"); return -1; }
   static thread_local int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count < 1) sm_count = 148; }
@@ -274,8 +334,35 @@ extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const f
     configured = true;
   }
   const int tiles = tiles_m * ((N + bn - 1) / bn), grid = tiles < sm_count ? tiles : sm_count;
-  if (wide) k_linear_bf16<256><<<grid, THREADS, smem_bytes<256>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
-  else k_linear_bf16<128><<<grid, THREADS, smem_bytes<128>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu);
+  if (wide) k_linear_bf16<256><<<grid, THREADS, smem_bytes<256>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu, out_bf16);
+  else k_linear_bf16<128><<<grid, THREADS, smem_bytes<128>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu, out_bf16);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+  return 0;
+}
+
+extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, float* y, int M, int N, int K, int relu,
+                                 void* stream) {
+  return pcgrl_linear_bf16_ex(x_bf16, w_bf16, bias, y, M, N, K, relu, 0, stream);
+}
+
+// im2col of NHWC activations for a KS x KS convolution (stride, zero padding `pad`): in [n][H][W][C] uint8 (in_bf16 == 0) or
+// bf16 -> out [n * Ho * Wo][Kpad] bf16 with k = (ky * KS + kx) * C + c, zero-filled up to Kpad (Kpad % 8 == 0, >= KS*KS*C).
+// conv + bias + ReLU = pcgrl_im2col followed by pcgrl_linear_bf16_ex on weights laid out [Cout][Kpad].
+extern "C" int pcgrl_im2col(const void* in, int in_bf16, void* out_bf16, int n, int H, int W, int C, int ksize, int stride, int pad,
+                            int Kpad, void* stream) {
+  using namespace pcgrl_linear;
+  if (!in || !out_bf16) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
+  if (n <= 0 || H <= 0 || W <= 0 || C <= 0 || ksize <= 0 || stride <= 0 || pad < 0 || (Kpad & 7) || Kpad < ksize * ksize * C) {
+    snprintf(g_linear_err, sizeof(g_linear_err), "bad im2col arguments (Kpad %% 8 == 0, Kpad >= ksize^2 * C)");
+    return -1;
+  }
+  const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) { snprintf(g_linear_err, sizeof(g_linear_err), "convolution output is empty"); return -1; }
+  const size_t total = (size_t)n * Ho * Wo * (Kpad >> 3);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 32u ? (total + 255) / 256 : 148u * 32u);
+  if (in_bf16) k_im2col<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out_bf16, n, H, W, C, ksize, stride, pad, Ho, Wo, Kpad);
+  else k_im2col<uint8_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in, (__nv_bfloat16*)out_bf16, n, H, W, C, ksize, stride, pad, Ho, Wo, Kpad);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
   return 0;

@@ -297,6 +297,18 @@ int pcgrl_get_stats_cpu(const pcgrl_config* cfg, const uint8_t* maps, int32_t* s
  */
 int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const float* bias, float* y, int M, int N, int K,
                       int relu, void* stream);
+/* same, with the output type selectable: out_bf16 != 0 writes bf16 (N % 8 == 0) -- the activations of the next layer */
+int pcgrl_linear_bf16_ex(const void* x_bf16, const void* w_bf16, const float* bias, void* y, int M, int N, int K,
+                         int relu, int out_bf16, void* stream);
+/*
+ * im2col of NHWC activations for a ksize x ksize convolution (`conv(...)` of stable-baselines' a2c.utils as used by
+ * model.py:9-77; pad = 0 VALID, pad = ksize / 2 SAME): in [n][H][W][C] uint8 (in_bf16 == 0: the wrapper's observation) or
+ * bf16 -> out [n * Ho * Wo][Kpad] bf16, k = (ky * ksize + kx) * C + c, zero-filled up to Kpad (Kpad % 8 == 0).
+ * conv + bias + ReLU = pcgrl_im2col, then pcgrl_linear_bf16_ex on weights laid out [Cout][Kpad]; its [n * Ho * Wo][Cout]
+ * output IS the NHWC activation tensor of the next layer.
+ */
+int pcgrl_im2col(const void* in, int in_bf16, void* out_bf16, int n, int H, int W, int C, int ksize, int stride,
+                 int pad, int Kpad, void* stream);
 const char* pcgrl_linear_last_error(void);
 
 #ifdef __cplusplus

@@ -40,3 +40,32 @@ def test_tcgen05_linear_inside_the_policy():
         net.use_tcgen05_fc = True
         got = net(obs)
     assert float((got - want).abs().max()) <= 2e-2 * (1 + float(want.abs().max()))
+
+
+@pytest.mark.parametrize("kind,obs_shape,n_actions,n", [
+    ("CustomPolicyBigMap", (28, 28, 1), 3, 700), ("CustomPolicySmallMap", (10, 10, 5), 9, 130),
+    ("CustomPolicyBigMap", (22, 22, 8), 12, 257), ("FullyConvPolicyBigMap", (14, 14, 1), 14 * 14 * 2, 96),
+    ("FullyConvPolicySmallMap", (5, 5, 5), 125, 64)])
+def test_native_policy_forward_matches_torch(kind, obs_shape, n_actions, n):
+    """policy_native.NativePolicy (im2col + tcgen05 GEMM for every layer, bf16 activations, fp32 accumulation) against the
+    torch fp32 modules of models.py.  Tolerance: bf16 rounding of weights and of 4-9 activation tensors; stated as
+    |err| <= 0.03 * max|ref| + 0.02 per output tensor."""
+    import torch
+    from gym_pcgrl_b200.models import ActorCritic
+    from gym_pcgrl_b200.policy_native import NativePolicy
+    torch.manual_seed(n)
+    net = ActorCritic(kind, obs_shape, n_actions).cuda()
+    with torch.no_grad():
+        for p in net.parameters():          # non-trivial biases and heads
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    hi = 2 if obs_shape[2] > 1 else 2
+    obs = torch.randint(0, hi, (n,) + obs_shape, dtype=torch.uint8, device="cuda")
+    with torch.no_grad():
+        want_logits, want_value = net(obs)
+    got_logits, got_value = NativePolicy(net)(obs)
+    torch.cuda.synchronize()
+    assert tuple(got_logits.shape) == tuple(want_logits.shape) and tuple(got_value.shape) == tuple(want_value.shape)
+    for got, want in ((got_logits, want_logits), (got_value, want_value)):
+        tol = 0.03 * float(want.abs().max()) + 0.02
+        assert float((got.float() - want).abs().max()) <= tol, (kind, float((got.float() - want).abs().max()), tol)

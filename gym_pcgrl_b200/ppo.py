@@ -25,7 +25,7 @@ def make_training_env(game, representation, num_envs, device="cuda", seed=0, **k
 
 class PPO:
     def __init__(self, env, policy=None, n_steps=128, gamma=0.99, lam=0.95, ent_coef=0.01, vf_coef=0.5, learning_rate=2.5e-4,
-                 max_grad_norm=0.5, nminibatches=4, noptepochs=4, cliprange=0.2, seed=0):
+                 max_grad_norm=0.5, nminibatches=4, noptepochs=4, cliprange=0.2, seed=0, native_policy=False):
         self.env = env
         base = env.pcgrl_env
         self.device = torch.device(base.device if str(base.device) != "cuda" else "cuda:%d" % torch.cuda.current_device())
@@ -35,6 +35,12 @@ class PPO:
         torch.manual_seed(seed)
         self.policy = ActorCritic(kind, env.shape, n_actions).to(self.device)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        # rollout-time inference through this repo's own kernels (policy_native.py: im2col + tcgen05 GEMM); the updates
+        # keep the autograd modules, the bf16 weight snapshot is refreshed after every update
+        self.native = None
+        if native_policy:
+            from .policy_native import NativePolicy
+            self.native = NativePolicy(self.policy)
         self.gamma, self.lam, self.ent_coef, self.vf_coef = gamma, lam, ent_coef, vf_coef
         self.max_grad_norm, self.nminibatches, self.noptepochs, self.cliprange = max_grad_norm, nminibatches, noptepochs, cliprange
         T, N = n_steps, self.n_envs
@@ -53,8 +59,9 @@ class PPO:
     def collect(self):
         if self.obs is None:
             self.obs = self.env.reset()
+        infer = self.native if self.native is not None else self.policy
         for t in range(self.n_steps):
-            logits, value = self.policy(self.obs)
+            logits, value = infer(self.obs)
             dist = torch.distributions.Categorical(logits=logits)
             action = dist.sample()
             self.obs_buf[t].copy_(self.obs)
@@ -65,7 +72,7 @@ class PPO:
             if bool(done.any()):                              # one small D2H per step with finished episodes (logging only)
                 self.finished_returns.append(self.ep_ret[done].clone())
                 self.ep_ret[done] = 0
-        _, last_value = self.policy(self.obs)
+        _, last_value = infer(self.obs)
         adv = torch.empty_like(self.rew_buf)
         lastgae = torch.zeros(self.n_envs, device=self.device)
         for t in reversed(range(self.n_steps)):               # GAE(lambda); done[t] ends the episode AFTER step t
@@ -103,6 +110,8 @@ class PPO:
                 nn_utils_clip(self.policy.parameters(), self.max_grad_norm)
                 self.opt.step()
                 stats += torch.stack([pg_loss.detach(), vf_loss.detach(), entropy.detach(), loss.detach()])
+        if self.native is not None:
+            self.native.refresh()
         return (stats / (self.noptepochs * self.nminibatches)).tolist()
 
     def learn(self, total_timesteps, log_every=1, log=print):

@@ -16,9 +16,10 @@ def main():
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--timesteps", type=float, default=2e6)
     ap.add_argument("--n-steps", type=int, default=128)
+    ap.add_argument("--native-policy", action="store_true", help="rollout inference through im2col + the tcgen05 GEMM kernel")
     a = ap.parse_args()
     env = make_training_env(a.game, a.rep, a.envs)
-    PPO(env, n_steps=a.n_steps).learn(int(a.timesteps))
+    PPO(env, n_steps=a.n_steps, native_policy=a.native_policy).learn(int(a.timesteps))
 
 
 if __name__ == "__main__":

@@ -19,8 +19,9 @@ LIB = os.path.join(ROOT, "gym_pcgrl_b200", "csrc", "libpcgrl_b200.so")
 def sass_lines(kernel_substr):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=True, text=True).stdout
+    txt = ""   # one cubin per translation unit: scan them all
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        txt += subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=True, text=True).stdout + "\n"
     funcs, cur, line = {}, None, None
     for ln in txt.split("\n"):
         m = re.match(r"\s*\.section\s+\.text\.(\S+),", ln)

@@ -382,7 +382,8 @@ __device__ __forceinline__ int ld_volatile(const int32_t* p) { return *reinterpr
 
 struct ArenaRefs {
   ArenaHead* A;
-  uint32_t *table, *cache, *heap, *nodes;
+  uint32_t *table, *cache, *nodes;
+  HeapRef heap;
   int table_size;
 };
 
@@ -564,12 +565,13 @@ __device__ __noinline__ void async_help(const pcgrl_config& cfg, const pcgrl_buf
 }
 
 template <int PROB>
-__global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __grid_constant__ pcgrl_config cfg,
+__global__ void __launch_bounds__(32 * ASYNC_WPB, 4) k_rollout_async(const __grid_constant__ pcgrl_config cfg,
                                                                      const __grid_constant__ pcgrl_buffers b,
                                                                      const int32_t* __restrict__ actions, double* reward_out,
                                                                      uint8_t* done_out, int T, int n, AsyncHeader* hdr,
                                                                      AsyncGroup* groups, uint32_t* node_pool,
-                                                                     size_t nodes_per_pass, int table_size, Staging sg) {
+                                                                     size_t nodes_per_pass, int table_size, Staging sg,
+                                                                     uint32_t* heap_pool, size_t heap_words, int heap_fast) {
   constexpr int NP = ProblemTraits<PROB>::NPLANES, NS = ProblemTraits<PROB>::NSTATS;
   extern __shared__ __align__(16) uint32_t dyn[];
   __shared__ ArenaHead A;
@@ -579,11 +581,12 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 2) k_rollout_async(const __gri
   R.A = &A;
   R.table = dyn;
   R.cache = dyn + table_size;
-  R.heap = R.cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;
+  R.heap.fast = R.cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;  // the first heap_fast open-list entries (top levels)
+  R.heap.cap = heap_fast;
+  R.heap.slow_biased = heap_pool + (size_t)blockIdx.x * heap_words - heap_fast;  // the tail: this CTA's slice of HBM scratch
   R.nodes = node_pool + (size_t)blockIdx.x * nodes_per_pass * SOLVER_NODE_WORDS;
   R.table_size = table_size;
-  const size_t heap_words = (size_t)3 * cfg.solver_power + 8;
-  WarpSmem* reset_areas = reinterpret_cast<WarpSmem*>(R.heap + ((heap_words + 3) & ~(size_t)3));
+  WarpSmem* reset_areas = reinterpret_cast<WarpSmem*>(R.heap.fast + (((size_t)heap_fast + 3) & ~(size_t)3));
   const int my_area = wib % ASYNC_RESET_AREAS;
   WarpSmem& reset_sm = reset_areas[my_area];
   AsyncGroup* G = groups + blockIdx.x * ASYNC_WPB + wib;
@@ -958,8 +961,8 @@ template <int PROB>
 static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const int32_t* actions, double* reward_out,
                          uint8_t* done_out, int T, int n, cudaStream_t s, Staging sg) {
   if constexpr (GameOf<PROB>::GAME >= 0) {
-    int table_size;
-    const size_t smem = ((solver_arena_words(cfg, &table_size) + 3) & ~(size_t)3) * sizeof(uint32_t) + ASYNC_RESET_AREAS * sizeof(WarpSmem);
+    int table_size, heap_fast;
+    const size_t smem = ((solver_async_arena_words(cfg, &table_size, &heap_fast) + 3) & ~(size_t)3) * sizeof(uint32_t) + ASYNC_RESET_AREAS * sizeof(WarpSmem);
     // launch geometry is a function of (device, problem, smem): queried once, not on every per-step call
     struct Geometry { size_t smem; int sm_count, per_sm; };
     static thread_local Geometry geo[SOLVER_MAX_DEVICES][PCGRL_NUM_PROBLEMS] = {};
@@ -986,8 +989,9 @@ static int rollout_async(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
     AsyncGroup* groups = (AsyncGroup*)(region + 256);
     cudaMemsetAsync(region, 0, 256 + sizeof(AsyncGroup) * (size_t)grid * ASYNC_WPB, s);
     uint32_t* pool = (uint32_t*)((char*)b->scratch + lay.nodes_off);
+    uint32_t* heap_pool = (uint32_t*)((char*)b->scratch + lay.heap_off);
     k_rollout_async<PROB><<<grid, 32 * ASYNC_WPB, smem, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, hdr, groups, pool,
-                                                             lay.nodes_per_pass, table_size, sg);
+                                                             lay.nodes_per_pass, table_size, sg, heap_pool, lay.heap_words, heap_fast);
     return cuda_rc(cudaGetLastError(), "pcgrl_rollout (async) launch");
   } else {
     return fail(-1, "not a solver problem");

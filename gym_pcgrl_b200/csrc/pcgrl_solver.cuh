@@ -44,15 +44,18 @@ struct SolverQueue {
 };
 
 struct SolverLayout {
-  size_t queue_bytes, old_stats_off, heat_off, nodes_off, async_off, total;
+  size_t queue_bytes, old_stats_off, heat_off, nodes_off, async_off, heap_off, total;
   int slots;
-  size_t nodes_per_pass;
+  size_t nodes_per_pass, heap_words;
 };
 
 // k_rollout_async bookkeeping (see pcgrl_b200.cu): one header + one 128-byte request slot per env warp
-#define ASYNC_MAX_CTAS 512
+#define ASYNC_MAX_CTAS 1024
 #ifndef ASYNC_WPB
-#define ASYNC_WPB 4 /* env warps per CTA (= per search arena) */
+#define ASYNC_WPB 2 /* env warps per CTA (= per search arena): 174 registers x 64 threads lets four CTAs share an SM */
+#endif
+#ifndef ASYNC_HEAP_FAST
+#define ASYNC_HEAP_FAST 2048 /* open-list entries kept in shared memory (the top 11 levels); the tail lives in HBM scratch */
 #endif
 struct AsyncHeader { int32_t work, envs_done, posted, pad; };
 struct __align__(16) AsyncGroup {
@@ -81,7 +84,9 @@ static inline SolverLayout solver_layout(const pcgrl_config* c, int n, int max_s
   L.slots = n < max_slots ? n : max_slots;
   L.nodes_per_pass = (size_t)4 * (size_t)c->solver_power + 8;
   L.async_off = align_up(L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t), 256);
-  L.total = L.async_off + async_region_bytes();
+  L.heap_words = (size_t)3 * (size_t)c->solver_power + 8;  // open-list tail of one k_rollout_async arena (one per CTA, <= 4 * slots CTAs)
+  L.heap_off = align_up(L.async_off + async_region_bytes(), 256);
+  L.total = L.heap_off + (size_t)L.slots * 4 * L.heap_words * sizeof(uint32_t);
   return L;
 }
 
@@ -479,33 +484,41 @@ __device__ __forceinline__ uint32_t key_hash(const SState& s) {
 // CPython heapq on packed entries (priority << 15 | node); comparisons use the priority only, strict <
 // (Lib/heapq.py _siftdown / _siftup; engine.py Node.__lt__ with 2*h + b*depth, b = 2*balance).
 #define HP(e) ((e) >> 15)
-__device__ __forceinline__ void heap_siftdown(uint32_t* heap, int startpos, int pos) {
-  const uint32_t item = heap[pos];
+// The open list: entries below `cap` live in shared memory, the tail in a per-arena slice of HBM scratch (k_rollout_async
+// keeps only the top levels on chip so that four arenas fit one SM; k_solve keeps everything in shared memory: cap = INT_MAX).
+struct HeapRef {
+  uint32_t* fast;
+  uint32_t* slow_biased;  // slow - cap: entry i >= cap lives at slow_biased[i]
+  int cap;
+};
+__device__ __forceinline__ uint32_t* hslot(const HeapRef& h, int i) { return (i < h.cap ? h.fast : h.slow_biased) + i; }
+__device__ __forceinline__ void heap_siftdown(const HeapRef& heap, int startpos, int pos) {
+  const uint32_t item = *hslot(heap, pos);
   while (pos > startpos) {
     const int parentpos = (pos - 1) >> 1;
-    const uint32_t parent = heap[parentpos];
-    if (HP(item) < HP(parent)) { heap[pos] = parent; pos = parentpos; continue; }
+    const uint32_t parent = *hslot(heap, parentpos);
+    if (HP(item) < HP(parent)) { *hslot(heap, pos) = parent; pos = parentpos; continue; }
     break;
   }
-  heap[pos] = item;
+  *hslot(heap, pos) = item;
 }
-__device__ __forceinline__ uint32_t heap_pop(uint32_t* heap, int& n) {
-  const uint32_t last = heap[--n];
+__device__ __forceinline__ uint32_t heap_pop(const HeapRef& heap, int& n) {
+  const uint32_t last = *hslot(heap, --n);
   if (n == 0) return last;
-  const uint32_t ret = heap[0];
+  const uint32_t ret = heap.fast[0];
   int pos = 0, childpos = 1;
   while (childpos < n) {
     const int rightpos = childpos + 1;
-    uint32_t child = heap[childpos];
+    uint32_t child = *hslot(heap, childpos);
     if (rightpos < n) {
-      const uint32_t right = heap[rightpos];
+      const uint32_t right = *hslot(heap, rightpos);
       if (!(HP(child) < HP(right))) { childpos = rightpos; child = right; }
     }
-    heap[pos] = child;
+    *hslot(heap, pos) = child;
     pos = childpos;
     childpos = 2 * pos + 1;
   }
-  heap[pos] = last;
+  *hslot(heap, pos) = last;
   heap_siftdown(heap, 0, pos);
   return ret;
 }
@@ -546,7 +559,7 @@ __device__ __forceinline__ void node_put(uint32_t* nodes, uint32_t* cache, int i
 // Returns (lane 0): res[0] won, res[1] depth, res[2] h, res[3] misc counters of solState; res[0] = -1 if cancelled.
 template <int GAME>
 __device__ void search_pass(const Level& L, const SState& root0, int b, int power, uint32_t* nodes, uint32_t* cache,
-                            uint32_t* heap, uint32_t* table, int table_mask, const volatile int32_t* best_win,
+                            const HeapRef heap, uint32_t* table, int table_mask, const volatile int32_t* best_win,
                             int pass_index, int* res, int* exhausted, int lane) {
   const bool check_lose = (GAME != GAME_SOKOBAN);
   const bool sk_small = (GAME == GAME_SOKOBAN) && L.small;
@@ -561,7 +574,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     }
     root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
     node_put(nodes, cache, 0, root);
-    if (b >= 0) { heap[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
+    if (b >= 0) { heap.fast[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
     res[0] = 0;
     *exhausted = 0;
   }
@@ -688,7 +701,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
       const int pd = __shfl_sync(FULL_MASK, prio, d);
       if ((vmask >> d) & 1u) {
         if (lane == 0 && b >= 0) {
-          heap[nheap] = ((uint32_t)pd << 15) | (uint32_t)idx;
+          *hslot(heap, nheap) = ((uint32_t)pd << 15) | (uint32_t)idx;
           nheap++;
           heap_siftdown(heap, 0, nheap - 1);
         }
@@ -931,7 +944,10 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
   const int count = *q.count;
   uint32_t* table = dyn;
   uint32_t* cache = dyn + table_size;
-  uint32_t* heap = cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;
+  HeapRef heap;  // the whole open list in shared memory
+  heap.fast = cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;
+  heap.slow_biased = heap.fast;
+  heap.cap = 0x7fffffff;
   __shared__ SState root_s;
   uint32_t* nodes = node_pool + ((size_t)slot * 4 + pass) * nodes_per_pass * SOLVER_NODE_WORDS;
   const int W = cfg.width, H = cfg.height, cells = W * H;
@@ -1015,6 +1031,17 @@ static inline size_t solver_arena_words(const pcgrl_config* cfg, int* table_size
   while (table_size < cfg->solver_power + cfg->solver_power / 2) table_size <<= 1;
   const size_t heap_words = (size_t)3 * cfg->solver_power + 8;
   if (table_size_out) *table_size_out = table_size;
+  return (size_t)table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words;
+}
+
+// k_rollout_async keeps only the first ASYNC_HEAP_FAST open-list entries in shared memory
+static inline size_t solver_async_arena_words(const pcgrl_config* cfg, int* table_size_out, int* heap_fast_out) {
+  int table_size;
+  solver_arena_words(cfg, &table_size);
+  size_t heap_words = (size_t)3 * cfg->solver_power + 8;
+  if (heap_words > ASYNC_HEAP_FAST) heap_words = ASYNC_HEAP_FAST;
+  if (table_size_out) *table_size_out = table_size;
+  if (heap_fast_out) *heap_fast_out = (int)heap_words;
   return (size_t)table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words;
 }
 

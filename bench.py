@@ -564,7 +564,17 @@ class Bench:
                     del io
                     io = None
                     async_ms = self.time_e2e_async(wl, n, 48, 16, 1999 + self.rank)
-                red = self.max_over_ranks([float(np.median(per_region)), step_ms, float(np.median(e2e_ms)), async_ms or 0.0])
+                big_ms, big_n = None, 131072
+                if wl["prob"] in ("sokoban", "ddave", "mdungeon"):
+                    # the same per-step call on a batch large enough to amortise the longest search of the step
+                    del env
+                    env = make_env(big_n, self.dev, env_offset=self.rank * big_n, workload=wl)
+                    env.reset()
+                    self.preroll(env, 256, 78 + self.rank)
+                    b_ms, io, _ = self.time_e2e(env, 24, 1, "delta", 98 + self.rank)
+                    env.check_status()
+                    big_ms = float(np.median(b_ms))
+                red = self.max_over_ranks([float(np.median(per_region)), step_ms, float(np.median(e2e_ms)), async_ms or 0.0, big_ms or 0.0])
                 tot = n * self.world
                 W, H = env._prob._width, env._prob._height
                 out[name] = {"envs_per_gpu": n, "map": "%dx%d" % (W, H),
@@ -575,6 +585,8 @@ class Bench:
                 if async_ms:
                     out[name]["e2e_async_groups"] = tot * 48 / (red[3] * 1e-3)
                     out[name]["e2e_async_api"] = "AsyncGroupedEnv: 16 env groups, one pcgrl_step_host_begin/_end step in flight each"
+                if big_ms:
+                    out[name]["e2e_large_batch"] = {"envs_per_gpu": big_n, "value": big_n * self.world * 24 / (red[4] * 1e-3)}
                 del env, io
             except Exception as ex:
                 out[name] = {"error": repr(ex)[:300]}

@@ -565,7 +565,7 @@ __device__ __noinline__ void async_help(const pcgrl_config& cfg, const pcgrl_buf
 }
 
 template <int PROB>
-__global__ void __launch_bounds__(32 * ASYNC_WPB, 4) k_rollout_async(const __grid_constant__ pcgrl_config cfg,
+__global__ void __launch_bounds__(32 * ASYNC_WPB, ASYNC_MIN_CTAS) k_rollout_async(const __grid_constant__ pcgrl_config cfg,
                                                                      const __grid_constant__ pcgrl_buffers b,
                                                                      const int32_t* __restrict__ actions, double* reward_out,
                                                                      uint8_t* done_out, int T, int n, AsyncHeader* hdr,
@@ -581,12 +581,11 @@ __global__ void __launch_bounds__(32 * ASYNC_WPB, 4) k_rollout_async(const __gri
   R.A = &A;
   R.table = dyn;
   R.cache = dyn + table_size;
-  R.heap.fast = R.cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;  // the first heap_fast open-list entries (top levels)
-  R.heap.cap = heap_fast;
-  R.heap.slow_biased = heap_pool + (size_t)blockIdx.x * heap_words - heap_fast;  // the tail: this CTA's slice of HBM scratch
+  uint32_t* heap_fast_p = R.cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;  // the first heap_fast open-list entries (top levels)
+  R.heap = heap_ref(heap_fast_p, heap_pool + (size_t)blockIdx.x * heap_words, heap_fast);  // tail: this CTA's slice of HBM scratch
   R.nodes = node_pool + (size_t)blockIdx.x * nodes_per_pass * SOLVER_NODE_WORDS;
   R.table_size = table_size;
-  WarpSmem* reset_areas = reinterpret_cast<WarpSmem*>(R.heap.fast + (((size_t)heap_fast + 3) & ~(size_t)3));
+  WarpSmem* reset_areas = reinterpret_cast<WarpSmem*>(heap_fast_p + (((size_t)heap_fast + 3) & ~(size_t)3));
   const int my_area = wib % ASYNC_RESET_AREAS;
   WarpSmem& reset_sm = reset_areas[my_area];
   AsyncGroup* G = groups + blockIdx.x * ASYNC_WPB + wib;

@@ -57,6 +57,9 @@ struct SolverLayout {
 #ifndef ASYNC_HEAP_FAST
 #define ASYNC_HEAP_FAST 2048 /* open-list entries kept in shared memory (the top 11 levels); the tail lives in HBM scratch */
 #endif
+#ifndef ASYNC_MIN_CTAS
+#define ASYNC_MIN_CTAS 4 /* arenas per SM the register allocation must allow */
+#endif
 struct AsyncHeader { int32_t work, envs_done, posted, pad; };
 struct __align__(16) AsyncGroup {
   int32_t env;         // env whose map (in HBM) is being solved
@@ -84,7 +87,7 @@ static inline SolverLayout solver_layout(const pcgrl_config* c, int n, int max_s
   L.slots = n < max_slots ? n : max_slots;
   L.nodes_per_pass = (size_t)4 * (size_t)c->solver_power + 8;
   L.async_off = align_up(L.nodes_off + (size_t)L.slots * 4 * L.nodes_per_pass * SOLVER_NODE_WORDS * sizeof(uint32_t), 256);
-  L.heap_words = (size_t)3 * (size_t)c->solver_power + 8;  // open-list tail of one k_rollout_async arena (one per CTA, <= 4 * slots CTAs)
+  L.heap_words = ((size_t)3 * (size_t)c->solver_power + 9) & ~(size_t)1;  // (even) open-list tail of one k_rollout_async arena (one per CTA, <= 4 * slots CTAs)
   L.heap_off = align_up(L.async_off + async_region_bytes(), 256);
   L.total = L.heap_off + (size_t)L.slots * 4 * L.heap_words * sizeof(uint32_t);
   return L;
@@ -484,42 +487,68 @@ __device__ __forceinline__ uint32_t key_hash(const SState& s) {
 // CPython heapq on packed entries (priority << 15 | node); comparisons use the priority only, strict <
 // (Lib/heapq.py _siftdown / _siftup; engine.py Node.__lt__ with 2*h + b*depth, b = 2*balance).
 #define HP(e) ((e) >> 15)
-// The open list: entries below `cap` live in shared memory, the tail in a per-arena slice of HBM scratch (k_rollout_async
-// keeps only the top levels on chip so that four arenas fit one SM; k_solve keeps everything in shared memory: cap = INT_MAX).
+// The open list, 1-based (entry i in 1..n; the children of i are the aligned 8-byte pair 2i, 2i+1).  Entries below `cap`
+// live in shared memory (addressed as .shared: `fast_s`), the tail in a per-arena slice of HBM scratch; cap is even so a
+// child pair never straddles the two.  k_solve keeps everything in shared memory (cap = INT_MAX).
 struct HeapRef {
-  uint32_t* fast;
+  uint32_t fast_s;        // shared-space byte address of entry 0
   uint32_t* slow_biased;  // slow - cap: entry i >= cap lives at slow_biased[i]
   int cap;
 };
-__device__ __forceinline__ uint32_t* hslot(const HeapRef& h, int i) { return (i < h.cap ? h.fast : h.slow_biased) + i; }
-__device__ __forceinline__ void heap_siftdown(const HeapRef& heap, int startpos, int pos) {
-  const uint32_t item = *hslot(heap, pos);
-  while (pos > startpos) {
-    const int parentpos = (pos - 1) >> 1;
-    const uint32_t parent = *hslot(heap, parentpos);
-    if (HP(item) < HP(parent)) { *hslot(heap, pos) = parent; pos = parentpos; continue; }
+__device__ __forceinline__ HeapRef heap_ref(uint32_t* fast, uint32_t* slow, int cap) {
+  HeapRef h;
+  h.fast_s = (uint32_t)__cvta_generic_to_shared(fast);
+  h.slow_biased = slow ? slow - cap : nullptr;
+  h.cap = cap;
+  return h;
+}
+__device__ __forceinline__ uint32_t hget(const HeapRef& h, int i) {
+  if (i < h.cap) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(h.fast_s + 4u * (uint32_t)i) : "memory");
+    return v;
+  }
+  return h.slow_biased[i];
+}
+__device__ __forceinline__ uint2 hget_pair(const HeapRef& h, int i) {  // i even
+  if (i < h.cap) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(h.fast_s + 4u * (uint32_t)i) : "memory");
+    return v;
+  }
+  return *reinterpret_cast<const uint2*>(h.slow_biased + i);
+}
+__device__ __forceinline__ void hset(const HeapRef& h, int i, uint32_t v) {
+  if (i < h.cap) asm volatile("st.shared.u32 [%0], %1;" :: "r"(h.fast_s + 4u * (uint32_t)i), "r"(v) : "memory");
+  else h.slow_biased[i] = v;
+}
+// heapq._siftdown(heap, 0, pos) for `item` placed in the hole at `pos`
+__device__ __forceinline__ void heap_siftdown(const HeapRef& heap, int pos, uint32_t item) {
+  while (pos > 1) {
+    const int parentpos = pos >> 1;
+    const uint32_t parent = hget(heap, parentpos);
+    if (HP(item) < HP(parent)) { hset(heap, pos, parent); pos = parentpos; continue; }
     break;
   }
-  *hslot(heap, pos) = item;
+  hset(heap, pos, item);
 }
+__device__ __forceinline__ void heap_push(const HeapRef& heap, int& n, uint32_t item) { heap_siftdown(heap, ++n, item); }
+// heapq.heappop: the last entry refills the root through _siftup (smaller child up to a leaf, then _siftdown)
 __device__ __forceinline__ uint32_t heap_pop(const HeapRef& heap, int& n) {
-  const uint32_t last = *hslot(heap, --n);
+  const uint32_t last = hget(heap, n);
+  n--;
   if (n == 0) return last;
-  const uint32_t ret = heap.fast[0];
-  int pos = 0, childpos = 1;
-  while (childpos < n) {
-    const int rightpos = childpos + 1;
-    uint32_t child = *hslot(heap, childpos);
-    if (rightpos < n) {
-      const uint32_t right = *hslot(heap, rightpos);
-      if (!(HP(child) < HP(right))) { childpos = rightpos; child = right; }
-    }
-    *hslot(heap, pos) = child;
+  const uint32_t ret = hget(heap, 1);
+  int pos = 1, childpos = 2;
+  while (childpos <= n) {
+    const uint2 pr = hget_pair(heap, childpos);  // (left, right); right is ignored when it is past the end
+    uint32_t child = pr.x;
+    if (childpos < n && !(HP(pr.x) < HP(pr.y))) { childpos++; child = pr.y; }
+    hset(heap, pos, child);
     pos = childpos;
-    childpos = 2 * pos + 1;
+    childpos = 2 * pos;
   }
-  *hslot(heap, pos) = last;
-  heap_siftdown(heap, 0, pos);
+  heap_siftdown(heap, pos, last);
   return ret;
 }
 
@@ -574,7 +603,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     }
     root.dh = 0u | ((uint32_t)(g_heuristic<GAME>(L, root) + SOLVER_PRIO_BIAS) << 16);
     node_put(nodes, cache, 0, root);
-    if (b >= 0) { heap.fast[0] = ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u; nheap = 1; }
+    if (b >= 0) heap_push(heap, nheap, ((uint32_t)(2 * st_h(root) + 2 * SOLVER_PRIO_BIAS) << 15) | 0u);
     res[0] = 0;
     *exhausted = 0;
   }
@@ -700,11 +729,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     for (int d = 0; d < 4; d++) {
       const int pd = __shfl_sync(FULL_MASK, prio, d);
       if ((vmask >> d) & 1u) {
-        if (lane == 0 && b >= 0) {
-          *hslot(heap, nheap) = ((uint32_t)pd << 15) | (uint32_t)idx;
-          nheap++;
-          heap_siftdown(heap, 0, nheap - 1);
-        }
+        if (lane == 0 && b >= 0) heap_push(heap, nheap, ((uint32_t)pd << 15) | (uint32_t)idx);
         idx++;
       }
     }
@@ -944,10 +969,7 @@ __global__ void __launch_bounds__(32) k_solve(const __grid_constant__ pcgrl_conf
   const int count = *q.count;
   uint32_t* table = dyn;
   uint32_t* cache = dyn + table_size;
-  HeapRef heap;  // the whole open list in shared memory
-  heap.fast = cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS;
-  heap.slow_biased = heap.fast;
-  heap.cap = 0x7fffffff;
+  const HeapRef heap = heap_ref(cache + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS, nullptr, 0x7fffffff);  // all in shared memory
   __shared__ SState root_s;
   uint32_t* nodes = node_pool + ((size_t)slot * 4 + pass) * nodes_per_pass * SOLVER_NODE_WORDS;
   const int W = cfg.width, H = cfg.height, cells = W * H;
@@ -1038,8 +1060,8 @@ static inline size_t solver_arena_words(const pcgrl_config* cfg, int* table_size
 static inline size_t solver_async_arena_words(const pcgrl_config* cfg, int* table_size_out, int* heap_fast_out) {
   int table_size;
   solver_arena_words(cfg, &table_size);
-  size_t heap_words = (size_t)3 * cfg->solver_power + 8;
-  if (heap_words > ASYNC_HEAP_FAST) heap_words = ASYNC_HEAP_FAST;
+  size_t heap_words = ((size_t)3 * cfg->solver_power + 9) & ~(size_t)1;  // even: a child pair never straddles the regions
+  if (ASYNC_HEAP_FAST > 0 && heap_words > ASYNC_HEAP_FAST) heap_words = ASYNC_HEAP_FAST;
   if (table_size_out) *table_size_out = table_size;
   if (heap_fast_out) *heap_fast_out = (int)heap_words;
   return (size_t)table_size + SOLVER_CACHE_NODES * SOLVER_NODE_WORDS + heap_words;

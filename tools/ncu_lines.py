@@ -76,10 +76,16 @@ def main():
         per_line[line][1] += s
         total_i += n
         total_s += s
+    # NCU_LINES_FILE=<substring>: keep only source files matching (percentages become relative to the kept lines);
+    # NCU_LINES_SORT=samp: rank by stall samples instead of executed instructions
+    flt, by = os.environ.get("NCU_LINES_FILE"), (1 if os.environ.get("NCU_LINES_SORT") == "samp" else 0)
+    if flt:
+        per_line = {k: v for k, v in per_line.items() if flt in k[0]}
+        total_i, total_s = sum(v[0] for v in per_line.values()), sum(v[1] for v in per_line.values())
     print("kernel:", b["name"][:80], "| SASS:", cands[0][:60])
     print("total warp-instructions %d, stall samples %d" % (total_i, total_s))
     src_cache = {}
-    for (f, l), (n, s) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:topn]:
+    for (f, l), (n, s) in sorted(per_line.items(), key=lambda kv: -kv[1][by])[:topn]:
         if f not in src_cache:
             p = os.path.join(ROOT, "gym_pcgrl_b200", "csrc", f)
             src_cache[f] = open(p).read().split("\n") if os.path.exists(p) else []

@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     if (t + 2 < T)  // the action rows of the next steps are independent of the state: pull them towards L1 now
       asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)((row + 2u * (uint32_t)n) * (uint32_t)adim)));
     iteration++;  // pcgrl_env.py:130
+    // this step can end the episode through the change / iteration limits: start pulling what the reset will read
+    if (auto_reset && (changes + max_change_per_step(cfg.representation) >= cfg.max_changes || iteration >= cfg.max_iterations))
+      prefetch_reset_inputs(r, lane);
     int old[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];

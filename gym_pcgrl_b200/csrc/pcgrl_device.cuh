@@ -84,9 +84,10 @@ struct WarpRng {
   uint32_t cache;  // tempered st[base + lane]
   bool dirty;
 
-  __device__ __forceinline__ void init(uint32_t* s, int lane = -1) {
+  // known_pos >= 0: the caller has already loaded s[624]
+  __device__ __forceinline__ void init(uint32_t* s, int lane = -1, int known_pos = -1) {
     st = s;
-    pos = (int)s[624];
+    pos = known_pos >= 0 ? known_pos : (int)s[624];
     base = -1000;
     cache = 0;
     dirty = false;
@@ -177,7 +178,7 @@ struct WarpRng {
     uint32_t* g = st;
     uint32_t v[20];
 #pragma unroll
-    for (int k = 0; k < 20; k++) v[k] = (k * 32 + lane < 624) ? g[k * 32 + lane] : 0u;  // 20 loads in flight
+    for (int k = 0; k < 20; k++) v[k] = (k * 32 + lane < 624) ? __ldcg(g + k * 32 + lane) : 0u;  // 20 loads in flight (st is the HBM copy here)
 #pragma unroll
     for (int k = 0; k < 20; k++) if (k * 32 + lane < 624) smem_key[k * 32 + lane] = v[k];
     __syncwarp();

@@ -168,6 +168,16 @@ __device__ __forceinline__ void warp_fill_bytes(uint8_t* dst, int nbytes, uint8_
   }
 }
 
+// A reset reads the 624 key words of the representation stream (20 lines of 128 B), the problem stream's position and
+// the tile probabilities: three dependent HBM round trips when issued at the reset itself.  A step that may end the
+// episode through the change / iteration limits issues these prefetches before its own statistics are computed.
+__device__ __forceinline__ int max_change_per_step(int representation) { return representation >= PCGRL_REP_NARROWCAST ? 9 : 1; }
+__device__ __forceinline__ void prefetch_reset_inputs(const EnvRefs& r, int lane) {
+  if (lane <= 20) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.rng_rep + min(lane * 32, 623)));  // 5000 B per env: 20-21 lines
+  else if (lane == 21) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.rng_prob + 624));
+  else if (lane == 22) asm volatile("prefetch.global.L1 [%0];" ::"l"(r.tile_prob));
+}
+
 // PcgrlEnv.reset for one env, up to (and including) the map part of get_stats.  The caller finishes
 // Problem.reset (start_stats) -- after the solver for the solver problems.
 template <int PROB>
@@ -179,18 +189,22 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
   const bool generate = (cfg.flags & PCGRL_FLAG_RANDOM_START) || (b.start_valid[e] == 0);
   __syncwarp();
 #ifdef PCGRL_PROFILE
-  long long tp[8]; int ntp = 0;
+  long long tp[12]; int ntp = 0;
 #define TP() do { __syncwarp(); tp[ntp++] = clock64(); } while (0)
 #else
 #define TP() do {} while (0)
 #endif
   TP();
   uint32_t* rng_home = nullptr;
-  WarpRng pr;  // problem stream (binary_prob.py:68-72): start its two dependent loads now, consume at the end
+  WarpRng pr;  // problem stream (binary_prob.py:68-72): consumed at the end
   const bool redraw_probs = (PROB == PCGRL_PROB_BINARY) && (cfg.flags & PCGRL_FLAG_RANDOM_PROBS);
-  if (redraw_probs) pr.init(r.rng_prob, lane);
+  // its position word is loaded together with the representation stream's key (one round trip for both); the load
+  // that depends on it is issued after the key has been staged
+  const uint32_t pr_pos = redraw_probs ? r.rng_prob[624] : 0u;
   if (generate) {  // representation.py:41-43 -> helper.py:310-312 gen_random_map
     rng_home = rng.stage(sm.mt, lane);  // the reset consumes 2*H*W (+2) draws and usually crosses a twist
+    TP();
+    if (redraw_probs) pr.init(r.rng_prob, lane, (int)pr_pos);
     TP();
     // helper.py:343-352 get_int_prob, then RandomState.choice: cdf = cumsum(p); cdf /= cdf[-1]
     // One probability per lane (a single load round trip), sequential sums in the reference's order via shuffles,
@@ -216,9 +230,11 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
 #pragma unroll
     for (int t = 0; t < PCGRL_MAX_TILES; t++) thr[t] = __shfl_sync(FULL_MASK, thr_lane, t);
     const int nchunks = (cells + 31) >> 5;
+    TP();
     for (int s0 = 0; s0 < cells; s0 += 256) {  // segments of 256 cells: 512 draws staged at once, 8 cells per lane
       const int nseg = min(256, cells - s0);
       rng.fill(sm.draws, 2 * nseg, lane);  // H*W random_sample() doubles in row-major order
+      if (s0 == 0) TP();
 #pragma unroll 2
       for (int k = 0; k < 8; k++) {
         const int j = k * 32 + lane;  // cell inside the segment
@@ -239,6 +255,7 @@ __device__ __forceinline__ void env_reset(const pcgrl_config& cfg, const pcgrl_b
     if (lane == 0) b.start_valid[e] = 1;
     TP();
   } else {  // representation.py:44-45
+    if (redraw_probs) pr.init(r.rng_prob, lane, (int)pr_pos);
     for (int i = lane; i < cells; i += 32) r.map[i] = r.start_map[i];
     board = load_board<NP>(r.start_map, W, H, lane, sm.bits);
   }

@@ -66,7 +66,10 @@ def main():
     if not cands:   # namespaced kernels (pcgrl_smb::...)
         cands = [f for f in funcs if ksub in f]
     fn = funcs[cands[0]]
-    per_line = collections.defaultdict(lambda: [0, 0])
+    stall_cols = [c for c in ("stall_no_inst", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_branch_resolving", "stall_lg")
+                  if c in hdr] if os.environ.get("NCU_LINES_STALLS") else []
+    stall_idx = [hdr.index(c) for c in stall_cols]
+    per_line = collections.defaultdict(lambda: [0, 0] + [0] * len(stall_cols))
     total_i = total_s = 0
     for r in b["rows"]:
         off = int(r[0], 16) - base
@@ -74,6 +77,8 @@ def main():
         line = fn.get(off, (("?", 0), ""))[0] or ("?", 0)
         per_line[line][0] += n
         per_line[line][1] += s
+        for q, ci in enumerate(stall_idx):
+            per_line[line][2 + q] += int(r[ci] or 0)
         total_i += n
         total_s += s
     # NCU_LINES_FILE=<substring>: keep only source files matching (percentages become relative to the kept lines);
@@ -85,12 +90,16 @@ def main():
     print("kernel:", b["name"][:80], "| SASS:", cands[0][:60])
     print("total warp-instructions %d, stall samples %d" % (total_i, total_s))
     src_cache = {}
-    for (f, l), (n, s) in sorted(per_line.items(), key=lambda kv: -kv[1][by])[:topn]:
+    if stall_cols:   # NCU_LINES_STALLS=1: per-line stall reasons (sample counts) after the percentages
+        print("stall columns:", " ".join(c.replace("stall_", "") for c in stall_cols))
+    for (f, l), vals in sorted(per_line.items(), key=lambda kv: -kv[1][by])[:topn]:
+        n, s = vals[0], vals[1]
         if f not in src_cache:
             p = os.path.join(ROOT, "gym_pcgrl_b200", "csrc", f)
             src_cache[f] = open(p).read().split("\n") if os.path.exists(p) else []
         text = src_cache[f][l - 1].strip()[:90] if 0 < l <= len(src_cache[f]) else ""
-        print("%6.2f%% inst %6.2f%% samp  %-20s %s" % (100.0 * n / max(total_i, 1), 100.0 * s / max(total_s, 1), "%s:%d" % (f, l), text))
+        extra = (" [" + " ".join("%d" % v for v in vals[2:]) + "]") if stall_cols else ""
+        print("%6.2f%% inst %6.2f%% samp%s  %-20s %s" % (100.0 * n / max(total_i, 1), 100.0 * s / max(total_s, 1), extra, "%s:%d" % (f, l), text))
 
 
 if __name__ == "__main__":

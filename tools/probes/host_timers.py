@@ -6,7 +6,7 @@ import numpy as np, torch
 from gym_pcgrl_b200 import _native, build as B, HostStepIO
 so = os.path.join(ROOT, "gpurun_out", "libpcgrl_profile.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
-subprocess.check_call(["nvcc"] + B.NVCC_FLAGS + ["-DPCGRL_PROFILE", "-o", so, "pcgrl_b200.cu"], cwd=B.CSRC)
+subprocess.check_call(["nvcc"] + B.NVCC_FLAGS + ["-DPCGRL_PROFILE", "-o", so] + B.SOURCES, cwd=B.CSRC)
 _native.LIB_PATH = so
 import bench
 n, K = 4096, 1000

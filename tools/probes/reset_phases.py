@@ -6,7 +6,7 @@ import numpy as np, torch
 from gym_pcgrl_b200 import _native, build as B
 so = os.path.join(ROOT, "gpurun_out", "libpcgrl_profile.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
-subprocess.check_call(["nvcc"] + B.NVCC_FLAGS + ["-DPCGRL_PROFILE", "-o", so, "pcgrl_b200.cu"], cwd=B.CSRC)
+subprocess.check_call(["nvcc"] + B.NVCC_FLAGS + ["-DPCGRL_PROFILE", "-o", so] + B.SOURCES, cwd=B.CSRC)
 _native.LIB_PATH = so
 import bench
 n = 4096
@@ -22,11 +22,11 @@ for t in range(600):
 torch.cuda.synchronize()
 acc = env._tens["status"].cpu().numpy().view(np.int64)[4:]
 cnt = acc[0]
-names = ["stage", "gen+bits", "randint+unstage", "map_stats", "probs+heat"]
+names = ["stage key -> smem", "prob stream init", "thresholds (fp64)", "fill 512 draws (twist)", "cells -> map + bits", "randint+unstage", "map_stats", "probs+heat"]
 print("resets", cnt)
 for k, nm in enumerate(names):
-    print("%-18s %8.0f cycles" % (nm, acc[k + 1] / max(cnt, 1)))
-print("total              %8.0f cycles" % (acc[1:6].sum() / max(cnt, 1)))
+    print("%-24s %8.0f cycles" % (nm, acc[k + 1] / max(cnt, 1)))
+print("total              %8.0f cycles" % (acc[1:1 + len(names)].sum() / max(cnt, 1)))
 
 print("-- single-step launch phases per warp (cycles): prologue | apply_action | map_stats | outputs+reset+epilogue")
 full = env._tens["status"].cpu().numpy().view(np.int64)

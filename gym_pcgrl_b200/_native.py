@@ -180,7 +180,7 @@ def get_stats_cpu(prob, maps):
 
 def get_stats(prob, maps):
     """Stand-alone batched Problem.get_stats (pcgrl_get_stats): uint8 CUDA [N,H,W] -> int32 [N, MAX_STATS].
-    A CPU tensor goes to the host twin (problems that have one)."""
+    A CPU tensor goes to the host twin."""
     import torch
     from ._config import build_config
     from .envs.reps import REPRESENTATIONS

@@ -1338,16 +1338,15 @@ extern "C" int pcgrl_smb_get_stats(const uint8_t* maps, int32_t* stats_out, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// host twins: the same entry points on HOST pointers, no GPU involved.  Implemented for the problems
-// whose step logic is scalar `__host__ __device__` code (smb); the bitboard problems return -2.
+// host twins: the same entry points on HOST pointers, no GPU involved, for every built-in problem: the
+// step logic is scalar `__host__ __device__` code shared with the kernels (smb, the solver problems' game models) or the
+// bitboard algorithm restated over row arrays (binary, zelda); only the search / BFS loops are host-specific.
 // ------------------------------------------------------------------------------------------------
 static int cpu_supported(const pcgrl_config* cfg) {
   if (!cfg) return fail(-1, "config is NULL");
   int rc = pcgrl_config_validate(cfg);
   if (rc) return rc;
-  if (cfg->problem != PCGRL_PROB_SMB && cfg->problem != PCGRL_PROB_BINARY && cfg->problem != PCGRL_PROB_ZELDA)
-    return fail(-2, "host twin not available for this problem (GPU search kernels): use the CUDA entry point");
-  return 0;
+  return 0;  // every built-in problem has a host twin (pcgrl_host_twin.cuh, pcgrl_solver_host.cuh, pcgrl_smb.cuh)
 }
 struct HostWorkOwner {
   pcgrl_smb::HostWork hw;

@@ -1,4 +1,5 @@
-// pcgrl_host_twin.cuh -- host twins of the graph-only problems (binary, zelda): Problem.get_stats on the CPU.
+// pcgrl_host_twin.cuh -- host twins of the graph-only problems (binary, zelda): Problem.get_stats on the CPU
+// (the solver problems: pcgrl_solver_host.cuh, which reuses the row-array helpers below).
 //
 // The device code gives one map row to one warp lane and propagates BFS frontiers with shuffles; a host thread has no
 // lanes, so the same BITBOARD ALGORITHM (pcgrl_device.cuh / pcgrl_problems.cuh: one word per row, wave = dilation & passable

@@ -5,6 +5,7 @@
 
 #include "pcgrl_env.cuh"
 #include "pcgrl_host_twin.cuh"
+#include "pcgrl_solver_host.cuh"
 #include "pcgrl_smb.cuh"
 
 namespace pcgrl_smb {
@@ -352,7 +353,13 @@ struct HostWork {
 };
 
 static inline int host_nstats(const pcgrl_config* cfg) {
-  return cfg->problem == PCGRL_PROB_BINARY ? 2 : cfg->problem == PCGRL_PROB_ZELDA ? 7 : 8;
+  switch (cfg->problem) {
+    case PCGRL_PROB_BINARY: return 2;
+    case PCGRL_PROB_ZELDA: return 7;
+    case PCGRL_PROB_SOKOBAN: return 6;
+    case PCGRL_PROB_DDAVE: case PCGRL_PROB_MDUNGEON: return 11;
+    default: return 8;
+  }
 }
 // Problem.get_stats: smb = scans + A* play-through (this file), binary / zelda = host bitboards (pcgrl_host_twin.cuh)
 static inline void host_get_stats(const pcgrl_config* cfg, const uint8_t* map, uint32_t* touched, HostWork& hw, int32_t* st) {
@@ -360,18 +367,25 @@ static inline void host_get_stats(const pcgrl_config* cfg, const uint8_t* map, u
   if (cfg->problem == PCGRL_PROB_SMB) {
     scan_stats(map, cfg->width, cfg->height, st);
     run_game_scalar(map, cfg->width, cfg->height, cfg->solver_power, hw.solid, touched, hw.visited, hw.heap, st, nullptr);
-  } else {
-    pcgrl_host::get_stats(cfg, map, st);
+  } else if (!pcgrl_host::get_stats(cfg, map, st)) {  // binary / zelda; else a solver problem (pcgrl_solver_host.cuh)
+    static thread_local pcgrl_host::SearchWork work;
+    pcgrl_host::solver_get_stats(cfg, map, work, st);
   }
 }
 static inline double host_reward(const pcgrl_config* cfg, const int32_t* n, const int32_t* o) {
   if (cfg->problem == PCGRL_PROB_BINARY) return pcgrl::problem_reward<PCGRL_PROB_BINARY>(*cfg, n, o);
   if (cfg->problem == PCGRL_PROB_ZELDA) return pcgrl::problem_reward<PCGRL_PROB_ZELDA>(*cfg, n, o);
+  if (cfg->problem == PCGRL_PROB_SOKOBAN) return pcgrl::problem_reward<PCGRL_PROB_SOKOBAN>(*cfg, n, o);
+  if (cfg->problem == PCGRL_PROB_DDAVE) return pcgrl::problem_reward<PCGRL_PROB_DDAVE>(*cfg, n, o);
+  if (cfg->problem == PCGRL_PROB_MDUNGEON) return pcgrl::problem_reward<PCGRL_PROB_MDUNGEON>(*cfg, n, o);
   return get_reward(*cfg, n, o);
 }
 static inline bool host_over(const pcgrl_config* cfg, const int32_t* n, const int32_t* start) {
   if (cfg->problem == PCGRL_PROB_BINARY) return pcgrl::problem_over<PCGRL_PROB_BINARY>(*cfg, n, start);
   if (cfg->problem == PCGRL_PROB_ZELDA) return pcgrl::problem_over<PCGRL_PROB_ZELDA>(*cfg, n, start);
+  if (cfg->problem == PCGRL_PROB_SOKOBAN) return pcgrl::problem_over<PCGRL_PROB_SOKOBAN>(*cfg, n, start);
+  if (cfg->problem == PCGRL_PROB_DDAVE) return pcgrl::problem_over<PCGRL_PROB_DDAVE>(*cfg, n, start);
+  if (cfg->problem == PCGRL_PROB_MDUNGEON) return pcgrl::problem_over<PCGRL_PROB_MDUNGEON>(*cfg, n, start);
   return episode_over(n);
 }
 

@@ -208,31 +208,33 @@ struct SState {
   uint32_t pad;
 };
 
-__device__ __forceinline__ int st_px(const SState& s) { return (int)(s.ks & 0xffu); }
-__device__ __forceinline__ int st_py(const SState& s) { return (int)((s.ks >> 8) & 0xffu); }
-__device__ __forceinline__ int st_health(const SState& s) { return (int)((s.ks >> 16) & 0xffu); }
-__device__ __forceinline__ void st_set_pos(SState& s, int x, int y) { s.ks = (s.ks & 0xffff0000u) | (uint32_t)x | ((uint32_t)y << 8); }
-__device__ __forceinline__ void st_set_health(SState& s, int h) { s.ks = (s.ks & 0xff00ffffu) | ((uint32_t)h << 16); }
-__device__ __forceinline__ int st_depth(const SState& s) { return (int)(s.dh & 0xffffu); }
-__device__ __forceinline__ int st_h(const SState& s) { return (int)(s.dh >> 16) - SOLVER_PRIO_BIAS; }
+#define SOLVER_HD __host__ __device__ __forceinline__
+SOLVER_HD int st_px(const SState& s) { return (int)(s.ks & 0xffu); }
+SOLVER_HD int st_py(const SState& s) { return (int)((s.ks >> 8) & 0xffu); }
+SOLVER_HD int st_health(const SState& s) { return (int)((s.ks >> 16) & 0xffu); }
+SOLVER_HD void st_set_pos(SState& s, int x, int y) { s.ks = (s.ks & 0xffff0000u) | (uint32_t)x | ((uint32_t)y << 8); }
+SOLVER_HD void st_set_health(SState& s, int h) { s.ks = (s.ks & 0xff00ffffu) | ((uint32_t)h << 16); }
+SOLVER_HD int st_depth(const SState& s) { return (int)(s.dh & 0xffffu); }
+SOLVER_HD int st_h(const SState& s) { return (int)(s.dh >> 16) - SOLVER_PRIO_BIAS; }
 
-__device__ __forceinline__ bool mask_test(const SState& s, int idx) {
+SOLVER_HD bool mask_test(const SState& s, int idx) {
   const uint32_t w = (idx < 64) ? ((idx < 32) ? s.m[0] : s.m[1]) : ((idx < 96) ? s.m[2] : s.m[3]);
   return (w >> (idx & 31)) & 1u;
 }
-__device__ __forceinline__ void mask_clear(SState& s, int idx) {
+SOLVER_HD void mask_clear(SState& s, int idx) {
   const uint32_t bit = ~(1u << (idx & 31));
 #pragma unroll
   for (int w = 0; w < 4; w++) if ((idx >> 5) == w) s.m[w] &= bit;
 }
-__device__ __forceinline__ bool lv_solid(const Level& L, int x, int y) { return (L.solid[y] >> x) & 1u; }
-__device__ __forceinline__ bool lv_movable(const Level& L, int x, int y) {  // ddave :204-205, mdungeon :201-202
+SOLVER_HD bool lv_solid(const Level& L, int x, int y) { return (L.solid[y] >> x) & 1u; }
+SOLVER_HD bool lv_movable(const Level& L, int x, int y) {  // ddave :204-205, mdungeon :201-202
   return !(x < 0 || y < 0 || x >= L.bw || y >= L.bh || lv_solid(L, x, y));
 }
-__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+SOLVER_HD int iabs(int v) { return v < 0 ? -v : v; }
 
 // --- sokoban (sokoban/engine.py) ----------------------------------------------------------------
-__device__ __forceinline__ int sk_crate_at(const SState& s, int x, int y) {  // :262-266 first match in list order
+SOLVER_HD int sk_crate_at(const SState& s, int x, int y) {  // :262-266 first match in list order
+#ifdef __CUDA_ARCH__
   const uint32_t vv = 0x01010101u * (uint32_t)(x | (y << 4));
 #pragma unroll
   for (int w = 0; w < 4; w++) {
@@ -240,27 +242,33 @@ __device__ __forceinline__ int sk_crate_at(const SState& s, int x, int y) {  // 
     if (eq) return 4 * w + ((__ffs(eq) - 1) >> 3);
   }
   return -1;
+#else
+  const uint32_t v = (uint32_t)(x | (y << 4));
+  for (int i = 0; i < 16; i++)
+    if (((s.m[i >> 2] >> (8 * (i & 3))) & 0xffu) == v) return i;
+  return -1;
+#endif
 }
-__device__ __forceinline__ uint32_t sk_crate(const SState& s, int i) {
+SOLVER_HD uint32_t sk_crate(const SState& s, int i) {
   const uint32_t w = (i < 8) ? ((i < 4) ? s.m[0] : s.m[1]) : ((i < 12) ? s.m[2] : s.m[3]);
   return (w >> (8 * (i & 3))) & 0xffu;
 }
-__device__ __forceinline__ void sk_set_crate(SState& s, int i, int x, int y) {
+SOLVER_HD void sk_set_crate(SState& s, int i, int x, int y) {
   const int sh = 8 * (i & 3);
   const uint32_t v = (uint32_t)(x | (y << 4)) << sh, keep = ~(0xffu << sh);
 #pragma unroll
   for (int w = 0; w < 4; w++) if ((i >> 2) == w) s.m[w] = (s.m[w] & keep) | v;
 }
-__device__ __forceinline__ bool sk_movable(const Level& L, const SState& s, int x, int y) {  // :268-269
+SOLVER_HD bool sk_movable(const Level& L, const SState& s, int x, int y) {  // :268-269
   if (x < 0 || y < 0 || x > L.bw - 1 || y > L.bh - 1) return false;
   return !lv_solid(L, x, y) && sk_crate_at(s, x, y) < 0;
 }
-__device__ __forceinline__ bool sk_win(const Level& L, const SState& s) {  // :271-280
+SOLVER_HD bool sk_win(const Level& L, const SState& s) {  // :271-280
   if (L.ntargets != L.ncrates || L.ntargets == 0) return false;
   for (int t = 0; t < L.ntargets; t++) if (sk_crate_at(s, L.tx[t], L.ty[t]) < 0) return false;
   return true;
 }
-__device__ __forceinline__ int sk_heuristic(const Level& L, const SState& s) {  // :282-296
+SOLVER_HD int sk_heuristic(const Level& L, const SState& s) {  // :282-296
   uint32_t used = 0;
   int distance = 0;
   for (int c = 0; c < L.ncrates; c++) {
@@ -280,7 +288,7 @@ __device__ __forceinline__ int sk_heuristic(const Level& L, const SState& s) {  
   }
   return distance;
 }
-__device__ __forceinline__ bool sk_update(const Level& L, SState& s, int dx, int dy) {  // :298-327 -> crateMove
+SOLVER_HD bool sk_update(const Level& L, SState& s, int dx, int dy) {  // :298-327 -> crateMove
   if (sk_win(L, s)) return false;
   const int nx = st_px(s) + dx, ny = st_py(s) + dy;
   if (sk_movable(L, s, nx, ny)) { st_set_pos(s, nx, ny); return false; }
@@ -295,18 +303,18 @@ __device__ __forceinline__ bool sk_update(const Level& L, SState& s, int dx, int
   }
   return false;
 }
-__device__ __forceinline__ bool sk_deadlocked(const Level& L, const SState& s) {  // :248-252
+SOLVER_HD bool sk_deadlocked(const Level& L, const SState& s) {  // :248-252
   for (int c = 0; c < L.ncrates; c++) {
     const uint32_t cr = sk_crate(s, c);
     if ((L.dead[cr >> 4] >> (cr & 15u)) & 1u) return true;
   }
   return false;
 }
-__device__ __forceinline__ bool sk_target_at(const Level& L, int x, int y) {
+SOLVER_HD bool sk_target_at(const Level& L, int x, int y) {
   for (int t = 0; t < L.ntargets; t++) if (L.tx[t] == x && L.ty[t] == y) return true;
   return false;
 }
-__device__ void sk_init_deadlocks(Level& L) {  // :203-246 (single thread)
+__host__ __device__ inline void sk_init_deadlocks(Level& L) {  // :203-246 (single thread)
   for (int y = 0; y < 16; y++) L.dead[y] = 0;
   uint32_t corner[16];
   for (int y = 0; y < 16; y++) corner[y] = 0;
@@ -340,11 +348,11 @@ __device__ void sk_init_deadlocks(Level& L) {  // :203-246 (single thread)
 }
 
 // --- ddave (ddave/engine.py) --------------------------------------------------------------------
-__device__ __forceinline__ int cell_index(const Level& L, int x, int y) { return (y - 1) * L.W + (x - 1); }
-__device__ __forceinline__ bool dd_win(const Level& L, const SState& s) {  // :319-320 (key count == 1 - key_present)
+SOLVER_HD int cell_index(const Level& L, int x, int y) { return (y - 1) * L.W + (x - 1); }
+SOLVER_HD bool dd_win(const Level& L, const SState& s) {  // :319-320 (key count == 1 - key_present)
   return ((s.ks >> 24) & 1u) == 0u && st_px(s) == L.doorx && st_py(s) == L.doory;
 }
-__device__ __forceinline__ void dd_update(const Level& L, SState& s, int dx, int dy) {  // :244-280 + :225-242
+SOLVER_HD void dd_update(const Level& L, SState& s, int dx, int dy) {  // :244-280 + :225-242
   if (dd_win(L, s) || st_health(s) <= 0) return;
   const int px = st_px(s), py = st_py(s);
   int air = (int)(s.misc & 0xffu), diamonds = (int)((s.misc >> 8) & 0xffu), jumps = (int)(s.misc >> 16);
@@ -372,15 +380,15 @@ __device__ __forceinline__ void dd_update(const Level& L, SState& s, int dx, int
   }
   s.misc = (uint32_t)air | ((uint32_t)diamonds << 8) | ((uint32_t)jumps << 16);
 }
-__device__ __forceinline__ int dd_heuristic(const Level& L, const SState& s) {  // :294-299
+SOLVER_HD int dd_heuristic(const Level& L, const SState& s) {  // :294-299
   int d = iabs(st_px(s) - L.doorx) + iabs(st_py(s) - L.doory);
   if ((s.ks >> 24) & 1u) d = iabs(st_px(s) - L.keyx) + iabs(st_py(s) - L.keyy) + (L.bw + L.bh);
   return d - 5 * (int)((s.misc >> 8) & 0xffu);
 }
 
 // --- mdungeon (mdungeon/engine.py) ---------------------------------------------------------------
-__device__ __forceinline__ bool md_win(const Level& L, const SState& s) { return st_px(s) == L.doorx && st_py(s) == L.doory; }  // :308-309
-__device__ __forceinline__ void md_update(const Level& L, SState& s, int dx, int dy) {  // :254-270 + :222-252
+SOLVER_HD bool md_win(const Level& L, const SState& s) { return st_px(s) == L.doorx && st_py(s) == L.doory; }  // :308-309
+SOLVER_HD void md_update(const Level& L, SState& s, int dx, int dy) {  // :254-270 + :222-252
   if (md_win(L, s) || st_health(s) <= 0) return;
   const int nx = st_px(s) + dx, ny = st_py(s) + dy;
   if (!lv_movable(L, nx, ny)) return;
@@ -398,20 +406,20 @@ __device__ __forceinline__ void md_update(const Level& L, SState& s, int dx, int
     s.misc = (uint32_t)potions | ((uint32_t)treasures << 8) | ((uint32_t)enemies << 16);
   }
 }
-__device__ __forceinline__ int md_heuristic(const Level& L, const SState& s) {  // :285-289
+SOLVER_HD int md_heuristic(const Level& L, const SState& s) {  // :285-289
   return iabs(st_px(s) - L.doorx) + iabs(st_py(s) - L.doory) + 4 * (5 - st_health(s)) - 4 * (int)((s.misc >> 8) & 0xffu);
 }
 
-template <int GAME> __device__ __forceinline__ bool g_win(const Level& L, const SState& s) {
+template <int GAME> SOLVER_HD bool g_win(const Level& L, const SState& s) {
   return GAME == GAME_SOKOBAN ? sk_win(L, s) : GAME == GAME_DDAVE ? dd_win(L, s) : md_win(L, s);
 }
-template <int GAME> __device__ __forceinline__ int g_heuristic(const Level& L, const SState& s) {
+template <int GAME> SOLVER_HD int g_heuristic(const Level& L, const SState& s) {
   return GAME == GAME_SOKOBAN ? sk_heuristic(L, s) : GAME == GAME_DDAVE ? dd_heuristic(L, s) : md_heuristic(L, s);
 }
 
 // *_prob.py _run_game level framing + engine.stringInitialize; run by lane 0 after the tiles are staged
 template <int GAME>
-__device__ void level_init(Level& L, SState& root, int W, int H) {
+__host__ __device__ inline void level_init(Level& L, SState& root, int W, int H) {
   L.W = W; L.H = H; L.bw = W + 2; L.bh = H + 2;
   L.ntargets = 0; L.ncrates = 0; L.overflow = 0;
   L.doorx = L.doory = L.keyx = L.keyy = 0;
@@ -553,13 +561,65 @@ __device__ __forceinline__ uint32_t heap_pop(const HeapRef& heap, int& n) {
 }
 
 // crate occupancy of a sokoban state as a 64-bit mask over bordered cells (small levels only)
-__device__ __forceinline__ unsigned long long sk_occupancy(const Level& L, const SState& s) {
+SOLVER_HD unsigned long long sk_occupancy(const Level& L, const SState& s) {
   unsigned long long occ = 0ull;
   for (int c = 0; c < L.ncrates; c++) {
     const uint32_t cr = sk_crate(s, c);
     occ |= 1ull << ((int)(cr >> 4) * L.bw + (int)(cr & 15u));
   }
   return occ;
+}
+
+// One child of Node.getChildren: direction d in the engine's `directions` order applied to a copy `c` of the expanded
+// node `cs`; returns whether the child is kept (sokoban prunes no-move and deadlocked children, engine.py:14-24) and its
+// heuristic in h.  Shared by the warp searches and the host twin.
+template <int GAME>
+SOLVER_HD bool make_child(const Level& L, const SState& cs, int d, bool sk_small, SState& c, int& h) {
+  bool valid = false;
+  h = 0;
+  if (GAME == GAME_SOKOBAN) {  // engine.py:3 and :14-24
+    const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
+    if (sk_small) {
+      // bit-mask form of State.update (:298-327): the expanded node is never a winning state
+      const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
+      const int nx = st_px(cs) + dx, ny = st_py(cs) + dy;
+      const unsigned long long nbit = 1ull << (ny * L.bw + nx);  // inside: the border ring is solid
+      h = st_h(cs);
+      if (!((L.solid64 | occ) & nbit)) {
+        st_set_pos(c, nx, ny);
+        valid = true;
+      } else if (occ & nbit) {
+        const int cx = nx + dx, cy = ny + dy;
+        if (cx >= 0 && cy >= 0 && cx < L.bw && cy < L.bh) {
+          const unsigned long long cbit = 1ull << (cy * L.bw + cx);
+          if (!((L.solid64 | occ) & cbit)) {
+            st_set_pos(c, nx, ny);
+            sk_set_crate(c, sk_crate_at(cs, nx, ny), cx, cy);
+            const unsigned long long occ2 = occ ^ nbit ^ cbit;
+            c.misc = (uint32_t)occ2;
+            c.pad = (uint32_t)(occ2 >> 32);
+            valid = ((occ2 & L.dead64) == 0ull);  // a crate moved: prune deadlocks (any crate)
+            h = sk_heuristic(L, c);
+          }
+        }
+      }
+    } else {
+      const bool crate_move = sk_update(L, c, dx, dy);
+      valid = (c.ks & 0xffffu) != (cs.ks & 0xffffu) && !(crate_move && sk_deadlocked(L, c));
+      h = sk_heuristic(L, c);
+    }
+  } else if (GAME == GAME_DDAVE) {  // ddave/engine.py:3  (0,0) (-1,0) (1,0) (0,-1)
+    const int dx = (d == 1) ? -1 : (d == 2) ? 1 : 0, dy = (d == 3) ? -1 : 0;
+    dd_update(L, c, dx, dy);
+    valid = true;
+    h = dd_heuristic(L, c);
+  } else {  // mdungeon/engine.py:3
+    const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
+    md_update(L, c, dx, dy);
+    valid = true;
+    h = md_heuristic(L, c);
+  }
+  return valid;
 }
 
 #define SOLVER_CACHE_NODES 128 /* shared-memory ring of the most recently created nodes */
@@ -676,49 +736,7 @@ __device__ void search_pass(const Level& L, const SState& root0, int b, int powe
     SState c = cs;
     int h = 0;
     if (lane < 4) {
-      const int d = lane;
-      if (GAME == GAME_SOKOBAN) {  // engine.py:3 and :14-24
-        const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
-        if (sk_small) {
-          // bit-mask form of State.update (:298-327): the expanded node is never a winning state
-          const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
-          const int nx = st_px(cs) + dx, ny = st_py(cs) + dy;
-          const unsigned long long nbit = 1ull << (ny * L.bw + nx);  // inside: the border ring is solid
-          h = st_h(cs);
-          if (!((L.solid64 | occ) & nbit)) {
-            st_set_pos(c, nx, ny);
-            valid = true;
-          } else if (occ & nbit) {
-            const int cx = nx + dx, cy = ny + dy;
-            if (cx >= 0 && cy >= 0 && cx < L.bw && cy < L.bh) {
-              const unsigned long long cbit = 1ull << (cy * L.bw + cx);
-              if (!((L.solid64 | occ) & cbit)) {
-                st_set_pos(c, nx, ny);
-                sk_set_crate(c, sk_crate_at(cs, nx, ny), cx, cy);
-                const unsigned long long occ2 = occ ^ nbit ^ cbit;
-                c.misc = (uint32_t)occ2;
-                c.pad = (uint32_t)(occ2 >> 32);
-                valid = ((occ2 & L.dead64) == 0ull);  // a crate moved: prune deadlocks (any crate)
-                h = sk_heuristic(L, c);
-              }
-            }
-          }
-        } else {
-          const bool crate_move = sk_update(L, c, dx, dy);
-          valid = (c.ks & 0xffffu) != (cs.ks & 0xffffu) && !(crate_move && sk_deadlocked(L, c));
-          h = sk_heuristic(L, c);
-        }
-      } else if (GAME == GAME_DDAVE) {  // ddave/engine.py:3  (0,0) (-1,0) (1,0) (0,-1)
-        const int dx = (d == 1) ? -1 : (d == 2) ? 1 : 0, dy = (d == 3) ? -1 : 0;
-        dd_update(L, c, dx, dy);
-        valid = true;
-        h = dd_heuristic(L, c);
-      } else {  // mdungeon/engine.py:3
-        const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
-        md_update(L, c, dx, dy);
-        valid = true;
-        h = md_heuristic(L, c);
-      }
+      valid = make_child<GAME>(L, cs, lane, sk_small, c, h);  // Node.getChildren, `directions` order = lane
       c.dh = (uint32_t)(cd + 1) | ((uint32_t)(h + SOLVER_PRIO_BIAS) << 16);
     }
     const uint32_t vmask = __ballot_sync(FULL_MASK, valid) & 0xFu;
@@ -877,49 +895,8 @@ __device__ void search_bfs_batched(const Level& L, const SState& root0, int powe
 #pragma unroll
       for (int d = 0; d < 4; d++) {
         c[d] = cs;
-        bool valid = false;
         int h = 0;
-        if (GAME == GAME_SOKOBAN) {
-          const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
-          if (sk_small) {
-            const unsigned long long occ = (unsigned long long)cs.misc | ((unsigned long long)cs.pad << 32);
-            const int nx = st_px(cs) + dx, ny = st_py(cs) + dy;
-            const unsigned long long nbit = 1ull << (ny * L.bw + nx);
-            h = st_h(cs);
-            if (!((L.solid64 | occ) & nbit)) {
-              st_set_pos(c[d], nx, ny);
-              valid = true;
-            } else if (occ & nbit) {
-              const int cx = nx + dx, cy = ny + dy;
-              if (cx >= 0 && cy >= 0 && cx < L.bw && cy < L.bh) {
-                const unsigned long long cbit = 1ull << (cy * L.bw + cx);
-                if (!((L.solid64 | occ) & cbit)) {
-                  st_set_pos(c[d], nx, ny);
-                  sk_set_crate(c[d], sk_crate_at(cs, nx, ny), cx, cy);
-                  const unsigned long long occ2 = occ ^ nbit ^ cbit;
-                  c[d].misc = (uint32_t)occ2;
-                  c[d].pad = (uint32_t)(occ2 >> 32);
-                  valid = ((occ2 & L.dead64) == 0ull);
-                  h = sk_heuristic(L, c[d]);
-                }
-              }
-            }
-          } else {
-            const bool crate_move = sk_update(L, c[d], dx, dy);
-            valid = (c[d].ks & 0xffffu) != (cs.ks & 0xffffu) && !(crate_move && sk_deadlocked(L, c[d]));
-            h = sk_heuristic(L, c[d]);
-          }
-        } else if (GAME == GAME_DDAVE) {
-          const int dx = (d == 1) ? -1 : (d == 2) ? 1 : 0, dy = (d == 3) ? -1 : 0;
-          dd_update(L, c[d], dx, dy);
-          valid = true;
-          h = dd_heuristic(L, c[d]);
-        } else {
-          const int dx = (d == 0) ? -1 : (d == 1) ? 1 : 0, dy = (d == 2) ? -1 : (d == 3) ? 1 : 0;
-          md_update(L, c[d], dx, dy);
-          valid = true;
-          h = md_heuristic(L, c[d]);
-        }
+        const bool valid = make_child<GAME>(L, cs, d, sk_small, c[d], h);
         c[d].dh = (uint32_t)(cd + 1) | ((uint32_t)(h + SOLVER_PRIO_BIAS) << 16);
         h4[d] = h;
         if (valid) vmask |= 1u << d;

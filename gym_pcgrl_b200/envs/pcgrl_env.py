@@ -289,7 +289,7 @@ class BatchedPcgrlEnv:
         self._host = torch.device(self.device).type == "cpu"
         _native.validate(cfg)
         if self._host:
-            # host twin (pcgrl_*_cpu): explicit device="cpu", only for the problems that have one -- never a fallback
+            # host twin (pcgrl_*_cpu): explicit device="cpu" -- never a fallback
             self._dev = torch.device("cpu")
             self._tens, self._cbufs = _native.alloc_buffers(cfg, self.num_envs, self._dev)
             self._d_actions = torch.zeros(self.num_envs * self._adim, dtype=torch.int32)
@@ -425,7 +425,7 @@ class PcgrlEnv:
     metadata = {'render.modes': []}
 
     def __init__(self, prob="binary", rep="narrow", device="cuda"):
-        # device="cpu" selects the host twin (pcgrl_*_cpu) for the problems that have one
+        # device="cpu" selects the host twin (pcgrl_*_cpu)
         self._batched = BatchedPcgrlEnv(prob, rep, num_envs=1, device=device, auto_reset=False)
         self._prob = self._batched._prob
         self._rep = self._batched._rep

@@ -280,9 +280,9 @@ int pcgrl_smb_get_stats(const uint8_t* maps, int32_t* stats_out, int n, int widt
  * Host twins: the same operations on HOST pointers, computed on the calling CPU thread by the very
  * scalar `__host__ __device__` functions the kernels run -- for plumbing / CI without a GPU (BASELINE config 1 style
  * single-env runs).  They are separate, explicitly named entry points: the CUDA entry points above never fall back to
- * them.  Available for the problems whose step logic is scalar code (smb); for the warp-cooperative bitboard problems
- * they return -2 with an explanatory pcgrl_last_error().  pcgrl_buffers.scratch must hold pcgrl_scratch_bytes() bytes of
- * host memory.
+ * them.  Available for every built-in problem: smb and the solver problems' game models are the kernels' own scalar
+ * functions (under a plain scalar search loop), binary / zelda restate the bitboard algorithm over row arrays.
+ * pcgrl_buffers.scratch must hold pcgrl_scratch_bytes() bytes of host memory.
  */
 int pcgrl_reset_cpu(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const uint8_t* mask_or_null, int n);
 int pcgrl_step_cpu(const pcgrl_config* cfg, const pcgrl_buffers* bufs, const int32_t* actions, int n);

@@ -1,9 +1,10 @@
-"""Host twins of the graph-only problems (pcgrl_reset_cpu / pcgrl_step_cpu / pcgrl_get_stats_cpu for binary and zelda):
-the bitboard algorithm of the kernels restated over row arrays on the host (csrc/pcgrl_host_twin.cuh), checked WITHOUT a
-GPU against
-  * every binary / zelda golden trajectory recorded from the unmodified reference (incl. BASELINE config 1:
+"""Host twins (pcgrl_reset_cpu / pcgrl_step_cpu / pcgrl_get_stats_cpu) of binary, zelda, sokoban, ddave and mdungeon: the
+bitboard algorithm of the kernels restated over row arrays on the host (csrc/pcgrl_host_twin.cuh) and, for the solver
+problems, the kernels' own `__host__ __device__` game models under a plain scalar search loop
+(csrc/pcgrl_solver_host.cuh), checked WITHOUT a GPU against
+  * every golden trajectory of these problems recorded from the unmodified reference (incl. BASELINE config 1:
     binary-narrow 11x11, 1000 random-action steps -- SURVEY App. B.3 digest c455bfaf0f3e3b63),
-  * the reference-labelled get_stats fixtures, and the oracle on random ragged sizes up to 32 x 32.
+  * the reference-labelled get_stats fixtures, and the oracle on random ragged sizes.
 This is the "config 1 runs without a GPU and without the oracle" path: PcgrlEnv(..., device="cpu")."""
 import hashlib
 import struct
@@ -17,7 +18,7 @@ import util
 from gym_pcgrl_b200 import PROBLEMS, REPRESENTATIONS, PcgrlEnv, _abi, _native
 from gym_pcgrl_b200._config import build_config
 
-KATS = [m for m in util.kat_configs() if m["env_id"].split("-")[0] in ("binary", "zelda")]
+KATS = [m for m in util.kat_configs() if m["env_id"].split("-")[0] in ("binary", "zelda", "sokoban", "ddave", "mdungeon")]
 
 
 @pytest.mark.parametrize("meta", KATS, ids=[m["name"] for m in KATS])
@@ -107,7 +108,49 @@ def test_host_twin_get_stats_matches_reference_golden_and_oracle(prob_name):
         np.testing.assert_array_equal(got, want, err_msg="%s %dx%d" % (prob_name, w, h))
 
 
-def test_solver_problems_have_no_host_twin():
-    env = PcgrlEnv("sokoban", "wide", device="cpu")
-    with pytest.raises(_native.NativeError, match="host twin not available"):
-        env.reset()
+@pytest.mark.parametrize("prob_name", ["sokoban", "ddave", "mdungeon"])
+def test_solver_host_twin_get_stats_matches_reference_golden_and_oracle(prob_name):
+    """Problem.get_stats incl. the BFS / A* play-through: reference-labelled maps, then oracle-labelled random maps with
+    the preconditions forced on half of them (one player, matching crates / targets, one key / exit / door)."""
+    n = 0
+    for maps, stats in util.stats_groups(prob_name):
+        prob = PROBLEMS[prob_name]()
+        prob.adjust_param(width=maps.shape[2], height=maps.shape[1])
+        got = _native.get_stats(prob, torch.from_numpy(maps)).numpy()
+        np.testing.assert_array_equal(got[:, :stats.shape[1]], stats)
+        n += len(maps)
+    assert n > 0
+    rng = np.random.RandomState(29)
+    sizes = {"sokoban": [(5, 5), (7, 6), (3, 9), (8, 8)], "ddave": [(11, 7), (7, 11), (5, 5), (14, 9)],
+             "mdungeon": [(7, 11), (11, 7), (6, 6), (14, 9)]}[prob_name]
+    for (w, h) in sizes:
+        prob = PROBLEMS[prob_name]()
+        prob.adjust_param(width=w, height=h)
+        T = len(prob.tile_types)
+        maps = []
+        for k in range(24):
+            dens = 0.5 + 0.45 * rng.random_sample()
+            p = np.full(T, (1 - dens) * 0.5 / (T - 2)); p[0] = dens; p[1] = (1 - dens) * 0.5
+            m = rng.choice(T, size=(h, w), p=p / p.sum()).astype(np.uint8)
+            if k % 2 == 0:      # make the play-through likely to run: exactly one of each singleton tile
+                flat = m.reshape(-1)
+                singles = {"sokoban": [2], "ddave": [2, 3, 5], "mdungeon": [2, 3]}[prob_name]
+                for t in singles:
+                    flat[flat == t] = 0
+                cells = rng.choice(flat.size, size=len(singles), replace=False)
+                for t, c in zip(singles, cells):
+                    flat[c] = t
+                if prob_name == "sokoban":
+                    flat[(flat == 3) | (flat == 4)] = 0
+                    free = np.flatnonzero(flat == 0)
+                    kk = int(rng.randint(1, 3))
+                    if len(free) >= 2 * kk:
+                        pick = rng.choice(free, size=2 * kk, replace=False)
+                        flat[pick[:kk]] = 3
+                        flat[pick[kk:]] = 4
+            maps.append(m)
+        maps = np.stack(maps)
+        cfg = build_config(prob, REPRESENTATIONS["wide"](), 1, 1, auto_reset=False)
+        want = oracle.get_stats(cfg, maps, threads=4)
+        got = _native.get_stats(prob, torch.from_numpy(maps)).numpy()
+        np.testing.assert_array_equal(got, want, err_msg="%s %dx%d" % (prob_name, w, h))

@@ -17,7 +17,8 @@ EXPORTS = ["pcgrl_abi_version", "pcgrl_last_error", "pcgrl_config_validate", "pc
            "pcgrl_host_staging_bytes", "pcgrl_obs_image", "pcgrl_action_map", "pcgrl_rollout_host",
            "pcgrl_smb_scratch_bytes", "pcgrl_smb_get_stats", "pcgrl_reset_cpu", "pcgrl_step_cpu", "pcgrl_get_stats_cpu",
            "pcgrl_step_host_begin", "pcgrl_step_host_end", "pcgrl_render",
-           "pcgrl_linear_bf16", "pcgrl_linear_last_error", "pcgrl_linear_bf16_ex", "pcgrl_im2col"]
+           "pcgrl_linear_bf16", "pcgrl_linear_last_error", "pcgrl_linear_bf16_ex", "pcgrl_im2col",
+           "pcgrl_conv3x3_bf16", "pcgrl_linear_bf16_pad"]
 
 _lib = None
 
@@ -88,6 +89,10 @@ def lib():
         L.pcgrl_linear_bf16_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.pcgrl_im2col.restype = C.c_int
         L.pcgrl_im2col.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+        L.pcgrl_conv3x3_bf16.restype = C.c_int
+        L.pcgrl_conv3x3_bf16.argtypes = [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]
+        L.pcgrl_linear_bf16_pad.restype = C.c_int
+        L.pcgrl_linear_bf16_pad.argtypes = [C.c_void_p] * 4 + [C.c_int] * 6 + [C.c_void_p]
         L.pcgrl_host_staging_bytes.restype = C.c_size_t
         L.pcgrl_host_staging_bytes.argtypes = [C.POINTER(_abi.PcgrlConfig), C.c_int]
         if L.pcgrl_abi_version() != _abi.ABI_VERSION:

@@ -94,7 +94,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constant__ CUtensorMap map_x,
                                                             const __grid_constant__ CUtensorMap map_w,
                                                             const float* __restrict__ bias, void* __restrict__ y_out, int M, int N,
-                                                            int K, int relu, int out_bf16) {
+                                                            int K, int relu, int out_bf16, int pad_h, int pad_w) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128: 1024-B aligned
   uint8_t* smem_a = smem;
@@ -197,6 +197,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
           mbar_arrive(&tmem_empty[as]);
         }
         if (row < M) {
+          // pad_w > 0: row m = (e, y, x) of an [n, pad_h, pad_w] image batch lands at (e, y + 1, x + 1) of the zero-bordered
+          // [n, pad_h + 2, pad_w + 2] buffer the implicit-GEMM convolution reads (k_conv3x3_bf16)
+          size_t orow = (size_t)row;
+          if (pad_w > 0) {
+            const int x = row % pad_w, t = row / pad_w, yy = t % pad_h, e = t / pad_h;
+            orow = ((size_t)e * (pad_h + 2) + yy + 1) * (pad_w + 2) + x + 1;
+          }
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j++) {
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
             f[j] = relu ? fmaxf(t, 0.0f) : t;
           }
           if (out_bf16) {  // bf16 activations for the next layer (N % 8 == 0): 16-byte stores of eight values
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(y_out) + (size_t)row * N + n0 + c0;
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(y_out) + orow * N + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (n0 + c0 + j + 7 < N) {
@@ -221,11 +228,167 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
               }
             }
           } else {
-            float* out = reinterpret_cast<float*>(y_out) + (size_t)row * N + n0 + c0;
+            float* out = reinterpret_cast<float*>(y_out) + orow * N + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (n0 + c0 + j + 3 < N) *reinterpret_cast<float4*>(out + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               else for (int q = 0; q < 4; q++) if (n0 + c0 + j + q < N) out[j + q] = f[j + q];
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// 3 x 3, stride 1, SAME convolution + bias + ReLU as an IMPLICIT GEMM (the seven 64-channel layers and the n_tools head of the
+// reference's fully convolutional policies, model.py:25-77).  Activations live in a zero-bordered NHWC buffer
+// P[n][H + 2][W + 2][C] (bf16, C % 64 == 0).  Over the flattened padded positions p the input of filter tap (r, s) for 128
+// consecutive outputs is the SAME 2-D tensor [n (H+2) (W+2), C] shifted by (r - 1)(W + 2) + (s - 1) rows, so every A tile is a
+// plain TMA box load at a row offset (out-of-range rows are zero-filled by TMA) and no patch matrix is ever written:
+//     out[p][:] = relu(bias + sum_{tap} P[p + shift(tap)][:] . Wt[tap][:, :]^T)      for interior p; border p are stored as 0
+// so the output is again a zero-bordered buffer for the next layer.  The whole weight matrix (9 C/64 blocks of BN x 64) is
+// loaded once per CTA and stays in shared memory; the ring of stages carries A tiles only.  Same warp roles, pipelines and
+// TMEM double buffering as k_linear_bf16.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int CONV_STAGES = 6;
+template <int BN> __host__ __device__ constexpr int conv_smem_bytes(int kblocks) {
+  return kblocks * tile_b_bytes<BN>() + CONV_STAGES * TILE_A_BYTES + 1024 + 2048;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_constant__ CUtensorMap map_x,
+                                                             const __grid_constant__ CUtensorMap map_w,
+                                                             const float* __restrict__ bias, __nv_bfloat16* __restrict__ y_out,
+                                                             int Mp, int N, int C, int H, int W, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TILE_B_BYTES = tile_b_bytes<BLOCK_N>();
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  const int cblocks = C / BLOCK_K, num_kb = 9 * cblocks;
+  uint8_t* smem_b = smem;                                  // [num_kb] weight blocks, resident
+  uint8_t* smem_a = smem + num_kb * TILE_B_BYTES;          // [CONV_STAGES] activation tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + CONV_STAGES * TILE_A_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + CONV_STAGES;
+  uint64_t* tmem_full = bars + 2 * CONV_STAGES;
+  uint64_t* tmem_empty = bars + 2 * CONV_STAGES + 2;
+  uint64_t* b_full = bars + 2 * CONV_STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CONV_STAGES + 5);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * CONV_STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (Mp + BLOCK_M - 1) / BLOCK_M;
+  const int PW = W + 2, PH = H + 2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    for (int s = 0; s < CONV_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    mbar_init(b_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64)
+    for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) bias_s[c] = (bias && c < N) ? bias[c] : 0.0f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(b_full, (uint32_t)(num_kb * TILE_B_BYTES));
+      for (int kb = 0; kb < num_kb; kb++) tma_load_2d(smem_b + kb * TILE_B_BYTES, &map_w, b_full, kb * BLOCK_K, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * BLOCK_M;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int tap = kb / cblocks, cb = kb - tap * cblocks;
+          const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
+          const int s = it % CONV_STAGES;
+          mbar_wait(&empty[s], ((it / CONV_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], TILE_A_BYTES);
+          tma_load_2d(smem_a + s * TILE_A_BYTES, &map_x, &full[s], cb * BLOCK_K, m0 + shift);  // rows < 0 or >= Mp: zero fill
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      mbar_wait(b_full, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
+        const int as = lt & 1;
+        mbar_wait(&tmem_empty[as], ((lt >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % CONV_STAGES;
+          mbar_wait(&full[s], (it / CONV_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + kb * TILE_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), instr_desc<BLOCK_N>(), (kb | k) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {  // ===== epilogue: TMEM -> bias + ReLU, zero at border positions -> bf16 NHWC =====
+    const int quarter = warp & 3;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
+      const int m0 = tile * BLOCK_M, as = lt & 1;
+      mbar_wait(&tmem_full[as], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + quarter * 32 + lane;
+      const int px = row % PW, py = (row / PW) % PH;
+      const bool interior = px >= 1 && px <= W && py >= 1 && py <= H;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= BLOCK_N) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&tmem_empty[as]);
+        }
+        if (row < Mp) {
+          __nv_bfloat16* out = y_out + (size_t)row * N + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (c0 + j + 7 < N) {  // N % 8 == 0
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);
+              if (interior) {
+                uint32_t* ow = &o.x;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  float a = __uint_as_float(v[j + 2 * q]) + bias_s[c0 + j + 2 * q], b = __uint_as_float(v[j + 2 * q + 1]) + bias_s[c0 + j + 2 * q + 1];
+                  if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                  const __nv_bfloat162 p2 = __floats2bfloat162_rn(a, b);
+                  ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
+                }
+              }
+              *reinterpret_cast<uint4*>(out + j) = o;
             }
           }
         }
@@ -313,8 +476,8 @@ extern "C" const char* pcgrl_linear_last_error(void) { return g_linear_err; }
 // Y[M,N] (row-major, fp32 or bf16) = act(X[M,K] . W[N,K]^T + bias[N]); X, W bf16 row-major device pointers (16-byte aligned,
 // K % 8 == 0; N % 4 == 0 for fp32 output, N % 8 == 0 for bf16 output); bias may be NULL; relu != 0 applies max(., 0).
 // Enqueues on `stream`; 0 = OK.
-extern "C" int pcgrl_linear_bf16_ex(const void* x_bf16, const void* w_bf16, const float* bias, void* y, int M, int N, int K, int relu,
-                                    int out_bf16, void* stream) {
+static int linear_launch(const void* x_bf16, const void* w_bf16, const float* bias, void* y, int M, int N, int K, int relu,
+                         int out_bf16, int pad_h, int pad_w, void* stream) {
   using namespace pcgrl_linear;
   if (!x_bf16 || !w_bf16 || !y) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
   if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & (out_bf16 ? 7 : 3))) { snprintf(g_linear_err, sizeof(g_linear_err), "need M, N, K > 0, K %% 8 == 0, N %% 4 == 0 (fp32 out) or N %% 8 == 0 (bf16 out)"); return -1; }
@@ -334,9 +497,61 @@ extern "C" int pcgrl_linear_bf16_ex(const void* x_bf16, const void* w_bf16, cons
     configured = true;
   }
   const int tiles = tiles_m * ((N + bn - 1) / bn), grid = tiles < sm_count ? tiles : sm_count;
-  if (wide) k_linear_bf16<256><<<grid, THREADS, smem_bytes<256>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu, out_bf16);
-  else k_linear_bf16<128><<<grid, THREADS, smem_bytes<128>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu, out_bf16);
+  if (wide) k_linear_bf16<256><<<grid, THREADS, smem_bytes<256>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu, out_bf16, pad_h, pad_w);
+  else k_linear_bf16<128><<<grid, THREADS, smem_bytes<128>(), (cudaStream_t)stream>>>(mx, mw, bias, y, M, N, K, relu, out_bf16, pad_h, pad_w);
   cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+  return 0;
+}
+
+extern "C" int pcgrl_linear_bf16_ex(const void* x_bf16, const void* w_bf16, const float* bias, void* y, int M, int N, int K, int relu,
+                                    int out_bf16, void* stream) {
+  return linear_launch(x_bf16, w_bf16, bias, y, M, N, K, relu, out_bf16, 0, 0, stream);
+}
+
+// The same GEMM with bf16 output rows scattered into a zero-bordered NHWC buffer: row m = (e, y, x) of an [M / (H W), H, W]
+// image batch is written at (e, y + 1, x + 1) of y_padded[M / (H W)][H + 2][W + 2][N] (the caller zeroes the buffer once; the
+// border is never written).  This is how the first convolution of a fully convolutional policy (im2col: few input channels)
+// hands its activations to pcgrl_conv3x3_bf16.
+extern "C" int pcgrl_linear_bf16_pad(const void* x_bf16, const void* w_bf16, const float* bias, void* y_padded, int M, int N, int K,
+                                     int relu, int H, int W, void* stream) {
+  if (H <= 0 || W <= 0 || M % (H * W)) { snprintf(g_linear_err, sizeof(g_linear_err), "M must be a multiple of H * W"); return -1; }
+  return linear_launch(x_bf16, w_bf16, bias, y_padded, M, N, K, relu, 1, H, W, stream);
+}
+
+// 3 x 3 / stride 1 / SAME convolution + bias (+ ReLU) on zero-bordered NHWC bf16 activations (k_conv3x3_bf16):
+//   x_padded [n][H + 2][W + 2][C], C % 64 == 0;  w [Npad][9 C] bf16 with k = (ky * 3 + kx) * C + c, Npad % 8 == 0, Npad <= 64;
+//   y_padded [n][H + 2][W + 2][Npad]: interior = act(conv + bias), border = 0.  Enqueues on `stream`; 0 = OK.
+extern "C" int pcgrl_conv3x3_bf16(const void* x_padded, const void* w_bf16, const float* bias, void* y_padded, int n, int H, int W, int C,
+                                  int Npad, int relu, void* stream) {
+  using namespace pcgrl_linear;
+  if (!x_padded || !w_bf16 || !y_padded) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
+  if (n <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % BLOCK_K) || Npad <= 0 || (Npad & 7) || Npad > 64) {
+    snprintf(g_linear_err, sizeof(g_linear_err), "need C %% 64 == 0 and Npad %% 8 == 0, Npad <= 64");
+    return -1;
+  }
+  if (((uintptr_t)x_padded | (uintptr_t)w_bf16 | (uintptr_t)y_padded) & 15) { snprintf(g_linear_err, sizeof(g_linear_err), "pointers must be 16-byte aligned"); return -1; }
+  const long long mp = (long long)n * (H + 2) * (W + 2);
+  if (mp >= (1ll << 31) - 4096) { snprintf(g_linear_err, sizeof(g_linear_err), "too many padded positions: split the batch"); return -1; }
+  const int Mp = (int)mp, kblocks = 9 * (C / BLOCK_K), bn = Npad <= 32 ? 32 : 64;
+  const int smem = bn == 32 ? conv_smem_bytes<32>(kblocks) : conv_smem_bytes<64>(kblocks);
+  if (smem > 227 * 1024) { snprintf(g_linear_err, sizeof(g_linear_err), "C too large for the resident-weight layout"); return -1; }
+  static thread_local int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count < 1) sm_count = 148; }
+  CUtensorMap mx, mw;
+  if (make_map(&mx, x_padded, Mp, C, BLOCK_M) || make_map(&mw, w_bf16, Npad, 9 * C, bn)) { snprintf(g_linear_err, sizeof(g_linear_err), "cuTensorMapEncodeTiled failed"); return -1; }
+  static thread_local int configured32 = 0, configured64 = 0;
+  int& configured = bn == 32 ? configured32 : configured64;
+  if (configured < smem) {
+    const cudaError_t c1 = bn == 32 ? cudaFuncSetAttribute(k_conv3x3_bf16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                    : cudaFuncSetAttribute(k_conv3x3_bf16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (c1 != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "smem opt-in: %s", cudaGetErrorString(c1)); return (int)c1; }
+    configured = smem;
+  }
+  const int tiles = (Mp + BLOCK_M - 1) / BLOCK_M, grid = tiles < sm_count ? tiles : sm_count;
+  if (bn == 32) k_conv3x3_bf16<32><<<grid, THREADS, smem, (cudaStream_t)stream>>>(mx, mw, bias, (__nv_bfloat16*)y_padded, Mp, Npad, C, H, W, relu);
+  else k_conv3x3_bf16<64><<<grid, THREADS, smem, (cudaStream_t)stream>>>(mx, mw, bias, (__nv_bfloat16*)y_padded, Mp, Npad, C, H, W, relu);
+  const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
   return 0;
 }
@@ -348,12 +563,13 @@ extern "C" int pcgrl_linear_bf16(const void* x_bf16, const void* w_bf16, const f
 
 // im2col of NHWC activations for a KS x KS convolution (stride, zero padding `pad`): in [n][H][W][C] uint8 (in_bf16 == 0) or
 // bf16 -> out [n * Ho * Wo][Kpad] bf16 with k = (ky * KS + kx) * C + c, zero-filled up to Kpad (Kpad % 8 == 0, >= KS*KS*C).
+// pad = -1 skips a one-cell border of the input: a VALID convolution over the interior of a zero-bordered buffer.
 // conv + bias + ReLU = pcgrl_im2col followed by pcgrl_linear_bf16_ex on weights laid out [Cout][Kpad].
 extern "C" int pcgrl_im2col(const void* in, int in_bf16, void* out_bf16, int n, int H, int W, int C, int ksize, int stride, int pad,
                             int Kpad, void* stream) {
   using namespace pcgrl_linear;
   if (!in || !out_bf16) { snprintf(g_linear_err, sizeof(g_linear_err), "NULL argument"); return -1; }
-  if (n <= 0 || H <= 0 || W <= 0 || C <= 0 || ksize <= 0 || stride <= 0 || pad < 0 || (Kpad & 7) || Kpad < ksize * ksize * C) {
+  if (n <= 0 || H <= 0 || W <= 0 || C <= 0 || ksize <= 0 || stride <= 0 || pad < -1 || (Kpad & 7) || Kpad < ksize * ksize * C) {
     snprintf(g_linear_err, sizeof(g_linear_err), "bad im2col arguments (Kpad %% 8 == 0, Kpad >= ksize^2 * C)");
     return -1;
   }

@@ -1,10 +1,12 @@
 """The policy forward pass of model.py on this repo's own kernels.
 
 ``NativePolicy(net)`` takes an ``ActorCritic`` (models.py: the reference's four policy classes) and runs its inference
-path -- observation [N, H, W, C] uint8 from the fused wrapper kernel -> logits, value -- without cuDNN / cuBLAS: every
-convolution is ``pcgrl_im2col`` (NHWC patches, bf16) followed by ``pcgrl_linear_bf16_ex`` (csrc/pcgrl_linear.cu: TMA ->
-tcgen05.mma -> TMEM, bias + ReLU fused in the epilogue, bf16 activations written in the NHWC layout the next layer reads),
-the dense layers are the same GEMM kernel.  torch only owns the buffers (and slices the padded head columns).
+path -- observation [N, H, W, C] uint8 from the fused wrapper kernel -> logits, value -- without cuDNN / cuBLAS.  Strided /
+VALID / few-channel convolutions are ``pcgrl_im2col`` (NHWC patches, bf16) followed by ``pcgrl_linear_bf16_ex``
+(csrc/pcgrl_linear.cu: TMA -> tcgen05.mma -> TMEM, bias + ReLU fused in the epilogue, bf16 activations written in the NHWC
+layout the next layer reads); the 3 x 3 SAME layers of the fully convolutional policies (c2..c8) are an implicit GEMM on
+zero-bordered NHWC buffers (``pcgrl_conv3x3_bf16``: no patch matrix, weights resident in shared memory); the dense layers
+are the same GEMM kernel.  torch only owns the buffers (and slices the padded head columns).
 Weights are snapshotted in bf16 at construction (``refresh()`` after an optimiser step); accumulation is fp32.
 """
 import torch
@@ -66,6 +68,56 @@ class _Conv:
         return y, ho, wo, self.gemm.npad
 
 
+def _check(rc, what):
+    if rc:
+        raise _native.NativeError("%s failed (rc=%d): %s" % (what, rc, _native.lib().pcgrl_linear_last_error().decode()))
+
+
+class _ConvFirstPadded:
+    """The first SAME convolution of a fully convolutional policy (few input channels: im2col + GEMM), writing its bf16
+    activations into the zero-bordered [n, H + 2, W + 2, 64] buffer the implicit-GEMM layers read."""
+
+    def __init__(self, conv, device):
+        cout, cin, kh, kw = conv.weight.shape
+        assert kh == 3 and conv.stride[0] == 1 and conv.padding[0] == 1 and cout <= 64
+        self.cin, self.ks = cin, kh
+        w2 = torch.zeros((64, kh * kw * cin), dtype=conv.weight.dtype, device=conv.weight.device)   # channels cout..63 stay zero
+        w2[:cout] = conv.weight.detach().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+        b = torch.zeros(64, dtype=conv.bias.dtype, device=conv.bias.device)
+        b[:cout] = conv.bias.detach()
+        self.gemm = _Gemm(w2, b, True, True, device)
+        self.cols = None
+
+    def __call__(self, obs, out_padded, n, h, w, c, stream):
+        assert c == self.cin
+        m = n * h * w
+        if self.cols is None or self.cols.shape[0] != m:
+            self.cols = torch.empty((m, self.gemm.kpad), dtype=torch.bfloat16, device=self.gemm.w.device)
+        L = _native.lib()
+        _check(L.pcgrl_im2col(obs.data_ptr(), 0, self.cols.data_ptr(), n, h, w, c, 3, 1, 1, self.gemm.kpad, stream), "pcgrl_im2col")
+        g = self.gemm
+        _check(L.pcgrl_linear_bf16_pad(self.cols.data_ptr(), g.w.data_ptr(), g.b.data_ptr(), out_padded.data_ptr(), m, 64, g.kpad, 1,
+                                       h, w, stream), "pcgrl_linear_bf16_pad")
+
+
+class _Conv3x3Implicit:
+    """3 x 3 / stride 1 / SAME conv + bias + ReLU as an implicit GEMM on zero-bordered NHWC buffers (pcgrl_conv3x3_bf16)."""
+
+    def __init__(self, conv, device):
+        cout, cin, kh, kw = conv.weight.shape
+        assert kh == 3 and kw == 3 and conv.stride[0] == 1 and conv.padding[0] == 1 and cin <= 64 and cout <= 64
+        self.cout, self.npad = cout, (64 if cout > 32 else _pad8(cout))
+        w = torch.zeros((self.npad, 3, 3, 64), dtype=torch.float32, device=device)                   # input channels padded to 64
+        w[:cout, :, :, :cin] = conv.weight.detach().permute(0, 2, 3, 1).to(device=device, dtype=torch.float32)
+        self.w = w.reshape(self.npad, 9 * 64).to(torch.bfloat16).contiguous()
+        self.b = torch.zeros(self.npad, dtype=torch.float32, device=device)
+        self.b[:cout] = conv.bias.detach().to(device=device, dtype=torch.float32)
+
+    def __call__(self, x_padded, y_padded, n, h, w, stream):
+        _check(_native.lib().pcgrl_conv3x3_bf16(x_padded.data_ptr(), self.w.data_ptr(), self.b.data_ptr(), y_padded.data_ptr(), n, h, w,
+                                                64, self.npad, 1, stream), "pcgrl_conv3x3_bf16")
+
+
 class NativePolicy:
     def __init__(self, net):
         if not isinstance(net, ActorCritic):
@@ -80,8 +132,18 @@ class NativePolicy:
         self.device = _native.require_cuda(dev)
         ex = net.extractor
         if net.fully_conv:
-            self.body = [_Conv(c, dev) for c in ex.body]
+            # c1: im2col + GEMM into a zero-bordered buffer; c2..c8: implicit GEMM, ping-pong between two such buffers
+            self.first = _ConvFirstPadded(ex.body[0], dev)
+            self.body = [_Conv3x3Implicit(c, dev) for c in ex.body[1:]]
+            self.head_pad = self.body[-1].npad
             self.value_convs = [_Conv(c, dev) for c in ex.value]
+            v1 = ex.value[0]     # reads the c8 map: its input channels are padded like the c8 output (zero weights)
+            wv = torch.zeros((v1.out_channels, self.head_pad, v1.kernel_size[0], v1.kernel_size[1]), dtype=v1.weight.dtype, device=v1.weight.device)
+            wv[:, :v1.in_channels] = v1.weight.detach()
+            self.value_convs[0].cin = self.head_pad
+            self.value_convs[0].pad = -1     # VALID over the interior of the zero-bordered c8 map
+            self.value_convs[0].gemm = _Gemm(wv.permute(0, 2, 3, 1).reshape(v1.out_channels, -1), v1.bias.detach(), True, True, dev)
+            self.bufs = None
             self.vf = _Gemm(net.vf.weight.detach(), net.vf.bias.detach(), False, False, dev)
             self.n_tools = ex.body[-1].out_channels
         else:
@@ -109,13 +171,19 @@ class NativePolicy:
                 feat = self.fc1(x, n, stream)                       # x viewed as [n, h * w * 64]: contiguous, no copy
                 out = self.heads(feat, n, stream)                   # [n, pad4(A + 1)] fp32
                 return out[:, :self.n_actions], out[:, self.n_actions]
-            for conv in self.body:
-                x, h, w, c = conv(x, in_bf16, n, h, w, c, stream)
-                in_bf16 = True
+            if self.bufs is None or self.bufs[0].shape[:3] != (n, h + 2, w + 2):
+                self.bufs = [torch.zeros((n, h + 2, w + 2, 64), dtype=torch.bfloat16, device=obs.device) for _ in range(2)] + \
+                            [torch.zeros((n, h + 2, w + 2, self.head_pad), dtype=torch.bfloat16, device=obs.device)]
+            a, b, head = self.bufs
+            self.first(x, a, n, h, w, c, stream)
+            for conv in self.body[:-1]:
+                conv(a, b, n, h, w, stream)
+                a, b = b, a
+            self.body[-1](a, head, n, h, w, stream)                  # c8: n_tools channels (padded to a multiple of 8)
             tools = self.n_tools
-            act = x.view(n, h, w, c)[..., :tools]                   # c8 output, padded channels dropped
-            logits = act.float().reshape(n, h * w * tools)
-            v, vh, vw, vc = act.contiguous(), h, w, tools           # the value branch reads the n_tools-channel map
+            logits = head[:, 1:-1, 1:-1, :tools].float().reshape(n, h * w * tools)
+            # the value branch: VALID convolutions over the interior of the zero-bordered c8 map (im2col with pad = -1)
+            v, vh, vw, vc = head, h + 2, w + 2, self.head_pad
             for conv in self.value_convs:
                 v, vh, vw, vc = conv(v, True, n, vh, vw, vc, stream)
             value = self.vf(v, n, stream)                           # v viewed as [n, vh * vw * 64]

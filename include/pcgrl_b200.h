@@ -309,6 +309,21 @@ int pcgrl_linear_bf16_ex(const void* x_bf16, const void* w_bf16, const float* bi
  */
 int pcgrl_im2col(const void* in, int in_bf16, void* out_bf16, int n, int H, int W, int C, int ksize, int stride,
                  int pad, int Kpad, void* stream);
+/*
+ * The 3 x 3 / stride 1 / SAME convolutions of the fully convolutional policies (model.py:25-77: c2..c8) as an IMPLICIT
+ * GEMM -- no patch matrix.  Activations live in zero-bordered NHWC buffers P[n][H + 2][W + 2][C] (bf16): over the flattened
+ * padded positions the input of filter tap (ky, kx) is the same 2-D tensor shifted by (ky - 1)(W + 2) + (kx - 1) rows, i.e. a
+ * plain TMA tile load at a row offset; the weights stay resident in shared memory.
+ *   pcgrl_conv3x3_bf16: x_padded [n][H+2][W+2][C], C % 64 == 0; w [Npad][9 C] bf16, k = (ky * 3 + kx) * C + c, Npad % 8 == 0,
+ *                       Npad <= 64; y_padded [n][H+2][W+2][Npad]: interior = act(conv + bias), border = 0.
+ *   pcgrl_linear_bf16_pad: the GEMM of pcgrl_linear_bf16_ex with its bf16 output row m = (e, y, x) written at (e, y+1, x+1) of
+ *                       such a buffer (zeroed once by the caller) -- the hand-over from the first, im2col-based, layer.
+ *   pcgrl_im2col with pad = -1 reads the interior of such a buffer (the VALID convolutions of the value branch).
+ */
+int pcgrl_conv3x3_bf16(const void* x_padded, const void* w_bf16, const float* bias, void* y_padded, int n, int H, int W,
+                       int C, int Npad, int relu, void* stream);
+int pcgrl_linear_bf16_pad(const void* x_bf16, const void* w_bf16, const float* bias, void* y_padded, int M, int N, int K,
+                          int relu, int H, int W, void* stream);
 const char* pcgrl_linear_last_error(void);
 
 #ifdef __cplusplus

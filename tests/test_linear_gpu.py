@@ -69,3 +69,43 @@ def test_native_policy_forward_matches_torch(kind, obs_shape, n_actions, n):
     for got, want in ((got_logits, want_logits), (got_value, want_value)):
         tol = 0.03 * float(want.abs().max()) + 0.02
         assert float((got.float() - want).abs().max()) <= tol, (kind, float((got.float() - want).abs().max()), tol)
+
+
+@pytest.mark.parametrize("n,h,w,cout,relu", [(3, 5, 5, 64, 1), (7, 14, 14, 64, 1), (2, 16, 11, 5, 0), (33, 7, 11, 8, 1), (1, 1, 1, 64, 1),
+                                             (130, 14, 14, 2, 1)])
+def test_implicit_gemm_conv3x3_matches_torch(n, h, w, cout, relu):
+    """pcgrl_conv3x3_bf16 (tcgen05 implicit GEMM on a zero-bordered NHWC buffer: nine shifted TMA loads per tile, weights
+    resident in shared memory) against torch conv2d in fp32 on the same bf16-rounded inputs.  Tolerance: fp32 accumulation of
+    576 bf16 products + one bf16 rounding of the output: |err| <= 0.01 * max|ref| + 0.01.  The border of the output must be
+    exactly zero (it is the next layer's padding)."""
+    import torch
+    import torch.nn.functional as F
+    from gym_pcgrl_b200 import _native
+    torch.manual_seed(n * 100 + h)
+    cin = 64
+    x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
+    wt = (0.1 * torch.randn(cout, cin, 3, 3, device="cuda")).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda")
+    npad = 64 if cout > 32 else (cout + 7) // 8 * 8
+    xp = torch.zeros(n, h + 2, w + 2, cin, dtype=torch.bfloat16, device="cuda")
+    xp[:, 1:-1, 1:-1] = x
+    w2 = torch.zeros(npad, 3, 3, cin, dtype=torch.bfloat16, device="cuda")
+    w2[:cout] = wt.permute(0, 2, 3, 1)
+    b2 = torch.zeros(npad, device="cuda")
+    b2[:cout] = bias
+    yp = torch.full((n, h + 2, w + 2, npad), 7.0, dtype=torch.bfloat16, device="cuda")      # poisoned: the kernel must write the border
+    rc = _native.lib().pcgrl_conv3x3_bf16(xp.data_ptr(), w2.reshape(npad, -1).contiguous().data_ptr(), b2.data_ptr(), yp.data_ptr(),
+                                          n, h, w, cin, npad, relu, _native.stream_ptr(torch.device("cuda", 0)))
+    assert rc == 0, _native.lib().pcgrl_linear_last_error()
+    torch.cuda.synchronize()
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)
+    if relu:
+        want = want.relu()
+    want = want.permute(0, 2, 3, 1)
+    got = yp[:, 1:-1, 1:-1, :cout].float()
+    tol = 0.01 * float(want.abs().max()) + 0.01
+    assert float((got - want).abs().max()) <= tol, (float((got - want).abs().max()), tol)
+    assert float(yp[:, 0].abs().max()) == 0 and float(yp[:, -1].abs().max()) == 0
+    assert float(yp[:, :, 0].abs().max()) == 0 and float(yp[:, :, -1].abs().max()) == 0
+    if npad > cout:
+        assert float(yp[..., cout:].abs().max()) == 0

@@ -66,6 +66,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const void* tile) {
   return addr | (0ull << 16) /* LBO unused: one swizzle atom along K */ | (sbo << 32) | (1ull << 46) /* version: sm_100 */ |
          (2ull << 61) /* LayoutType::SWIZZLE_128B */;
 }
+// A tile may also be read starting `r` (< 8) rows into a 1024-byte swizzle atom by adding r * 128 bytes (r * 8 in this
+// descriptor's address field) to the start address and nothing else: the tensor core applies the 128-byte swizzle to the
+// ABSOLUTE shared-memory address it computes (start + (i / 8) * SBO + (i % 8) * 128 is linear in the row i because
+// SBO = 8 * 128), exactly like TMA did when it wrote the tile.  Measured: with the "matrix base offset" bits (49-51) set to
+// the row phase the results are wrong, with 0 they equal those of separately loaded tiles.  k_conv3x3_bf16 feeds the three
+// horizontal filter taps from ONE staged tile this way.
 // UMMA instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 template <int BN> __host__ __device__ constexpr uint32_t instr_desc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -127,7 +133,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  // (broadcast: the compiler then keeps the TMEM address in a uniform register instead of re-electing a lane per MMA)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: one ring of smem stages across all tiles of this CTA =====
@@ -249,19 +256,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
 // reference's fully convolutional policies, model.py:25-77).  Activations live in a zero-bordered NHWC buffer
 // P[n][H + 2][W + 2][C] (bf16, C % 64 == 0).  Over the flattened padded positions p the input of filter tap (r, s) for 128
 // consecutive outputs is the SAME 2-D tensor [n (H+2) (W+2), C] shifted by (r - 1)(W + 2) + (s - 1) rows, so every A tile is a
-// plain TMA box load at a row offset (out-of-range rows are zero-filled by TMA) and no patch matrix is ever written:
+// plain TMA box load at a row offset (out-of-range rows are zero-filled by TMA) and no patch matrix is ever written; the
+// three taps of one filter row differ by ONE row, so a single staged tile of 130 rows serves all three through UMMA
+// descriptors that start 0, 1 and 2 rows into the swizzle atom (see umma_smem_desc) -- each activation tile is read from L2
+// three times, not nine:
 //     out[p][:] = relu(bias + sum_{tap} P[p + shift(tap)][:] . Wt[tap][:, :]^T)      for interior p; border p are stored as 0
 // so the output is again a zero-bordered buffer for the next layer.  The whole weight matrix (9 C/64 blocks of BN x 64) is
 // loaded once per CTA and stays in shared memory; the ring of stages carries A tiles only.  Same warp roles, pipelines and
 // TMEM double buffering as k_linear_bf16.
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int CONV_STAGES = 6;
+constexpr int CONV_STAGES = 5;
+constexpr int CONV_ROWS = BLOCK_M + 2;                       // rows m0 - 1 .. m0 + 128 of one filter row: the taps kx = 0, 1, 2
+constexpr int CONV_A_BYTES = ((CONV_ROWS * BLOCK_K * 2 + 1023) / 1024) * 1024;  // stage stride: 1024-byte aligned (17 KB)
+constexpr int CONV_A_TX = CONV_ROWS * BLOCK_K * 2;           // bytes one TMA box delivers
+// epilogue: BN / 32 groups of four warps (one warp per TMEM lane quarter and 32-column slice), 2 KB transpose buffer per warp
+template <int BN> __host__ __device__ constexpr int conv_threads() { return 96 + 128 * (BN / 32); }  // TMA, 2 x MMA, epilogue groups
 template <int BN> __host__ __device__ constexpr int conv_smem_bytes(int kblocks) {
-  return kblocks * tile_b_bytes<BN>() + CONV_STAGES * TILE_A_BYTES + 1024 + 2048;
+  return kblocks * tile_b_bytes<BN>() + CONV_STAGES * CONV_A_BYTES + 1024 + 2048 + 4 * (BN / 32) * 2048;
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_constant__ CUtensorMap map_x,
+__global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(const __grid_constant__ CUtensorMap map_x,
                                                              const __grid_constant__ CUtensorMap map_w,
                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ y_out,
                                                              int Mp, int N, int C, int H, int W, int relu) {
@@ -271,8 +286,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_consta
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   const int cblocks = C / BLOCK_K, num_kb = 9 * cblocks;
   uint8_t* smem_b = smem;                                  // [num_kb] weight blocks, resident
-  uint8_t* smem_a = smem + num_kb * TILE_B_BYTES;          // [CONV_STAGES] activation tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + CONV_STAGES * TILE_A_BYTES);
+  uint8_t* smem_a = smem + num_kb * TILE_B_BYTES;          // [CONV_STAGES] activation tiles of CONV_ROWS rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + CONV_STAGES * CONV_A_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + CONV_STAGES;
   uint64_t* tmem_full = bars + 2 * CONV_STAGES;
@@ -280,6 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_consta
   uint64_t* b_full = bars + 2 * CONV_STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CONV_STAGES + 5);
   float* bias_s = reinterpret_cast<float*>(bars + 2 * CONV_STAGES + 6);
+  uint4* xpose = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 2048);  // [epilogue warp][32 rows][4 chunks]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (Mp + BLOCK_M - 1) / BLOCK_M;
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < CONV_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * (BLOCK_N / 32)); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -297,12 +313,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 64)
-    for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) bias_s[c] = (bias && c < N) ? bias[c] : 0.0f;
+  if (threadIdx.x >= 96)
+    for (int c = threadIdx.x - 96; c < BLOCK_N; c += blockDim.x - 96) bias_s[c] = (bias && c < N) ? bias[c] : 0.0f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  // (broadcast: the compiler then keeps the TMEM address in a uniform register instead of re-electing a lane per MMA)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
@@ -311,40 +328,58 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_consta
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = tile * BLOCK_M;
-        for (int kb = 0; kb < num_kb; kb++, it++) {
-          const int tap = kb / cblocks, cb = kb - tap * cblocks;
-          const int shift = (tap / 3 - 1) * PW + (tap % 3 - 1);
-          const int s = it % CONV_STAGES;
-          mbar_wait(&empty[s], ((it / CONV_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full[s], TILE_A_BYTES);
-          tma_load_2d(smem_a + s * TILE_A_BYTES, &map_x, &full[s], cb * BLOCK_K, m0 + shift);  // rows < 0 or >= Mp: zero fill
-        }
+        for (int ky = 0; ky < 3; ky++)
+          for (int cb = 0; cb < cblocks; cb++, it++) {
+            const int s = it % CONV_STAGES;
+            mbar_wait(&empty[s], ((it / CONV_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&full[s], CONV_A_TX);
+            // rows m0 + (ky - 1) PW - 1 .. + 129: serves kx = 0, 1, 2 at row offsets 0, 1, 2; rows < 0 or >= Mp: zero fill
+            tma_load_2d(smem_a + s * CONV_A_BYTES, &map_x, &full[s], cb * BLOCK_K, m0 + (ky - 1) * PW - 1);
+          }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 2) {
+    // ===== two MMA issuers: warp 1 drives the even tiles of this CTA (TMEM stage 0), warp 2 the odd ones (stage 1).  A
+    // 128 x 64 x 16 MMA lasts 32 cycles, less than one thread needs to issue it, so two threads issue into the tensor
+    // pipe; each shared-memory stage belongs to exactly one tile, hence to one issuer, and the ring order is unchanged.
+    if (lane == 0) {
       mbar_wait(b_full, 0);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
+      const int loads_per_tile = 3 * cblocks;
+      int lt = warp - 1;
+      for (int tile = blockIdx.x + (warp - 1) * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, lt += 2) {
+        int it = lt * loads_per_tile;
         const int as = lt & 1;
         mbar_wait(&tmem_empty[as], ((lt >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
-        for (int kb = 0; kb < num_kb; kb++, it++) {
-          const int s = it % CONV_STAGES;
-          mbar_wait(&full[s], (it / CONV_STAGES) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + kb * TILE_B_BYTES);
+        uint32_t first = 0u;  // the first MMA of a tile overwrites the accumulator
+        for (int ky = 0; ky < 3; ky++)
+          for (int cb = 0; cb < cblocks; cb++, it++) {
+            const int s = it % CONV_STAGES;
+            mbar_wait(&full[s], (it / CONV_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da0 = umma_smem_desc(smem_a + s * CONV_A_BYTES);            // kx = 1, 2: + 8, + 16 (one row = 128 B)
+            const uint64_t db0 = umma_smem_desc(smem_b + (ky * 3 * cblocks + cb) * TILE_B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), instr_desc<BLOCK_N>(), (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);
-        }
+            for (int kx = 0; kx < 3; kx++) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                umma_f16(tmem_d, da0 + (uint64_t)(8 * kx + 2 * k), db0 + (uint64_t)(kx * cblocks * (TILE_B_BYTES >> 4) + 2 * k),
+                         instr_desc<BLOCK_N>(), first);
+                first = 1u;
+              }
+            }
+            umma_commit(&empty[s]);
+          }
         umma_commit(&tmem_full[as]);
       }
     }
   } else {  // ===== epilogue: TMEM -> bias + ReLU, zero at border positions -> bf16 NHWC =====
-    const int quarter = warp & 3;
+    // warp (3 + 4 g + q') owns TMEM lanes of quarter (warp & 3) and the 32 accumulator columns [32 g, 32 g + 32): one
+    // tcgen05.ld per tile, packed to bf16 by the row's thread, transposed through 2 KB of shared memory so that the global
+    // stores are 64-byte row segments (four lanes per row) instead of one 16-byte piece per row and instruction.
+    const int quarter = warp & 3, c0 = ((warp - 3) >> 2) * 32;
+    uint4* xp = xpose + (warp - 3) * 128;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
       const int m0 = tile * BLOCK_M, as = lt & 1;
@@ -353,46 +388,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv3x3_bf16(const __grid_consta
       const int row = m0 + quarter * 32 + lane;
       const int px = row % PW, py = (row / PW) % PH;
       const bool interior = px >= 1 && px <= W && py >= 1 && py <= H;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= BLOCK_N) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&tmem_empty[as]);
-        }
-        if (row < Mp) {
-          __nv_bfloat16* out = y_out + (size_t)row * N + c0;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty[as]);  // the accumulator slice is in registers: hand the stage back to the MMA warp
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (c0 + j + 7 < N) {  // N % 8 == 0
-              uint4 o = make_uint4(0u, 0u, 0u, 0u);
-              if (interior) {
-                uint32_t* ow = &o.x;
+      for (int c = 0; c < 4; c++) {  // chunk c = columns [c0 + 8 c, +8) of this thread's row
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (interior) {
+          uint32_t* ow = &o.x;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  float a = __uint_as_float(v[j + 2 * q]) + bias_s[c0 + j + 2 * q], b = __uint_as_float(v[j + 2 * q + 1]) + bias_s[c0 + j + 2 * q + 1];
-                  if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                  const __nv_bfloat162 p2 = __floats2bfloat162_rn(a, b);
-                  ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
-                }
-              }
-              *reinterpret_cast<uint4*>(out + j) = o;
-            }
+          for (int q = 0; q < 4; q++) {
+            float a = __uint_as_float(v[8 * c + 2 * q]) + bias_s[c0 + 8 * c + 2 * q], b = __uint_as_float(v[8 * c + 2 * q + 1]) + bias_s[c0 + 8 * c + 2 * q + 1];
+            if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(a, b);
+            ow[q] = *reinterpret_cast<const uint32_t*>(&p2);
           }
         }
+        xp[lane * 4 + (c ^ ((lane >> 1) & 3))] = o;
       }
+      __syncwarp();
+      const int cc = lane & 3;  // this lane stores chunk cc of rows (lane >> 2) + 8 j
+      if (c0 + 8 * cc + 7 < N) {  // N % 8 == 0
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = (lane >> 2) + 8 * j, grow = m0 + quarter * 32 + r;
+          if (grow < Mp) *reinterpret_cast<uint4*>(y_out + (size_t)grow * N + c0 + 8 * cc) = xp[r * 4 + (cc ^ ((r >> 1) & 3))];
+        }
+      }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -539,7 +574,7 @@ extern "C" int pcgrl_conv3x3_bf16(const void* x_padded, const void* w_bf16, cons
   static thread_local int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count < 1) sm_count = 148; }
   CUtensorMap mx, mw;
-  if (make_map(&mx, x_padded, Mp, C, BLOCK_M) || make_map(&mw, w_bf16, Npad, 9 * C, bn)) { snprintf(g_linear_err, sizeof(g_linear_err), "cuTensorMapEncodeTiled failed"); return -1; }
+  if (make_map(&mx, x_padded, Mp, C, CONV_ROWS) || make_map(&mw, w_bf16, Npad, 9 * C, bn)) { snprintf(g_linear_err, sizeof(g_linear_err), "cuTensorMapEncodeTiled failed"); return -1; }
   static thread_local int configured32 = 0, configured64 = 0;
   int& configured = bn == 32 ? configured32 : configured64;
   if (configured < smem) {
@@ -549,8 +584,8 @@ extern "C" int pcgrl_conv3x3_bf16(const void* x_padded, const void* w_bf16, cons
     configured = smem;
   }
   const int tiles = (Mp + BLOCK_M - 1) / BLOCK_M, grid = tiles < sm_count ? tiles : sm_count;
-  if (bn == 32) k_conv3x3_bf16<32><<<grid, THREADS, smem, (cudaStream_t)stream>>>(mx, mw, bias, (__nv_bfloat16*)y_padded, Mp, Npad, C, H, W, relu);
-  else k_conv3x3_bf16<64><<<grid, THREADS, smem, (cudaStream_t)stream>>>(mx, mw, bias, (__nv_bfloat16*)y_padded, Mp, Npad, C, H, W, relu);
+  if (bn == 32) k_conv3x3_bf16<32><<<grid, conv_threads<32>(), smem, (cudaStream_t)stream>>>(mx, mw, bias, (__nv_bfloat16*)y_padded, Mp, Npad, C, H, W, relu);
+  else k_conv3x3_bf16<64><<<grid, conv_threads<64>(), smem, (cudaStream_t)stream>>>(mx, mw, bias, (__nv_bfloat16*)y_padded, Mp, Npad, C, H, W, relu);
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { snprintf(g_linear_err, sizeof(g_linear_err), "launch: %s", cudaGetErrorString(ce)); return (int)ce; }
   return 0;

@@ -1424,6 +1424,26 @@ extern "C" int pcgrl_obs_image(const pcgrl_config* cfg, const uint8_t* maps, con
   if (total >= (1ull << 32)) return fail(-1, "observation tensor too large (>= 2^32 elements): split the batch");
   cudaStream_t s = (cudaStream_t)stream;
   if (out_dtype == 0) {
+    // warp-per-env word builder for the two layouts the policies consume (raw index with S_w % 4 == 0, 8 one-hot channels)
+    const int mode = (channels == 1 && (S_w & 3) == 0) ? 0 : (channels == 8 ? 1 : -1);
+    if (mode >= 0 && crop_size <= 2 * OBS_FAST_SLACK && ((uintptr_t)maps & 3) == 0 && ((uintptr_t)out & 3) == 0) {
+      const int D = mode == 0 ? (S_w >> 2) : S_w, range = mode == 0 ? S_h * D : S_h * S_w;
+      const uint32_t magic = (65536u + (uint32_t)D - 1u) / (uint32_t)D;
+      bool exact = true;
+      for (int v = 0; v < range && exact; v++) exact = (int)(((uint32_t)v * magic) >> 16) == v / D;
+      if (exact) {
+        unsigned blocks = (unsigned)((n + OBS_FAST_WARPS - 1) / OBS_FAST_WARPS);
+        if (blocks > 148u * 8u) blocks = 148u * 8u;
+        const size_t map_bytes = (size_t)n * cfg->height * cfg->width;
+        if (mode == 0)
+          k_obs_image_u8_fast<0><<<blocks, 32 * OBS_FAST_WARPS, 0, s>>>(maps, pos, (uint32_t*)out, n, cfg->height, cfg->width, S_h, S_w,
+                                                                       crop_size, pad_value, magic, map_bytes);
+        else
+          k_obs_image_u8_fast<1><<<blocks, 32 * OBS_FAST_WARPS, 0, s>>>(maps, pos, (uint32_t*)out, n, cfg->height, cfg->width, S_h, S_w,
+                                                                       crop_size, pad_value, magic, map_bytes);
+        return cuda_rc(cudaGetLastError(), "pcgrl_obs_image launch");
+      }
+    }
     const unsigned blocks = (unsigned)((total + OBS_THREADS * 64 - 1) / (OBS_THREADS * 64));  // one 16 KB tile per CTA
     k_obs_image<uint8_t><<<blocks, OBS_THREADS, 0, s>>>(maps, pos, (uint8_t*)out, (uint32_t)total, n, cfg->height, cfg->width,
                                                         S_h, S_w, crop_size, pad_value, channels);

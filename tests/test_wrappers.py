@@ -114,6 +114,47 @@ def test_batched_cropped_image_matches_oracle(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prob,w,h,crop", [("binary", 16, 16, 28), ("binary", 13, 7, 28), ("binary", 9, 31, 12), ("binary", 32, 32, 64),
+                                           ("binary", 5, 3, 4), ("binary", 16, 16, 0), ("binary", 12, 5, 0), ("zelda", 11, 7, 22),
+                                           ("zelda", 11, 16, 22), ("mdungeon", 7, 11, 64), ("zelda", 9, 9, 0), ("mdungeon", 3, 5, 7)])
+def test_uint8_fast_path_equals_float_path(prob, w, h, crop):
+    """pcgrl_obs_image, uint8 output (warp-per-env word builder: funnel-shifted row windows for the raw index, one word per
+    four one-hot channels) against the float32 output of the generic kernel on the same random maps and cursors, at ragged
+    sizes (env strides that are not multiples of 4, crops wider than the map, cursors in every corner).  Exact equality."""
+    import ctypes as C
+    import torch
+    from gym_pcgrl_b200 import PROBLEMS, REPRESENTATIONS, _native
+    from gym_pcgrl_b200._config import build_config
+    p = PROBLEMS[prob]()
+    p.adjust_param(width=w, height=h)
+    cfg = build_config(p, REPRESENTATIONS["narrow"](), 1, 1, auto_reset=False)
+    T, n = len(p.tile_types), 301
+    g = torch.Generator().manual_seed(w * 100 + h)
+    maps = torch.randint(0, T, (n, h, w), generator=g, dtype=torch.uint8).cuda()
+    pos = torch.stack([torch.randint(0, w, (n,), generator=g), torch.randint(0, h, (n,), generator=g)], dim=1).to(torch.uint8)
+    pos[0] = torch.tensor([0, 0]); pos[1] = torch.tensor([w - 1, h - 1]); pos[2] = torch.tensor([0, h - 1]); pos[3] = torch.tensor([w - 1, 0])
+    pos = pos.cuda()
+    one_hot = prob != "binary"
+    sh, sw, c = (crop or h), (crop or w), (T if one_hot else 1)
+    outs = []
+    for dt, code in ((torch.uint8, 0), (torch.float32, 1)):
+        out = torch.full((n, sh, sw, c), 99, dtype=dt, device="cuda")
+        rc = _native.lib().pcgrl_obs_image(C.byref(cfg), maps.data_ptr(), pos.data_ptr(), out.data_ptr(), n, crop, 1, int(one_hot), code,
+                                           _native.stream_ptr(torch.device("cuda", 0)))
+        assert rc == 0, _native.lib().pcgrl_last_error()
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].float(), outs[1])
+    # and one env against numpy directly
+    m = maps[1].cpu().numpy()
+    padded = np.pad(m, crop // 2, constant_values=1) if crop else m
+    x, y = int(pos[1, 0]), int(pos[1, 1])
+    win = padded[y:y + crop, x:x + crop] if crop else padded
+    want = np.eye(T, dtype=np.uint8)[win] if one_hot else win[..., None]
+    np.testing.assert_array_equal(outs[0][1].cpu().numpy(), want)
+
+
+@pytest.mark.gpu
 def test_batched_action_map_matches_oracle():
     import torch
     from gym_pcgrl_b200 import wrappers as W

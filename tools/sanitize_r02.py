@@ -1,5 +1,5 @@
 """Small workloads of the round-2 kernels for `compute-sanitizer --tool memcheck` (k_smb_*, k_rollout_packed_binary,
-k_render, k_im2col, k_linear_bf16).   compute-sanitizer --tool memcheck python tools/sanitize_r02.py"""
+k_render, k_im2col, k_linear_bf16, k_conv3x3_bf16, k_obs_image_u8_fast, k_rollout_async with the split open list).   compute-sanitizer --tool memcheck python tools/sanitize_r02.py"""
 import os
 import sys
 
@@ -44,6 +44,31 @@ for (w, h, n) in ((16, 16, 21), (8, 8, 13)):
 for kind, shape, acts_n, n in (("CustomPolicyBigMap", (28, 28, 1), 3, 70), ("FullyConvPolicySmallMap", (5, 5, 5), 125, 33)):
     net = ActorCritic(kind, shape, acts_n).cuda()
     NativePolicy(net)(torch.randint(0, 2, (n,) + shape, dtype=torch.uint8, device="cuda"))
+net = ActorCritic("FullyConvPolicyBigMap", (14, 14, 1), 392).cuda()        # implicit-GEMM convolutions (BLOCK_N 64 and 32)
+NativePolicy(net)(torch.randint(0, 2, (19, 14, 14, 1), dtype=torch.uint8, device="cuda"))
 _native.linear_bf16(torch.randn(300, 200, device="cuda"), torch.randn(132, 200, device="cuda"), torch.randn(132, device="cuda"))
+# uint8 observation fast paths (raw index with a crop wider than the map; one-hot 8 channels) at odd env strides
+import ctypes as C
+from gym_pcgrl_b200 import PROBLEMS, REPRESENTATIONS
+from gym_pcgrl_b200._config import build_config
+for prob, w, h, crop in (("binary", 13, 7, 28), ("binary", 32, 32, 64), ("zelda", 11, 7, 22), ("mdungeon", 7, 11, 64)):
+    p = PROBLEMS[prob]()
+    p.adjust_param(width=w, height=h)
+    cfg = build_config(p, REPRESENTATIONS["narrow"](), 1, 1, auto_reset=False)
+    T, n = len(p.tile_types), 37
+    maps = torch.randint(0, T, (n, h, w), dtype=torch.uint8, device="cuda")
+    pos = torch.stack([torch.randint(0, w, (n,)), torch.randint(0, h, (n,))], dim=1).to(torch.uint8).cuda()
+    out = torch.empty((n, crop, crop, T if prob != "binary" else 1), dtype=torch.uint8, device="cuda")
+    rc = _native.lib().pcgrl_obs_image(C.byref(cfg), maps.data_ptr(), pos.data_ptr(), out.data_ptr(), n, crop, 1, int(prob != "binary"), 0,
+                                       _native.stream_ptr(torch.device("cuda", 0)))
+    assert rc == 0
+# solver problems: the open list spills from shared memory to the HBM tail on long searches
+for prob in ("sokoban", "mdungeon"):
+    e = BatchedPcgrlEnv(prob, "wide", num_envs=200, device="cuda", seed=3)
+    e.reset()
+    hi = [int(v) for v in e.action_space.nvec]
+    a = torch.stack([torch.randint(0, h, (40, 200), device="cuda", dtype=torch.int32) for h in hi], dim=-1).contiguous()
+    e.rollout(a)
+    e.check_status()
 torch.cuda.synchronize()
 print("sanitize workloads done")

@@ -123,7 +123,14 @@ __global__ void __launch_bounds__(32 * OBS_FAST_WARPS) k_obs_image_u8_fast(const
     const int off = (int)(b0 & 3);
     const size_t g0 = b0 >> 2;
     const int nw = (off + cells + 3) >> 2;
-    for (int k = lane; k < nw; k += 32) smap32[(OBS_FAST_SLACK >> 2) + k] = (g0 + k < last_word) ? maps32[g0 + k] : 0u;
+    for (int k = lane; k < nw; k += 32) {
+      uint32_t v = 0u;
+      const size_t g = g0 + k;
+      if ((g + 1) * 4 <= map_bytes_total) v = maps32[g];
+      else if (g < last_word)  // the last, partial word of the whole batch: never read past the caller's buffer
+        for (size_t b = g * 4; b < map_bytes_total; b++) v |= (uint32_t)maps[b] << (8 * (int)(b - g * 4));
+      smap32[(OBS_FAST_SLACK >> 2) + k] = v;
+    }
     int ox = 0, oy = 0;
     if (crop) { ox = (int)pos[2 * e] - pad; oy = (int)pos[2 * e + 1] - pad; }
     __syncwarp();

@@ -31,4 +31,4 @@ _native.lib().pcgrl_debug_timers(out)
 c = out[7]
 print("calls %d  wall %.1f us/step" % (c, wall))
 for i, nm in enumerate(["H2D enqueue", "kernel enqueue", "D2H enqueue", "sync wait", "apply records"]):
-    print("%-16s %6.1f us" % (nm, out[i] / c))
+    print("%-16s %6.1f us per step" % (nm, out[i] / (K + 8)))   # the counter ticks in _begin and in _end: divide by the steps

@@ -130,5 +130,33 @@ class PPO:
         return self
 
 
+    # ---- the reference's model.save / PPO2.load / agent.predict (train.py:40-48, inference.py:28-36)
+    def save(self, path):
+        base = self.env.pcgrl_env
+        torch.save({"policy": self.policy.state_dict(), "kind": self.policy.kind, "obs_shape": tuple(self.env.shape),
+                    "n_actions": int(self.env.action_space.n), "game": base._prob.name, "representation": base._rep.name,
+                    "num_timesteps": self.num_timesteps}, path)
+
+    def load(self, path):
+        """Load weights saved by ``save`` into this learner (same game / representation / observation shape)."""
+        ck = torch.load(path, map_location=self.device)
+        if ck["kind"] != self.policy.kind or tuple(ck["obs_shape"]) != tuple(self.env.shape) or ck["n_actions"] != int(self.env.action_space.n):
+            raise ValueError("checkpoint is for %s %s, this learner is %s %s" % (ck["kind"], ck["obs_shape"], self.policy.kind, tuple(self.env.shape)))
+        self.policy.load_state_dict(ck["policy"])
+        self.num_timesteps = int(ck.get("num_timesteps", 0))
+        if self.native is not None:
+            self.native.refresh()
+        return self
+
+    @torch.no_grad()
+    def predict(self, obs, deterministic=False):
+        """agent.predict(obs): actions int32 [N] for a batch of observations (sampled like stable-baselines unless
+        deterministic)."""
+        infer = self.native if self.native is not None else self.policy
+        logits, _ = infer(obs)
+        a = logits.argmax(dim=1) if deterministic else torch.distributions.Categorical(logits=logits).sample()
+        return a.to(torch.int32)
+
+
 def nn_utils_clip(params, max_norm):
     torch.nn.utils.clip_grad_norm_(params, max_norm)

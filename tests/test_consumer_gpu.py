@@ -60,3 +60,34 @@ def test_ppo_consumer_runs_on_device(game, rep, envs):
     assert all(torch.isfinite(p).all() for p in ppo.policy.parameters())
     assert ppo.obs_buf.dtype == torch.uint8 and ppo.obs_buf.is_cuda
     env.pcgrl_env.check_status()
+
+
+def test_ppo_save_load_predict_and_inference_tool(tmp_path):
+    """model.save / PPO2.load / agent.predict of the reference's train.py + inference.py: a saved learner reloads to the same
+    logits (torch modules and native kernels), and tools/inference.py plays one episode per env with it."""
+    import importlib.util
+    import os
+    import torch
+    from gym_pcgrl_b200.ppo import PPO, make_training_env
+    env = make_training_env("binary", "narrow", 64)
+    agent = PPO(env, n_steps=8, native_policy=True)
+    agent.learn(8 * 64)
+    path = str(tmp_path / "agent.pt")
+    agent.save(path)
+    env2 = make_training_env("binary", "narrow", 64)
+    other = PPO(env2, n_steps=8, native_policy=True, seed=123).load(path)
+    obs = env2.reset()
+    with torch.no_grad():
+        a, b = agent.policy(obs)[0], other.policy(obs)[0]
+    assert torch.equal(a, b)
+    acts = other.predict(obs, deterministic=True)
+    assert acts.dtype == torch.int32 and acts.shape == (64,) and int(acts.max()) < int(env2.action_space.n)
+    spec = importlib.util.spec_from_file_location("inference_tool", os.path.join(os.path.dirname(__file__), "..", "tools", "inference.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    out = str(tmp_path / "maps.npz")
+    ret = tool.infer("binary", "narrow", path, num_envs=32, change_percentage=0.4, out=out)
+    assert ret.shape == (32,)
+    import numpy as np
+    z = np.load(out)
+    assert z["maps"].shape == (32, 14, 14) and z["render"].shape[0] == 16 and z["render"].shape[-1] == 3

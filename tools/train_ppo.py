@@ -17,9 +17,13 @@ def main():
     ap.add_argument("--timesteps", type=float, default=2e6)
     ap.add_argument("--n-steps", type=int, default=128)
     ap.add_argument("--native-policy", action="store_true", help="rollout inference through im2col + the tcgen05 GEMM kernel")
+    ap.add_argument("--save", default=None, help="write the trained policy here (tools/inference.py loads it)")
     a = ap.parse_args()
     env = make_training_env(a.game, a.rep, a.envs)
-    PPO(env, n_steps=a.n_steps, native_policy=a.native_policy).learn(int(a.timesteps))
+    agent = PPO(env, n_steps=a.n_steps, native_policy=a.native_policy).learn(int(a.timesteps))
+    if a.save:
+        agent.save(a.save)
+        print("saved", a.save)
 
 
 if __name__ == "__main__":

@@ -91,7 +91,7 @@ class _ConvFirstPadded:
     def __call__(self, obs, out_padded, n, h, w, c, stream):
         assert c == self.cin
         m = n * h * w
-        if self.cols is None or self.cols.shape[0] < m:
+        if self.cols is None or self.cols.shape[0] != m:
             self.cols = torch.empty((m, self.gemm.kpad), dtype=torch.bfloat16, device=self.gemm.w.device)
         L = _native.lib()
         _check(L.pcgrl_im2col(obs.data_ptr(), 0, self.cols.data_ptr(), n, h, w, c, 3, 1, 1, self.gemm.kpad, stream), "pcgrl_im2col")
@@ -144,7 +144,6 @@ class NativePolicy:
             self.value_convs[0].pad = -1     # VALID over the interior of the zero-bordered c8 map
             self.value_convs[0].gemm = _Gemm(wv.permute(0, 2, 3, 1).reshape(v1.out_channels, -1), v1.bias.detach(), True, True, dev)
             self.bufs = None
-            self.chunk_bytes = 32 << 20
             self.vf = _Gemm(net.vf.weight.detach(), net.vf.bias.detach(), False, False, dev)
             self.n_tools = ex.body[-1].out_channels
         else:
@@ -172,21 +171,15 @@ class NativePolicy:
                 feat = self.fc1(x, n, stream)                       # x viewed as [n, h * w * 64]: contiguous, no copy
                 out = self.heads(feat, n, stream)                   # [n, pad4(A + 1)] fp32
                 return out[:, :self.n_actions], out[:, self.n_actions]
-            # The 64-channel activations are processed in env chunks small enough for two ping-pong buffers to stay in the
-            # 126 MB L2 (32 MB each): a chunk runs c1..c8 back to back, so the layers read their input from L2, not HBM.
-            cs = max(1, min(n, self.chunk_bytes // ((h + 2) * (w + 2) * 128)))
-            if self.bufs is None or self.bufs[0].shape[:3] != (cs, h + 2, w + 2) or self.bufs[2].shape[0] != n:
-                self.bufs = [torch.zeros((cs, h + 2, w + 2, 64), dtype=torch.bfloat16, device=obs.device) for _ in range(2)] + \
+            if self.bufs is None or self.bufs[0].shape[:3] != (n, h + 2, w + 2):
+                self.bufs = [torch.zeros((n, h + 2, w + 2, 64), dtype=torch.bfloat16, device=obs.device) for _ in range(2)] + \
                             [torch.zeros((n, h + 2, w + 2, self.head_pad), dtype=torch.bfloat16, device=obs.device)]
-            head = self.bufs[2]
-            for s0 in range(0, n, cs):
-                m = min(cs, n - s0)
-                a, b = self.bufs[0][:m], self.bufs[1][:m]
-                self.first(x[s0:s0 + m], a, m, h, w, c, stream)
-                for conv in self.body[:-1]:
-                    conv(a, b, m, h, w, stream)
-                    a, b = b, a
-                self.body[-1](a, head[s0:s0 + m], m, h, w, stream)   # c8: n_tools channels (padded to a multiple of 8)
+            a, b, head = self.bufs
+            self.first(x, a, n, h, w, c, stream)
+            for conv in self.body[:-1]:
+                conv(a, b, n, h, w, stream)
+                a, b = b, a
+            self.body[-1](a, head, n, h, w, stream)                  # c8: n_tools channels (padded to a multiple of 8)
             tools = self.n_tools
             logits = head[:, 1:-1, 1:-1, :tools].float().reshape(n, h * w * tools)
             # the value branch: VALID convolutions over the interior of the zero-bordered c8 map (im2col with pad = -1)

@@ -4,8 +4,6 @@ from gym_pcgrl_b200.models import ActorCritic
 from gym_pcgrl_b200.policy_native import NativePolicy
 net = ActorCritic("FullyConvPolicyBigMap", (14, 14, 1), 392).cuda()
 pol = NativePolicy(net)
-import os
-if os.environ.get("CHUNK_MB"): pol.chunk_bytes = int(os.environ["CHUNK_MB"]) << 20
 obs = torch.randint(0, 2, (4096, 14, 14, 1), dtype=torch.uint8, device="cuda")
 for _ in range(3): pol(obs)
 torch.cuda.synchronize()

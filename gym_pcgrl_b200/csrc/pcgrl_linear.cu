@@ -265,12 +265,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
 // loaded once per CTA and stays in shared memory; the ring of stages carries A tiles only.  Same warp roles, pipelines and
 // TMEM double buffering as k_linear_bf16.
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int CONV_STAGES = 5;
+#ifndef CONV_ISSUERS
+#define CONV_ISSUERS 2 /* MMA-issuing warps = TMEM accumulator stages (tile lt -> issuer / stage lt % CONV_ISSUERS) */
+#endif
+// Shared-memory stages: every issuer owns a private ring of CONV_RING stages that the TMA producer fills with the loads of
+// that issuer's tiles only.  Each (producer, issuer) pair is then a single-producer / single-consumer ring, whose phase
+// parities cannot alias; with ONE ring shared by several issuers an issuer may have to wait for the second phase of a stage
+// whose first phase (another issuer's tile) has not completed yet, and mbarrier.try_wait.parity cannot tell "phase k + 1
+// pending" from "phase k - 1 done" (found with four issuers: launch failure; latent with two).
+#ifndef CONV_RING_STAGES
+#define CONV_RING_STAGES 3
+#endif
+constexpr int CONV_RING = CONV_RING_STAGES;
+constexpr int CONV_STAGES = CONV_ISSUERS * CONV_RING;
 constexpr int CONV_ROWS = BLOCK_M + 2;                       // rows m0 - 1 .. m0 + 128 of one filter row: the taps kx = 0, 1, 2
 constexpr int CONV_A_BYTES = ((CONV_ROWS * BLOCK_K * 2 + 1023) / 1024) * 1024;  // stage stride: 1024-byte aligned (17 KB)
 constexpr int CONV_A_TX = CONV_ROWS * BLOCK_K * 2;           // bytes one TMA box delivers
 // epilogue: BN / 32 groups of four warps (one warp per TMEM lane quarter and 32-column slice), 2 KB transpose buffer per warp
-template <int BN> __host__ __device__ constexpr int conv_threads() { return 96 + 128 * (BN / 32); }  // TMA, 2 x MMA, epilogue groups
+template <int BN> __host__ __device__ constexpr int conv_threads() { return 32 * (1 + CONV_ISSUERS) + 128 * (BN / 32); }  // TMA, MMA issuers, epilogue groups
 template <int BN> __host__ __device__ constexpr int conv_smem_bytes(int kblocks) {
   return kblocks * tile_b_bytes<BN>() + CONV_STAGES * CONV_A_BYTES + 1024 + 2048 + 4 * (BN / 32) * 2048;
 }
@@ -283,7 +295,9 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int TILE_B_BYTES = tile_b_bytes<BLOCK_N>();
-  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  constexpr uint32_t TMEM_COLS = CONV_ISSUERS * BLOCK_N;
+  constexpr int EPI0 = 1 + CONV_ISSUERS;  // first epilogue warp
+  static_assert(CONV_ISSUERS == 2 || CONV_ISSUERS == 4, "TMEM columns must be a power of two");
   const int cblocks = C / BLOCK_K, num_kb = 9 * cblocks;
   uint8_t* smem_b = smem;                                  // [num_kb] weight blocks, resident
   uint8_t* smem_a = smem + num_kb * TILE_B_BYTES;          // [CONV_STAGES] activation tiles of CONV_ROWS rows
@@ -291,10 +305,10 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
   uint64_t* full = bars;
   uint64_t* empty = bars + CONV_STAGES;
   uint64_t* tmem_full = bars + 2 * CONV_STAGES;
-  uint64_t* tmem_empty = bars + 2 * CONV_STAGES + 2;
-  uint64_t* b_full = bars + 2 * CONV_STAGES + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CONV_STAGES + 5);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * CONV_STAGES + 6);
+  uint64_t* tmem_empty = bars + 2 * CONV_STAGES + CONV_ISSUERS;
+  uint64_t* b_full = bars + 2 * CONV_STAGES + 2 * CONV_ISSUERS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CONV_STAGES + 2 * CONV_ISSUERS + 1);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * CONV_STAGES + 2 * CONV_ISSUERS + 2);
   uint4* xpose = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 2048);  // [epilogue warp][32 rows][4 chunks]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -305,7 +319,7 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < CONV_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * (BLOCK_N / 32)); }
+    for (int a = 0; a < CONV_ISSUERS; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128 * (BLOCK_N / 32)); }
     mbar_init(b_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -313,8 +327,8 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 96)
-    for (int c = threadIdx.x - 96; c < BLOCK_N; c += blockDim.x - 96) bias_s[c] = (bias && c < N) ? bias[c] : 0.0f;
+  if (threadIdx.x >= 32 * EPI0)
+    for (int c = threadIdx.x - 32 * EPI0; c < BLOCK_N; c += blockDim.x - 32 * EPI0) bias_s[c] = (bias && c < N) ? bias[c] : 0.0f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -325,38 +339,42 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
     if (lane == 0) {  // ===== TMA producer =====
       mbar_expect_tx(b_full, (uint32_t)(num_kb * TILE_B_BYTES));
       for (int kb = 0; kb < num_kb; kb++) tma_load_2d(smem_b + kb * TILE_B_BYTES, &map_w, b_full, kb * BLOCK_K, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int loads_per_tile = 3 * cblocks;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
         const int m0 = tile * BLOCK_M;
+        const int ring = (lt % CONV_ISSUERS) * CONV_RING;       // the ring of the issuer that owns this tile
+        int it = (lt / CONV_ISSUERS) * loads_per_tile;          // position in that ring's own load sequence
         for (int ky = 0; ky < 3; ky++)
           for (int cb = 0; cb < cblocks; cb++, it++) {
-            const int s = it % CONV_STAGES;
-            mbar_wait(&empty[s], ((it / CONV_STAGES) & 1) ^ 1);
+            const int s = ring + it % CONV_RING;
+            mbar_wait(&empty[s], ((it / CONV_RING) & 1) ^ 1);
             mbar_expect_tx(&full[s], CONV_A_TX);
             // rows m0 + (ky - 1) PW - 1 .. + 129: serves kx = 0, 1, 2 at row offsets 0, 1, 2; rows < 0 or >= Mp: zero fill
             tma_load_2d(smem_a + s * CONV_A_BYTES, &map_x, &full[s], cb * BLOCK_K, m0 + (ky - 1) * PW - 1);
           }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===== two MMA issuers: warp 1 drives the even tiles of this CTA (TMEM stage 0), warp 2 the odd ones (stage 1).  A
-    // 128 x 64 x 16 MMA lasts 32 cycles, less than one thread needs to issue it, so two threads issue into the tensor
-    // pipe; each shared-memory stage belongs to exactly one tile, hence to one issuer, and the ring order is unchanged.
+  } else if (warp < EPI0) {
+    // ===== CONV_ISSUERS MMA issuers: warp 1 + j drives the tiles lt = j (mod CONV_ISSUERS) of this CTA into TMEM stage j
+    // from its own ring of shared-memory stages.  A 128 x 64 x 16 MMA lasts 32 cycles, less than one thread needs to
+    // issue it, so two threads issue into the tensor pipe.
     if (lane == 0) {
       mbar_wait(b_full, 0);
       const int loads_per_tile = 3 * cblocks;
+      const int ring = (warp - 1) * CONV_RING;
       int lt = warp - 1;
-      for (int tile = blockIdx.x + (warp - 1) * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, lt += 2) {
-        int it = lt * loads_per_tile;
-        const int as = lt & 1;
-        mbar_wait(&tmem_empty[as], ((lt >> 1) & 1) ^ 1);
+      for (int tile = blockIdx.x + (warp - 1) * gridDim.x; tile < num_tiles; tile += CONV_ISSUERS * gridDim.x, lt += CONV_ISSUERS) {
+        int it = (lt / CONV_ISSUERS) * loads_per_tile;
+        const int as = lt % CONV_ISSUERS;
+        mbar_wait(&tmem_empty[as], ((lt / CONV_ISSUERS) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
         uint32_t first = 0u;  // the first MMA of a tile overwrites the accumulator
         for (int ky = 0; ky < 3; ky++)
           for (int cb = 0; cb < cblocks; cb++, it++) {
-            const int s = it % CONV_STAGES;
-            mbar_wait(&full[s], (it / CONV_STAGES) & 1);
+            const int s = ring + it % CONV_RING;
+            mbar_wait(&full[s], (it / CONV_RING) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t da0 = umma_smem_desc(smem_a + s * CONV_A_BYTES);            // kx = 1, 2: + 8, + 16 (one row = 128 B)
             const uint64_t db0 = umma_smem_desc(smem_b + (ky * 3 * cblocks + cb) * TILE_B_BYTES);
@@ -375,15 +393,15 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
       }
     }
   } else {  // ===== epilogue: TMEM -> bias + ReLU, zero at border positions -> bf16 NHWC =====
-    // warp (3 + 4 g + q') owns TMEM lanes of quarter (warp & 3) and the 32 accumulator columns [32 g, 32 g + 32): one
+    // warp (EPI0 + 4 g + q') owns TMEM lanes of quarter (warp & 3) and the 32 accumulator columns [32 g, 32 g + 32): one
     // tcgen05.ld per tile, packed to bf16 by the row's thread, transposed through 2 KB of shared memory so that the global
     // stores are 64-byte row segments (four lanes per row) instead of one 16-byte piece per row and instruction.
-    const int quarter = warp & 3, c0 = ((warp - 3) >> 2) * 32;
-    uint4* xp = xpose + (warp - 3) * 128;
+    const int quarter = warp & 3, c0 = ((warp - EPI0) >> 2) * 32;
+    uint4* xp = xpose + (warp - EPI0) * 128;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
-      const int m0 = tile * BLOCK_M, as = lt & 1;
-      mbar_wait(&tmem_full[as], (lt >> 1) & 1);
+      const int m0 = tile * BLOCK_M, as = lt % CONV_ISSUERS;
+      mbar_wait(&tmem_full[as], (lt / CONV_ISSUERS) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + quarter * 32 + lane;
       const int px = row % PW, py = (row / PW) % PH;

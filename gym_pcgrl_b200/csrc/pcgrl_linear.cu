@@ -89,6 +89,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on `bar
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Warp-convergent forms (all 32 lanes execute them, elect.sync picks the issuing lane inside the PTX block): in a branch
+// on `lane == 0` the compiler wraps every UTCHMMA in an elect / branch loop of its own.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -151,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer: one thread drives the tensor core for the CTA =====
+    {  // ===== MMA issuer: the warp runs the loop convergently, elect.sync picks the lane that drives the tensor core =====
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
         const int as = lt & 1;
@@ -165,10 +184,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_linear_bf16(const __grid_constan
           const uint64_t da = umma_smem_desc(smem_a + s * TILE_A_BYTES), db = umma_smem_desc(smem_b + s * TILE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), instr_desc<BLOCK_N>(), (kb | k) ? 1u : 0u);
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+            umma_f16_elect(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), instr_desc<BLOCK_N>(), (kb | k) ? 1u : 0u);
+          umma_commit_elect(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&tmem_full[as]);  // accumulator of this tile complete
+        umma_commit_elect(&tmem_full[as]);  // accumulator of this tile complete
       }
     }
   } else {  // ===== epilogue (warps 2-5): TMEM -> registers -> bias + ReLU -> global =====
@@ -359,12 +378,13 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
     // ===== CONV_ISSUERS MMA issuers: warp 1 + j drives the tiles lt = j (mod CONV_ISSUERS) of this CTA into TMEM stage j
     // from its own ring of shared-memory stages.  A 128 x 64 x 16 MMA lasts 32 cycles, less than one thread needs to
     // issue it, so two threads issue into the tensor pipe.
-    if (lane == 0) {
+    {  // the whole warp runs the loop (convergent); elect.sync inside the MMA / commit helpers picks the issuing lane
       mbar_wait(b_full, 0);
       const int loads_per_tile = 3 * cblocks;
-      const int ring = (warp - 1) * CONV_RING;
-      int lt = warp - 1;
-      for (int tile = blockIdx.x + (warp - 1) * gridDim.x; tile < num_tiles; tile += CONV_ISSUERS * gridDim.x, lt += CONV_ISSUERS) {
+      const int issuer = __shfl_sync(0xffffffffu, warp - 1, 0);  // broadcast: loop state and descriptors stay in uniform registers
+      const int ring = issuer * CONV_RING;
+      int lt = issuer;
+      for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += CONV_ISSUERS * gridDim.x, lt += CONV_ISSUERS) {
         int it = (lt / CONV_ISSUERS) * loads_per_tile;
         const int as = lt % CONV_ISSUERS;
         mbar_wait(&tmem_empty[as], ((lt / CONV_ISSUERS) & 1) ^ 1);
@@ -382,14 +402,14 @@ __global__ void __launch_bounds__(conv_threads<BLOCK_N>(), 1) k_conv3x3_bf16(con
             for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-                umma_f16(tmem_d, da0 + (uint64_t)(8 * kx + 2 * k), db0 + (uint64_t)(kx * cblocks * (TILE_B_BYTES >> 4) + 2 * k),
+                umma_f16_elect(tmem_d, da0 + (uint64_t)(8 * kx + 2 * k), db0 + (uint64_t)(kx * cblocks * (TILE_B_BYTES >> 4) + 2 * k),
                          instr_desc<BLOCK_N>(), first);
                 first = 1u;
               }
             }
-            umma_commit(&empty[s]);
+            umma_commit_elect(&empty[s]);
           }
-        umma_commit(&tmem_full[as]);
+        umma_commit_elect(&tmem_full[as]);
       }
     }
   } else {  // ===== epilogue: TMEM -> bias + ReLU, zero at border positions -> bf16 NHWC =====

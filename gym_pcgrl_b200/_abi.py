@@ -18,6 +18,7 @@ FLAG_RANDOM_START = 4
 FLAG_RANDOM_PROBS = 8
 FLAG_AUTO_RESET = 16
 FLAG_HEAT_U16 = 32
+FLAG_FULL_STATS = 64
 
 PROBLEM_IDS = {"binary": PROB_BINARY, "zelda": PROB_ZELDA, "sokoban": PROB_SOKOBAN,
                "ddave": PROB_DDAVE, "mdungeon": PROB_MDUNGEON, "smb": PROB_SMB}

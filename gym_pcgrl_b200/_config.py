@@ -1,5 +1,7 @@
 """Freeze Problem / Representation parameters into the POD ``pcgrl_config`` block
 (include/pcgrl_b200.h) that is passed by value to every native call."""
+import os
+
 from . import _abi
 
 
@@ -18,6 +20,8 @@ def build_config(prob, rep, max_changes, max_iterations, auto_reset=True):
         flags |= _abi.FLAG_AUTO_RESET
     if int(max_changes) > 255:   # a heat-map cell can count up to max_changes edits (pcgrl_env.py:137)
         flags |= _abi.FLAG_HEAT_U16
+    if os.environ.get("PCGRL_FULL_STATS", "0") == "1":   # A/B switch: binary rollouts without the incremental statistics
+        flags |= _abi.FLAG_FULL_STATS
     cfg.flags = flags
     cfg.solver_power = p["solver_power"]
     for i, v in enumerate(p["iparam"]):

@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   bool prof_reset = false, prof_changed = false;
 #endif
 
+  // binary: cells of components known to hold the longest path (binary_stats_update); nothing known at launch
+  uint32_t best_cells = 0u;
+  const bool incremental = T > 1 && (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
   // one 32-bit row offset (t * n + e) is the only loop-carried index (rollout_dispatch checks T * n * adim < 2^31)
   uint32_t row = (uint32_t)e;
   for (int t = 0; t < T; t++, row += (uint32_t)n) {
@@ -100,14 +103,21 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     int old[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];
-    int hx, hy, cell, tile;
+    int hx, hy, cell, tile, ex, ey;
     bool multi;
-    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi);
+    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
     KP();
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
-      bool unused;
-      map_stats<PROB>(board, cfg, lane, st, unused);
+      if constexpr (PROB == PCGRL_PROB_BINARY) {
+        // binary_prob.py:81-86 after a single-cell edit: only the components next to the cell are re-measured
+        const uint32_t pass = type_mask<0x01u>(board, row_mask(W, H, lane));
+        if (!multi && incremental) binary_stats_update(pass, cell_bit(ey, ex, lane), tile == 0, lane, st[0], st[1], best_cells);
+        else regions_and_longest_path(pass, lane, st[0], st[1], best_cells);
+      } else {
+        bool unused;
+        map_stats<PROB>(board, cfg, lane, st, unused);
+      }
     }
     KP();
 #ifdef PCGRL_PROFILE
@@ -135,6 +145,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
       iteration = 0;
       changes = 0;
+      best_cells = 0u;
 #ifdef PCGRL_PROFILE
       prof_reset = true;
 #endif

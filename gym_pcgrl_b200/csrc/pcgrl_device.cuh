@@ -406,7 +406,10 @@ __device__ __forceinline__ int count_regions(uint32_t pass, int lane) {
 // single-cell components contribute 0 and two-cell components contribute 1 (both found for the whole map at
 // once from neighbour-count boards); a component whose first sweep has eccentricity d1 has diameter <= 2*d1,
 // so its second sweep is skipped when 2*d1 <= best.
-__device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane, int& regions_out, int& path_out) {
+// `best_cells` (optional by-product): cells of components whose double-sweep value is known to EQUAL path_out -- a subset
+// (components skipped by the 2*d1 <= best shortcut are left out even when they tie), possibly empty.
+__device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane, int& regions_out, int& path_out,
+                                                         uint32_t& best_cells) {
   // neighbour-presence boards: has a passable neighbour to the left / right / above / below
   uint32_t up = __shfl_up_sync(FULL_MASK, pass, 1), dn = __shfl_down_sync(FULL_MASK, pass, 1);
   if (lane == 0) up = 0;
@@ -425,6 +428,7 @@ __device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane
   const uint32_t dominoes = hd | (hd << 1) | vd | vd_low;
   const int ndom = popc_all(hd) + popc_all(vd);
   int regions = popc_all(iso) + ndom, best = ndom > 0 ? 1 : 0;
+  uint32_t bm = ndom > 0 ? dominoes : iso;
   uint32_t remaining = pass & ~iso & ~dominoes;
   uint32_t seed;
   while (first_cell_seed(remaining, lane, seed)) {
@@ -436,11 +440,82 @@ __device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane
       first_cell_seed(last, lane, seed);
       uint32_t v2, l2;
       const int d2 = bfs_ecc(seed, visited, v2, l2);
-      best = max(best, d2);
+      if (d2 > best) { best = d2; bm = visited; }
+      else if (d2 == best) bm |= visited;
     }
   }
   regions_out = regions;
   path_out = best;
+  best_cells = bm;
+}
+__device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane, int& regions_out, int& path_out) {
+  uint32_t unused;
+  regions_and_longest_path(pass, lane, regions_out, path_out, unused);
+}
+
+// Incremental form of the two binary statistics after ONE cell `cb` (a one-bit board) of the passable board changed
+// (`pass` is the board AFTER the edit; grew = the cell became passable).  Exact, because both statistics are functions
+// of the components alone: regions is their number and calc_longest_path (G/helper.py:250-264) is a maximum over
+// components of a value -- sweep from the component's row-major-first cell, sweep from the row-major-first farthest
+// cell -- that depends on nothing but the component's own cells.  An edit touches only the components next to the
+// cell: with P0 = the board without the cell, the `pieces` are the components of P0 that hold one of the cell's (at
+// most four) passable neighbours; a grow event replaces the pieces by their union plus the cell, a shrink event
+// replaces that union by the pieces.  Carried between calls: regions, best and `bm`, a (possibly empty) set of cells of
+// components whose value is known to equal best.  The maximum over the untouched components is known to be `best`
+// when an untouched component is in bm or when no touched old component is large enough to reach best (a component of
+// s cells has value <= s - 1); otherwise it is only known to be <= best, which still decides the new maximum whenever
+// a new component reaches best.  In the remaining case the whole board is recomputed.
+__device__ __forceinline__ void binary_stats_update(uint32_t pass, uint32_t cb, bool grew, int lane, int& regions, int& best,
+                                                    uint32_t& bm) {
+  const uint32_t p0 = pass & ~cb;
+  uint32_t nb = neighbours(cb, lane) & p0;
+  uint32_t piece[4] = {0u, 0u, 0u, 0u};
+  uint32_t touched = 0u;
+  int m = 0, max_piece = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    uint32_t seed;
+    if (first_cell_seed(nb, lane, seed)) {  // warp-uniform
+      piece[k] = flood(seed, p0);
+      nb &= ~piece[k];
+      touched |= piece[k];
+      max_piece = max(max_piece, popc_all(piece[k]));
+      m++;
+    }
+  }
+  regions += grew ? 1 - m : m - 1;
+  const int touched_cells = grew ? max_piece : popc_all(touched) + 1;  // the largest touched OLD component
+  const uint32_t old_cells = grew ? touched : (touched | cb);
+  const uint32_t keep = bm & ~old_cells;
+  const bool rest_is_best = __any_sync(FULL_MASK, keep != 0u) || touched_cells - 1 < best;
+  int cur = rest_is_best ? best : best - 1;  // a new component matters only if its value exceeds cur
+  uint32_t cur_cells = 0u;
+  if (grew) { piece[0] = touched | cb; m = 1; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (k < m) {  // warp-uniform
+      const uint32_t comp = piece[k];
+      if (popc_all(comp) - 1 > cur) {
+        uint32_t seed, visited, last;
+        first_cell_seed(comp, lane, seed);
+        const int d1 = bfs_ecc(seed, comp, visited, last);
+        if (2 * d1 > cur) {
+          first_cell_seed(last, lane, seed);
+          uint32_t v2, l2;
+          const int d2 = bfs_ecc(seed, comp, v2, l2);
+          if (d2 > cur) { cur = d2; cur_cells = comp; }
+          else if (d2 == cur) cur_cells |= comp;
+        }
+      }
+    }
+  }
+  if (cur >= best) {
+    bm = ((cur == best) ? keep : 0u) | cur_cells;
+    best = cur;
+  } else {  // the maximum sat in a touched component and no new component reaches it
+    int r2;
+    regions_and_longest_path(pass, lane, r2, best, bm);
+  }
 }
 
 // G/helper.py:37-62 get_floor_dist(map, from, floor): sum over `from` cells of the number of cells strictly

@@ -908,3 +908,52 @@ def test_plugin_path_builtin_problem_with_user_representation():
         old_d = {k: torch.from_numpy(prev_stats[:, i]) for i, k in enumerate(names)}
         np.testing.assert_array_equal(t2n(reward), env._prob.get_reward(new_d, old_d).numpy(), err_msg="reward %d" % t)
         prev_stats = want
+
+
+INCREMENTAL_CASES = [
+    # (env id, kwargs, n envs, steps per launch, launches): long fused rollouts, where the binary statistics are updated
+    # incrementally after single-cell edits (pcgrl_device.cuh binary_stats_update) -- dense, sparse and tiny maps
+    ("binary-narrow-v0", dict(width=16, height=16, change_percentage=0.6), 512, 150, 2),
+    ("binary-wide-v0", dict(width=16, height=16, change_percentage=1.0, probs={"empty": 0.85, "solid": 0.15}, random_probs=False), 256, 128, 2),
+    ("binary-turtle-v0", dict(width=14, height=14, change_percentage=1.0, probs={"empty": 0.3, "solid": 0.7}, random_probs=False), 256, 200, 1),
+    ("binary-wide-v0", dict(width=32, height=32, change_percentage=0.2), 96, 160, 1),
+    ("binary-narrow-v0", dict(width=32, height=9, change_percentage=1.0, probs={"empty": 0.7, "solid": 0.3}, random_probs=False), 128, 200, 1),
+    ("binary-wide-v0", dict(width=3, height=3, change_percentage=1.0), 128, 60, 2),
+    ("binary-wide-v0", dict(width=1, height=6, change_percentage=1.0), 64, 40, 1),
+    ("binary-wide-v0", dict(width=7, height=1, change_percentage=1.0), 64, 40, 1),
+]
+
+
+@pytest.mark.parametrize("case", INCREMENTAL_CASES, ids=["%s-%d" % (c[0], i) for i, c in enumerate(INCREMENTAL_CASES)])
+def test_incremental_binary_statistics_match_oracle(case, monkeypatch):
+    """regions / path-length maintained incrementally inside a fused rollout == the oracle's full recomputation at every
+    step (reward is a function of both), and == the same launch with PCGRL_FLAG_FULL_STATS."""
+    import torch
+    env_id, kwargs, n, T, launches = case
+    states = np.stack([util.randomstate_words(31_000 + i) for i in range(n)])
+    env = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
+    assert not (env.native_config.flags & _abi.FLAG_FULL_STATS)
+    monkeypatch.setenv("PCGRL_FULL_STATS", "1")
+    env_full = util.host_env(env_id, kwargs, num_envs=n, device="cuda")
+    assert env_full.native_config.flags & _abi.FLAG_FULL_STATS
+    ref = oracle.OracleEnv(env.native_config, n, threads=8)
+    for e in (env, env_full, ref):
+        e.set_rng_states(states)
+        e.reset()
+    arng = np.random.RandomState(77)
+    for launch in range(launches):
+        acts = np.stack([random_actions(env, arng, n) for _ in range(T)])
+        rew, done = env.rollout(torch.from_numpy(acts).cuda())
+        rew_f, done_f = env_full.rollout(torch.from_numpy(acts).cuda())
+        assert torch.equal(rew, rew_f) and torch.equal(done, done_f)
+        for k in range(T):
+            ref.step(acts[k])
+            ctx = "%s launch %d step %d" % (env_id, launch, k)
+            np.testing.assert_array_equal(t2n(rew[k]), ref["reward"], err_msg=ctx + " reward")
+            np.testing.assert_array_equal(t2n(done[k]).astype(np.uint8), ref["done"], err_msg=ctx + " done")
+        for key in ("map", "stats", "start_stats", "changes", "iteration"):
+            assert torch.equal(env._tens[key], env_full._tens[key]), key
+        np.testing.assert_array_equal(t2n(env._tens["map"]), ref["map"])
+        np.testing.assert_array_equal(t2n(env._tens["stats"])[:, :2], ref["stats"][:, :2])
+        np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"])
+    env.check_status()

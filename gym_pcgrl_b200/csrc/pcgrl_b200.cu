@@ -1,7 +1,7 @@
 // pcgrl_b200.cu -- kernels + C ABI (include/pcgrl_b200.h) of the batched PcgrlEnv hot path, sm_100a.
 //
 // Kernels (one warp per environment, 4 warps per CTA):
-//   k_rollout<PROB>     fused PcgrlEnv.step x T for the graph-only problems (binary, zelda):
+//   k_rollout<PROB, REP> fused PcgrlEnv.step x T for the graph-only problems (binary, zelda):
 //                       Representation.update -> get_stats -> get_reward/get_episode_over -> auto reset
 //   k_reset<PROB>       PcgrlEnv.reset
 //   k_get_stats<PROB>   stand-alone Problem.get_stats operator
@@ -47,7 +47,8 @@ __device__ __forceinline__ void store_info_counters(int32_t* info_row, int itera
 
 #include "pcgrl_packed.cuh"
 
-template <int PROB>
+// REPT >= 0: the representation is a compile-time constant (narrow / turtle / wide); REPT = -1: read from the config.
+template <int PROB, int REPT>
 __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__ pcgrl_config cfg,
                                                       const __grid_constant__ pcgrl_buffers b,
                                                       const int32_t* __restrict__ actions, double* reward_out,
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   if (e >= n) return;
   WarpSmem& sm = smem[wib];
   const int W = cfg.width, H = cfg.height, cells = W * H;
-  const int adim = action_dim(cfg.representation);
+  const int rep = (REPT >= 0) ? REPT : cfg.representation;
+  const int adim = action_dim(rep);
   const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
   const EnvRefs r = env_refs(cfg, b, e);
 
@@ -72,9 +74,9 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   KP();
   // all prologue loads are independent: issue them before the ballots of load_board serialise the warp
   WarpRng rng;
-  rng.init(r.rng_rep, (cfg.representation == PCGRL_REP_NARROW || cfg.representation >= PCGRL_REP_NARROWCAST) ? lane : -1);
+  rng.init(r.rng_rep, (rep == PCGRL_REP_NARROW || rep >= PCGRL_REP_NARROWCAST) ? lane : -1);
   int x = 0, y = 0;
-  if (cfg.representation != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
+  if (rep != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
   int iteration = b.iteration[e], changes = b.changes[e];
   int st[NS], start[NS];
   load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
@@ -90,22 +92,24 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   // binary: cells of components known to hold the longest path (binary_stats_update); nothing known at launch
   uint32_t best_cells = 0u;
   const bool incremental = T > 1 && (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
-  // one 32-bit row offset (t * n + e) is the only loop-carried index (rollout_dispatch checks T * n * adim < 2^31)
-  uint32_t row = (uint32_t)e;
-  for (int t = 0; t < T; t++, row += (uint32_t)n) {
-    const int32_t* act = actions + (size_t)(row * (uint32_t)adim);
+  // loop-carried row pointers (step t, env e) instead of index arithmetic per step
+  const int32_t* act = actions + (size_t)e * adim;
+  const size_t act_step = (size_t)n * adim;
+  double* rw = reward_out ? reward_out + e : nullptr;
+  uint8_t* dn = done_out ? done_out + e : nullptr;
+  for (int t = 0; t < T; t++, act += act_step) {
     if (t + 2 < T)  // the action rows of the next steps are independent of the state: pull them towards L1 now
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)((row + 2u * (uint32_t)n) * (uint32_t)adim)));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(act + 2 * act_step));
     iteration++;  // pcgrl_env.py:130
     // this step can end the episode through the change / iteration limits: start pulling what the reset will read
-    if (auto_reset && (changes + max_change_per_step(cfg.representation) >= cfg.max_changes || iteration >= cfg.max_iterations))
+    if (auto_reset && (changes + max_change_per_step(rep) >= cfg.max_changes || iteration >= cfg.max_iterations))
       prefetch_reset_inputs(r, lane);
     int old[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];
     int hx, hy, cell, tile, ex, ey;
     bool multi;
-    const int change = apply_action(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
+    const int change = apply_action<REPT>(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
     KP();
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
@@ -127,10 +131,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     const double reward = (change > 0) ? problem_reward<PROB>(cfg, st, old) : 0.0;  // :142 (get_reward(s, s) == 0)
     const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
                       iteration >= cfg.max_iterations;                            // :143
-    if (lane == 0) {
-      if (reward_out) reward_out[row] = reward;
-      if (done_out) done_out[row] = done ? 1 : 0;
-    }
+    if (rw) { if (lane == 0) *rw = reward; rw += n; }
+    if (dn) { if (lane == 0) *dn = done ? 1 : 0; dn += n; }
     if (t == T - 1) {  // the env's own reward / done / info buffers describe the last step only
       if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
       store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   }
   rng.finish(lane);
   if (lane == 0) {
-    if (cfg.representation != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
+    if (rep != PCGRL_REP_WIDE) { b.pos[2 * e] = (uint8_t)x; b.pos[2 * e + 1] = (uint8_t)y; }
     b.iteration[e] = iteration;
     b.changes[e] = changes;
   }
@@ -917,7 +919,12 @@ static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
       return cuda_rc(cudaGetLastError(), "pcgrl_rollout (packed) launch");
     }
   }
-  k_rollout<PROB><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg);
+  switch (cfg->representation) {  // the three base representations get their own instantiation
+    case PCGRL_REP_NARROW: k_rollout<PROB, PCGRL_REP_NARROW><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg); break;
+    case PCGRL_REP_TURTLE: k_rollout<PROB, PCGRL_REP_TURTLE><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg); break;
+    case PCGRL_REP_WIDE: k_rollout<PROB, PCGRL_REP_WIDE><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg); break;
+    default: k_rollout<PROB, -1><<<env_grid(n), 32 * WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n, sg); break;
+  }
   return cuda_rc(cudaGetLastError(), "pcgrl_step launch");
 }
 

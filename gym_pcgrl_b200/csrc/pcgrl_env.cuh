@@ -77,11 +77,13 @@ __device__ __forceinline__ int apply_stamp(const pcgrl_config& cfg, Board& board
 // (narrow_rep.py:99-114: the cursor AFTER it moved; turtle_rep.py:101-129; wide_rep.py:67-70; the cast / multi
 // variants stamp a 3x3 block).  Changed tiles are written to the uint8 map in HBM and to the bitboards.
 // cell/tile describe a single-cell edit (delta transport); multi is set when more than one cell may have changed.
-// (ex, ey) = the edited cell of a single-cell edit (cell = ey * W + ex).
+// (ex, ey) = the edited cell of a single-cell edit (cell = ey * W + ex).  REPT >= 0 fixes the representation at compile
+// time (the branch chain below folds away); REPT = -1 reads it from the config.
+template <int REPT = -1>
 __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32_t* __restrict__ act, Board& board,
                                             uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy,
                                             int& cell, int& tile, bool& multi, int& ex, int& ey) {
-  const int W = cfg.width, H = cfg.height, rep = cfg.representation;
+  const int W = cfg.width, H = cfg.height, rep = (REPT >= 0) ? REPT : cfg.representation;
   int change = 0, wx = x, wy = y, newt = -1;
   multi = false;
   if (rep == PCGRL_REP_NARROW) {
@@ -151,7 +153,7 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
                                             uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy,
                                             int& cell, int& tile, bool& multi) {
   int ex, ey;
-  return apply_action(cfg, act, board, map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
+  return apply_action<-1>(cfg, act, board, map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
 }
 
 // _heatmap[y][x] += 1 (pcgrl_env.py:137) as a fire-and-forget 32-bit reduction on the containing word

@@ -116,8 +116,11 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       if constexpr (PROB == PCGRL_PROB_BINARY) {
         // binary_prob.py:81-86 after a single-cell edit: only the components next to the cell are re-measured
         const uint32_t pass = type_mask<0x01u>(board, row_mask(W, H, lane));
-        if (!multi && incremental) binary_stats_update(pass, cell_bit(ey, ex, lane), tile == 0, lane, st[0], st[1], best_cells);
-        else regions_and_longest_path(pass, lane, st[0], st[1], best_cells);
+        if (!multi && incremental) binary_stats_update(pass, cell_bit(ey, ex, lane), tile == 0, lane, st[0], st[1], best_cells, sm.draws);
+        else if (T > 1) {  // multi-cell edit (or the A/B switch) inside a fused rollout: shared out-of-line copy
+          const uint3 full = regions_and_longest_path_call(pass, lane);
+          st[0] = (int)full.x; st[1] = (int)full.y; best_cells = full.z;
+        } else regions_and_longest_path(pass, lane, st[0], st[1], best_cells);  // single step: inline, latency first
       } else {
         bool unused;
         map_stats<PROB>(board, cfg, lane, st, unused);

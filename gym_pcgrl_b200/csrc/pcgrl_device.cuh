@@ -453,6 +453,22 @@ __device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane
   regions_and_longest_path(pass, lane, regions_out, path_out, unused);
 }
 
+// Out-of-line copies of the two sweeps (results in registers): binary_stats_update calls them from rolled loops so that
+// the hot loop of k_rollout stays small (instruction-cache misses were 24 % of its stall samples when every call site
+// carried its own unrolled copy).
+__device__ __noinline__ uint3 bfs_ecc_call(uint32_t seed, uint32_t pass) {
+  uint32_t visited, last;
+  const int d = bfs_ecc(seed, pass, visited, last);
+  return make_uint3((uint32_t)d, visited, last);
+}
+__device__ __noinline__ uint32_t flood_call(uint32_t seed, uint32_t pass) { return flood(seed, pass); }
+__device__ __noinline__ uint3 regions_and_longest_path_call(uint32_t pass, int lane) {  // (regions, path, best_cells)
+  int regions, path;
+  uint32_t bm;
+  regions_and_longest_path(pass, lane, regions, path, bm);
+  return make_uint3((uint32_t)regions, (uint32_t)path, bm);
+}
+
 // Incremental form of the two binary statistics after ONE cell `cb` (a one-bit board) of the passable board changed
 // (`pass` is the board AFTER the edit; grew = the cell became passable).  Exact, because both statistics are functions
 // of the components alone: regions is their number and calc_longest_path (G/helper.py:250-264) is a maximum over
@@ -466,22 +482,20 @@ __device__ __forceinline__ void regions_and_longest_path(uint32_t pass, int lane
 // s cells has value <= s - 1); otherwise it is only known to be <= best, which still decides the new maximum whenever
 // a new component reaches best.  In the remaining case the whole board is recomputed.
 __device__ __forceinline__ void binary_stats_update(uint32_t pass, uint32_t cb, bool grew, int lane, int& regions, int& best,
-                                                    uint32_t& bm) {
+                                                    uint32_t& bm, uint32_t* piece_smem) {
+  // piece_smem: 4 x 32 words of per-warp shared memory (piece k, row = lane)
   const uint32_t p0 = pass & ~cb;
   uint32_t nb = neighbours(cb, lane) & p0;
-  uint32_t piece[4] = {0u, 0u, 0u, 0u};
-  uint32_t touched = 0u;
+  uint32_t touched = 0u, seed;
   int m = 0, max_piece = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    uint32_t seed;
-    if (first_cell_seed(nb, lane, seed)) {  // warp-uniform
-      piece[k] = flood(seed, p0);
-      nb &= ~piece[k];
-      touched |= piece[k];
-      max_piece = max(max_piece, popc_all(piece[k]));
-      m++;
-    }
+#pragma unroll 1
+  while (first_cell_seed(nb, lane, seed)) {  // at most four rounds, warp-uniform
+    const uint32_t piece = flood_call(seed, p0);
+    piece_smem[m * 32 + lane] = piece;
+    nb &= ~piece;
+    touched |= piece;
+    max_piece = max(max_piece, popc_all(piece));
+    m++;
   }
   regions += grew ? 1 - m : m - 1;
   const int touched_cells = grew ? max_piece : popc_all(touched) + 1;  // the largest touched OLD component
@@ -490,22 +504,18 @@ __device__ __forceinline__ void binary_stats_update(uint32_t pass, uint32_t cb, 
   const bool rest_is_best = __any_sync(FULL_MASK, keep != 0u) || touched_cells - 1 < best;
   int cur = rest_is_best ? best : best - 1;  // a new component matters only if its value exceeds cur
   uint32_t cur_cells = 0u;
-  if (grew) { piece[0] = touched | cb; m = 1; }
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (k < m) {  // warp-uniform
-      const uint32_t comp = piece[k];
-      if (popc_all(comp) - 1 > cur) {
-        uint32_t seed, visited, last;
-        first_cell_seed(comp, lane, seed);
-        const int d1 = bfs_ecc(seed, comp, visited, last);
-        if (2 * d1 > cur) {
-          first_cell_seed(last, lane, seed);
-          uint32_t v2, l2;
-          const int d2 = bfs_ecc(seed, comp, v2, l2);
-          if (d2 > cur) { cur = d2; cur_cells = comp; }
-          else if (d2 == cur) cur_cells |= comp;
-        }
+  if (grew) { piece_smem[lane] = touched | cb; m = 1; }
+#pragma unroll 1
+  for (int k = 0; k < m; k++) {
+    const uint32_t comp = piece_smem[k * 32 + lane];
+    if (popc_all(comp) - 1 > cur) {
+      first_cell_seed(comp, lane, seed);
+      const uint3 s1 = bfs_ecc_call(seed, comp);  // (d1, visited, last)
+      if (2 * (int)s1.x > cur) {
+        first_cell_seed(s1.z, lane, seed);
+        const int d2 = (int)bfs_ecc_call(seed, comp).x;
+        if (d2 > cur) { cur = d2; cur_cells = comp; }
+        else if (d2 == cur) cur_cells |= comp;
       }
     }
   }
@@ -513,8 +523,9 @@ __device__ __forceinline__ void binary_stats_update(uint32_t pass, uint32_t cb, 
     bm = ((cur == best) ? keep : 0u) | cur_cells;
     best = cur;
   } else {  // the maximum sat in a touched component and no new component reaches it
-    int r2;
-    regions_and_longest_path(pass, lane, r2, best, bm);
+    const uint3 full = regions_and_longest_path_call(pass, lane);
+    best = (int)full.y;
+    bm = full.z;
   }
 }
 

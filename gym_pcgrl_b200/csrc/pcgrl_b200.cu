@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   const int rep = (REPT >= 0) ? REPT : cfg.representation;
   const int adim = action_dim(rep);
   const bool auto_reset = (cfg.flags & PCGRL_FLAG_AUTO_RESET) != 0;
-  const EnvRefs r = env_refs(cfg, b, e);
+  // the only per-env pointer that stays live across the step loop (the others are rebuilt where a reset needs them)
+  uint8_t* const env_map = b.map + (size_t)e * cells;
 
 #ifdef PCGRL_PROFILE
   long long kp[6]; int nkp = 0;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   KP();
   // all prologue loads are independent: issue them before the ballots of load_board serialise the warp
   WarpRng rng;
-  rng.init(r.rng_rep, (rep == PCGRL_REP_NARROW || rep >= PCGRL_REP_NARROWCAST) ? lane : -1);
+  rng.init(b.rng + (size_t)e * 2 * PCGRL_MT_WORDS, (rep == PCGRL_REP_NARROW || rep >= PCGRL_REP_NARROWCAST) ? lane : -1);
   int x = 0, y = 0;
   if (rep != PCGRL_REP_WIDE) { x = b.pos[2 * e]; y = b.pos[2 * e + 1]; }
   int iteration = b.iteration[e], changes = b.changes[e];
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
   // first step's action: pull its line into L1 now so the load in apply_action does not add a round trip
   asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)e * adim));
-  Board board = load_board<NP>(r.map, W, H, lane, sm.bits);
+  Board board = load_board<NP>(env_map, W, H, lane, sm.bits);
   KP();
 #ifdef PCGRL_PROFILE
   bool prof_reset = false, prof_changed = false;
@@ -92,24 +93,23 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   // binary: cells of components known to hold the longest path (binary_stats_update); nothing known at launch
   uint32_t best_cells = 0u;
   const bool incremental = T > 1 && (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
-  // loop-carried row pointers (step t, env e) instead of index arithmetic per step
-  const int32_t* act = actions + (size_t)e * adim;
-  const size_t act_step = (size_t)n * adim;
-  double* rw = reward_out ? reward_out + e : nullptr;
-  uint8_t* dn = done_out ? done_out + e : nullptr;
-  for (int t = 0; t < T; t++, act += act_step) {
+  // one 32-bit row offset (t * n + e) is the only loop-carried index (rollout_dispatch checks T * n * adim < 2^31): the
+  // base pointers are kernel parameters (constant bank operands), loop-carried 64-bit pointers were measured to spill
+  uint32_t row = (uint32_t)e;
+  for (int t = 0; t < T; t++, row += (uint32_t)n) {
+    const int32_t* act = actions + (size_t)(row * (uint32_t)adim);
     if (t + 2 < T)  // the action rows of the next steps are independent of the state: pull them towards L1 now
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(act + 2 * act_step));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)((row + 2u * (uint32_t)n) * (uint32_t)adim)));
     iteration++;  // pcgrl_env.py:130
     // this step can end the episode through the change / iteration limits: start pulling what the reset will read
     if (auto_reset && (changes + max_change_per_step(rep) >= cfg.max_changes || iteration >= cfg.max_iterations))
-      prefetch_reset_inputs(r, lane);
+      prefetch_reset_inputs(env_refs(cfg, b, e), lane);
     int old[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];
     int hx, hy, cell, tile, ex, ey;
     bool multi;
-    const int change = apply_action<REPT>(cfg, act, board, r.map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
+    const int change = apply_action<REPT>(cfg, act, board, env_map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
     KP();
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
@@ -134,8 +134,10 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     const double reward = (change > 0) ? problem_reward<PROB>(cfg, st, old) : 0.0;  // :142 (get_reward(s, s) == 0)
     const bool done = problem_over<PROB>(cfg, st, start) || changes >= cfg.max_changes ||
                       iteration >= cfg.max_iterations;                            // :143
-    if (rw) { if (lane == 0) *rw = reward; rw += n; }
-    if (dn) { if (lane == 0) *dn = done ? 1 : 0; dn += n; }
+    if (lane == 0) {
+      if (reward_out) reward_out[row] = reward;
+      if (done_out) done_out[row] = done ? 1 : 0;
+    }
     if (t == T - 1) {  // the env's own reward / done / info buffers describe the last step only
       if (lane == 0) { b.reward[e] = reward; b.done[e] = done ? 1 : 0; }
       store_row<NS>(b.info_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
 #ifdef PCGRL_PROFILE
       prof_reset = true;
 #endif
-      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, r.map);
+      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, false, true, cell, tile, env_map);
     } else {
       if (change > 0) heat_increment(cfg, b.heatmap, (size_t)e * cells + (size_t)hy * W + hx, lane);   // :137
-      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, r.map, multi);
+      if (t == T - 1) write_record(sg, cfg, e, lane, reward, done, x, y, change > 0, false, cell, tile, env_map, multi);
     }
   }
   rng.finish(lane);

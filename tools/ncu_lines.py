@@ -61,8 +61,10 @@ def main():
     base = int(b["rows"][0][0], 16)
     funcs = sass_lines(ksub)
     # pick the SASS function whose mangled name contains the kernel substring and instantiation
-    inst = re.search(r"<\(int\)(\d+)>", b["name"])
-    cands = [f for f in funcs if ksub in f and (inst is None or ("ILi%sE" % inst.group(1)) in f) and not f.startswith("_ZN") or (ksub in f and inst and ("ILi%sE" % inst.group(1)) in f)]
+    # template arguments "(int)0, (int)-1" -> mangled "ILi0ELin1EE"
+    targs = re.findall(r"\(int\)(-?\d+)", b["name"].split("(pcgrl_config")[0])
+    mang = ("I" + "".join("Li%sE" % (a.replace("-", "n")) for a in targs) + "E") if targs else None
+    cands = [f for f in funcs if (ksub + (mang or "")) in f]
     if not cands:   # namespaced kernels (pcgrl_smb::...)
         cands = [f for f in funcs if ksub in f]
     fn = funcs[cands[0]]

@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
       env_reset<PROB>(cfg, b, e, lane, sm, rng, board, x, y, st, unused);
 #pragma unroll
       for (int i = 0; i < NS; i++) start[i] = st[i];  // problem.py:45-46
+      // written here, where they change, so that only the entries get_episode_over reads stay live in the step loop
+      store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
       iteration = 0;
       changes = 0;
       best_cells = 0u;
@@ -169,7 +171,6 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     b.changes[e] = changes;
   }
   store_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st, lane);
-  store_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start, lane);
 #ifdef PCGRL_PROFILE
   KP();
   if (T == 1 && lane == 0 && nkp == 5) {  // status int64[16 + 8*cls + k]: cls 0 = no change, 1 = changed, 2 = reset

@@ -107,9 +107,9 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
     int old[NS];
 #pragma unroll
     for (int i = 0; i < NS; i++) old[i] = st[i];
-    int hx, hy, cell, tile, ex, ey;
+    int hx, hy, cell, tile, ex, ey, old_tile;
     bool multi;
-    const int change = apply_action<REPT>(cfg, act, board, env_map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
+    const int change = apply_action<REPT>(cfg, act, board, env_map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey, old_tile);
     KP();
     if (change > 0) {  // pcgrl_env.py:135-138
       changes += change;
@@ -122,8 +122,14 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
           st[0] = (int)full.x; st[1] = (int)full.y; best_cells = full.z;
         } else regions_and_longest_path(pass, lane, st[0], st[1], best_cells);  // single step: inline, latency first
       } else {
+        // zelda_prob.py:85: the region board holds every tile except solid (1) and door (4); a single-cell edit between two
+        // tiles on the same side leaves calc_num_regions unchanged (59 % of random edits), so its floods are skipped
+        constexpr unsigned REGION_TILES = 0xEDu;
+        const bool same_side = !multi && (((REGION_TILES >> old_tile) & 1u) == ((REGION_TILES >> tile) & 1u)) &&
+                               (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
+        const int known_regions = same_side ? st[4] : -1;
         bool unused;
-        map_stats<PROB>(board, cfg, lane, st, unused);
+        map_stats<PROB>(board, cfg, lane, st, unused, known_regions);
       }
     }
     KP();

@@ -82,9 +82,10 @@ __device__ __forceinline__ int apply_stamp(const pcgrl_config& cfg, Board& board
 template <int REPT = -1>
 __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32_t* __restrict__ act, Board& board,
                                             uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy,
-                                            int& cell, int& tile, bool& multi, int& ex, int& ey) {
+                                            int& cell, int& tile, bool& multi, int& ex, int& ey, int& old_tile) {
   const int W = cfg.width, H = cfg.height, rep = (REPT >= 0) ? REPT : cfg.representation;
   int change = 0, wx = x, wy = y, newt = -1;
+  old_tile = 0;
   multi = false;
   if (rep == PCGRL_REP_NARROW) {
     const int a = act[0];
@@ -124,6 +125,7 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
   }
   if (newt >= 0) {
     const int oldt = __shfl_sync(FULL_MASK, tile_at(board, wx), wy);
+    old_tile = oldt;
     change = (oldt != newt) ? 1 : 0;
     if (change) {
       if (lane == wy) set_tile(board, wx, newt);
@@ -152,8 +154,8 @@ __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32
 __device__ __forceinline__ int apply_action(const pcgrl_config& cfg, const int32_t* __restrict__ act, Board& board,
                                             uint8_t* map, WarpRng& rng, int lane, int& x, int& y, int& hx, int& hy,
                                             int& cell, int& tile, bool& multi) {
-  int ex, ey;
-  return apply_action<-1>(cfg, act, board, map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey);
+  int ex, ey, old_tile;
+  return apply_action<-1>(cfg, act, board, map, rng, lane, x, y, hx, hy, cell, tile, multi, ex, ey, old_tile);
 }
 
 // _heatmap[y][x] += 1 (pcgrl_env.py:137) as a fire-and-forget 32-bit reduction on the containing word

@@ -17,8 +17,11 @@ template <> struct ProblemTraits<PCGRL_PROB_MDUNGEON> { static constexpr int NPL
 // Everything of Problem.get_stats that is a map scan / flood fill / BFS.  For the solver problems the
 // play-through statistics keep their "not playable" defaults and *need_solver tells the caller that the
 // reference would call _run_game on this map.  st[] is warp-uniform.
+// known_regions >= 0 (zelda): the caller knows the region count of this map (a single-cell edit that did not change
+// whether the cell belongs to the region board leaves calc_num_regions unchanged), so the floods are skipped.
 template <int PROB>
-__device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cfg, int lane, int* st, bool& need_solver) {
+__device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cfg, int lane, int* st, bool& need_solver,
+                                          int known_regions = -1) {
   const int W = cfg.width, H = cfg.height;
   const uint32_t rm = row_mask(W, H, lane);
   need_solver = false;
@@ -34,7 +37,8 @@ __device__ __forceinline__ void map_stats(const Board& b, const pcgrl_config& cf
     st[1] = popc_all(key);
     st[2] = popc_all(door);
     st[3] = popc_all(enemies);
-    st[4] = count_regions(type_mask<0xEDu>(b, rm), lane);  // empty, player, key, bat, spider, scorpion
+    st[4] = known_regions >= 0 ? known_regions
+                               : count_regions(type_mask<0xEDu>(b, rm), lane);  // empty, player, key, bat, spider, scorpion
     if (st[0] == 1 && st[4] == 1) {
       if (st[3] > 0) {  // nearest enemy: first BFS wave (d > 0) that touches an enemy; key and door block
         const uint32_t pass = type_mask<0xE5u>(b, rm);

@@ -63,8 +63,8 @@ enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP
 #define PCGRL_FLAG_RANDOM_PROBS 8u  /* binary_prob.py:68-72: redraw tile probabilities at every reset          */
 #define PCGRL_FLAG_AUTO_RESET 16u   /* VecEnv semantics: an env that is done is reset inside step()            */
 #define PCGRL_FLAG_HEAT_U16 32u     /* heat map elements are uint16 (required when max_changes > 255)          */
-#define PCGRL_FLAG_FULL_STATS 64u   /* binary rollouts: recompute the whole map after every edit instead of the
-                                       incremental update (same results; A/B and test switch)                */
+#define PCGRL_FLAG_FULL_STATS 64u   /* binary / zelda: recompute every statistic of the whole map after every edit
+                                       instead of the incremental updates (same results; A/B and test switch) */
 
 /*
  * Stats row layout (int32, stride PCGRL_MAX_STATS), one order per problem == the key order of

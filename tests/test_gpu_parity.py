@@ -921,13 +921,19 @@ INCREMENTAL_CASES = [
     ("binary-wide-v0", dict(width=3, height=3, change_percentage=1.0), 128, 60, 2),
     ("binary-wide-v0", dict(width=1, height=6, change_percentage=1.0), 64, 40, 1),
     ("binary-wide-v0", dict(width=7, height=1, change_percentage=1.0), 64, 40, 1),
+    # zelda: the region floods are skipped when a single-cell edit stays on one side of the region board
+    ("zelda-narrow-v0", {}, 256, 120, 2),
+    ("zelda-turtle-v0", dict(width=11, height=16, change_percentage=0.5), 256, 200, 1),
+    ("zelda-wide-v0", dict(change_percentage=1.0, probs={
+        "empty": 0.93, "solid": 0.02, "player": 0.006, "key": 0.006, "door": 0.006, "bat": 0.01, "scorpion": 0.01, "spider": 0.012}), 256, 150, 1),
 ]
 
 
 @pytest.mark.parametrize("case", INCREMENTAL_CASES, ids=["%s-%d" % (c[0], i) for i, c in enumerate(INCREMENTAL_CASES)])
 def test_incremental_binary_statistics_match_oracle(case, monkeypatch):
-    """regions / path-length maintained incrementally inside a fused rollout == the oracle's full recomputation at every
-    step (reward is a function of both), and == the same launch with PCGRL_FLAG_FULL_STATS."""
+    """regions / path-length maintained incrementally inside a fused rollout (binary), region floods skipped for edits
+    that cannot change them (zelda) == the oracle's full recomputation at every step (reward is a function of the
+    statistics), and == the same launch with PCGRL_FLAG_FULL_STATS."""
     import torch
     env_id, kwargs, n, T, launches = case
     states = np.stack([util.randomstate_words(31_000 + i) for i in range(n)])
@@ -954,6 +960,7 @@ def test_incremental_binary_statistics_match_oracle(case, monkeypatch):
         for key in ("map", "stats", "start_stats", "changes", "iteration"):
             assert torch.equal(env._tens[key], env_full._tens[key]), key
         np.testing.assert_array_equal(t2n(env._tens["map"]), ref["map"])
-        np.testing.assert_array_equal(t2n(env._tens["stats"])[:, :2], ref["stats"][:, :2])
+        S = util.nstats(env_id.split("-")[0])
+        np.testing.assert_array_equal(t2n(env._tens["stats"])[:, :S], ref["stats"][:, :S])
         np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"])
     env.check_status()

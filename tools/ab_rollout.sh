@@ -3,7 +3,7 @@
 # executed / local-memory instruction counts of two steady-state 20-step launches.  Usage: tools/ab_rollout.sh <tag>
 tag=${1:-ab}
 cd "$(dirname "$0")/.."
-timeout 700 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "incremental or rollout_api or full_size or (batched_rollout_matches_oracle and binary)" 2>&1 | tail -3
+timeout 700 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "incremental or rollout_api or full_size or (batched_rollout_matches_oracle and (binary or zelda)) or step_host or graph_capturable" 2>&1 | tail -3
 B="python bench.py --steps 20 --warmup 5 --no-sweep --no-cpu"
 timeout 200 $B > gpurun_out/${tag}_T20.json 2>gpurun_out/${tag}.err
 timeout 200 $B --steps 512 > gpurun_out/${tag}_T128.json 2>>gpurun_out/${tag}.err

@@ -127,7 +127,14 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
         constexpr unsigned REGION_TILES = 0xEDu;
         const bool same_side = !multi && (((REGION_TILES >> old_tile) & 1u) == ((REGION_TILES >> tile) & 1u)) &&
                                (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
-        const int known_regions = same_side ? st[4] : -1;
+        int known_regions = same_side ? st[4] : -1;
+        if (!same_side && !multi && (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0) {
+          // the cell entered / left the region board: the 3x3 window around it usually tells how many regions it touches
+          const bool grew = ((REGION_TILES >> tile) & 1u) != 0u;
+          const uint32_t p0 = type_mask<REGION_TILES>(board, row_mask(W, H, lane)) & ~cell_bit(ey, ex, lane);
+          const int m = local_piece_count(p0, ex, ey);
+          if (m >= 0) known_regions = st[4] + (grew ? 1 - m : m - 1);
+        }
         bool unused;
         map_stats<PROB>(board, cfg, lane, st, unused, known_regions);
       }

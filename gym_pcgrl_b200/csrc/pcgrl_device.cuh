@@ -399,6 +399,26 @@ __device__ __forceinline__ int count_regions(uint32_t pass, int lane) {
   return regions;
 }
 
+// How many components of p0 (a board that does NOT contain the cell (ex, ey)) hold one of the cell's four neighbours,
+// decided from the 3x3 window around the cell alone: 0 when no neighbour is set, 1 when all set neighbours are linked
+// through set diagonal cells of the window (N-NE-E, E-SE-S, S-SW-W, W-NW-N), -1 when the window cannot tell (the
+// neighbours may still be connected through the rest of the map).  Toggling the cell then changes the number of regions
+// by 1 - m (cell set) or m - 1 (cell cleared).  Warp-uniform.
+__device__ __forceinline__ int local_piece_count(uint32_t p0, int ex, int ey) {
+  const uint32_t up_row = __shfl_sync(FULL_MASK, p0, (ey + 31) & 31), mid_row = __shfl_sync(FULL_MASK, p0, ey),
+                 dn_row = __shfl_sync(FULL_MASK, p0, (ey + 1) & 31);
+  // bits (ex-1, ex, ex+1) of a row -> bits 0..2
+  const uint32_t up = ey > 0 ? (uint32_t)((((unsigned long long)up_row) << 1) >> ex) & 7u : 0u;
+  const uint32_t mid = (uint32_t)((((unsigned long long)mid_row) << 1) >> ex) & 7u;
+  const uint32_t dn = ey < 31 ? (uint32_t)((((unsigned long long)dn_row) << 1) >> ex) & 7u : 0u;
+  const uint32_t N = (up >> 1) & 1u, S = (dn >> 1) & 1u, W = mid & 1u, E = (mid >> 2) & 1u;
+  const uint32_t NW = up & 1u, NE = (up >> 2) & 1u, SW = dn & 1u, SE = (dn >> 2) & 1u;
+  const int k = (int)(N + S + W + E);
+  if (k <= 1) return k;
+  const int links = (int)((N & NE & E) + (E & SE & S) + (S & SW & W) + (W & NW & N));
+  return (k - links <= 1) ? 1 : -1;
+}
+
 // G/helper.py:197-207 + :250-264 fused: regions and calc_longest_path of `pass`.
 // Per component (processed in row-major order of its first cell, like the reference): BFS from the first
 // cell, np.argmax tie-break = row-major-first cell of the last frontier, BFS from there, keep the max.

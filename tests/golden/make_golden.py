@@ -87,6 +87,16 @@ KAT_CONFIGS = [
     ("binary_turtlecast_warp", "binary-turtlecast-v0", dict(warp=True, width=9, height=12, change_percentage=0.5)),
     ("ddave_narrowcast_raster", "ddave-narrowcast-v0", dict(random_tile=False)),
     ("mdungeon_narrowmulti", "mdungeon-narrowmulti-v0", {}),
+    # the remaining ids, so that each of the 36 registered environments replays at least one reference trajectory
+    ("binary_narrowmulti", "binary-narrowmulti-v0", {}),
+    ("zelda_narrowcast", "zelda-narrowcast-v0", {}),
+    ("zelda_turtlecast", "zelda-turtlecast-v0", dict(change_percentage=0.5)),
+    ("sokoban_narrowcast_sparse", "sokoban-narrowcast-v0", dict(probs=SOKOBAN_SPARSE)),
+    ("sokoban_narrowmulti", "sokoban-narrowmulti-v0", {}),
+    ("ddave_narrowmulti_sparse", "ddave-narrowmulti-v0", dict(probs=DDAVE_SPARSE)),
+    ("ddave_turtlecast", "ddave-turtlecast-v0", dict(warp=True)),
+    ("mdungeon_narrowcast_sparse", "mdungeon-narrowcast-v0", dict(probs=MDUNGEON_SPARSE)),
+    ("mdungeon_turtlecast", "mdungeon-turtlecast-v0", {}),
     # random_start=False: every reset restores the first map (representation.py:41-45)
     ("zelda_wide_fixedstart", "zelda-wide-v0", dict(random_start=False)),
     ("binary_narrow_fixedstart_raster", "binary-narrow-v0", dict(random_start=False, random_tile=False, width=10, height=6, change_percentage=0.3)),

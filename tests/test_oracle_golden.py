@@ -121,3 +121,12 @@ def test_auto_reset_equals_manual_reset():
             assert o["iteration"][0] == 0 and o["heatmap"][0].sum() == 0
         else:
             np.testing.assert_array_equal(o["map"][0], traj["map"][t])
+
+
+def test_every_registered_id_has_a_reference_trajectory():
+    """36 ids = 6 problems x 6 representations (gym_pcgrl/__init__.py:6-12): each one replays at least one golden
+    trajectory recorded from the unmodified reference, so no id is covered by batched-vs-oracle evidence alone."""
+    import gym_pcgrl_b200
+    covered = {m["env_id"] for m in util.kat_configs()}
+    assert len(gym_pcgrl_b200.REGISTRY) == 36
+    assert sorted(set(gym_pcgrl_b200.REGISTRY) - covered) == []

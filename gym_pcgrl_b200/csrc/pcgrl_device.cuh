@@ -20,7 +20,7 @@ namespace pcgrl {
 // ------------------------------------------------------------------------------------------------
 // per-warp shared scratch
 // ------------------------------------------------------------------------------------------------
-struct WarpSmem {
+struct __align__(8) WarpSmem {
   uint32_t bits[3 * PCGRL_SBITS_STRIDE];  // ballot words of the three tile bit-planes (row-major bit stream)
   uint32_t draws[512];                    // tempered MT19937 outputs for one 256-cell segment of gen_random_map
   uint32_t mt[624];                       // MT19937 key staged here for the duration of a reset (twist + ~2*H*W draws)
@@ -176,11 +176,21 @@ struct WarpRng {
   // `pos` stays in the register.  unstage() writes the key back and returns to the HBM copy.
   __device__ __forceinline__ uint32_t* stage(uint32_t* smem_key, int lane) {
     uint32_t* g = st;
-    uint32_t v[20];
+    // 312 asynchronous 8-byte copies global -> shared (a stream starts on an 8-byte boundary: 2500 B per stream), all in
+    // flight at once and without staging registers; under the 72-register cap the register version (20 loads per lane)
+    // was issued in several dependent batches
+    if ((reinterpret_cast<uintptr_t>(g) & 7u) == 0u) {
+      const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_key);
 #pragma unroll
-    for (int k = 0; k < 20; k++) v[k] = (k * 32 + lane < 624) ? __ldcg(g + k * 32 + lane) : 0u;  // 20 loads in flight (st is the HBM copy here)
-#pragma unroll
-    for (int k = 0; k < 20; k++) if (k * 32 + lane < 624) smem_key[k * 32 + lane] = v[k];
+      for (int k = 0; k < 10; k++) {
+        const int i = k * 32 + lane;
+        if (i < 312) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * (uint32_t)i), "l"(g + 2 * i) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {  // a caller-owned rng buffer that is only 4-byte aligned
+      for (int i = lane; i < 624; i += 32) smem_key[i] = __ldcg(g + i);
+    }
     __syncwarp();
     st = smem_key;
     base = -1000;

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
 
   // binary: cells of components known to hold the longest path (binary_stats_update); nothing known at launch
   uint32_t best_cells = 0u;
-  const bool incremental = T > 1 && (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
+  const bool incremental = (cfg.flags & PCGRL_FLAG_FULL_STATS) == 0;
   // one 32-bit row offset (t * n + e) is the only loop-carried index (rollout_dispatch checks T * n * adim < 2^31): the
   // base pointers are kernel parameters (constant bank operands), loop-carried 64-bit pointers were measured to spill
   uint32_t row = (uint32_t)e;

@@ -24,7 +24,9 @@ max-over-ranks time of one K-step region.
                CUDA graph and replayed.
   e2e          the per-step C-ABI call with HOST buffers (pcgrl_step_host): every step reads that step's actions from
                pinned host memory and brings map + heatmap + pos + reward + done back to the host, synchronised -- the
-               call a gym / VecEnv binding makes.
+               call a gym / VecEnv binding makes.  Transport = mode 2 ("direct": the step kernel stores the results into
+               the pinned host arrays while it runs); `e2e_delta` (mode 1: change records + one D2H copy, applied by the
+               library) and `e2e_full_copy` (mode 0) are the other two transports of the same call.
   roofline     k_rollout<binary>: algorithmic bytes (4*H*W + 64 per env-step) / event time of the
                launches of the timed region, against the measured HBM copy bandwidth in MEASURED_PEAKS.json; `issue`
                is the warp-instruction issue-rate view of the same kernel (the limiter that actually binds).
@@ -418,6 +420,7 @@ class Bench:
         for t in range(8):
             io.struct.actions = base + t * stride
             env.step_host(io)
+        c0, r0, nsteps = int(io.struct.change_base), int(io.struct.reset_base), 0   # running counters of the delta transport
         # wall clock: the K-step region is run `per` times inside one barrier bracket (the NCCL barrier itself costs about
         # as much as one step, so a bracket around a single 20-step region would charge it to the steps); ms per REGION
         per = max(1, min(R, 400 // max(1, K)))
@@ -432,6 +435,10 @@ class Bench:
             t1 = time.perf_counter()
             self.barrier()
             out.append((t1 - t0) * 1e3 / per)
+            nsteps += per * K
+        if mode == "delta":   # per-step averages over the timed steps: envs with a change record, whole-map updates (auto-resets)
+            io.records_per_step = (int(io.struct.change_base) - c0) / max(1, nsteps)
+            io.resets_per_step = (int(io.struct.reset_base) - r0) / max(1, nsteps)
         return out, io, float(io.reward.sum())
 
     def time_e2e_rollout(self, env, K, chunk, R, seed):
@@ -557,7 +564,9 @@ class Bench:
                 e1.record()
                 self.barrier()
                 step_ms = e0.elapsed_time(e1)
-                e2e_ms, io, _ = self.time_e2e(env, 48, 2, "delta", 99 + self.rank)
+                # per-step host API: direct transport for the graph-only problems (the transport matters there), delta
+                # records for the solver problems (their step lasts milliseconds either way)
+                e2e_ms, io, _ = self.time_e2e(env, 48, 2, "direct" if wl["prob"] in ("binary", "zelda") else "delta", 99 + self.rank)
                 env.check_status()
                 async_ms = None
                 if wl["prob"] in ("sokoban", "ddave", "mdungeon", "smb"):   # a batch step waits for its slowest search
@@ -672,10 +681,12 @@ def main():
         res["graph"] = float(np.median(B.max_over_ranks(graph_ms))) if graph_ms else None
         res["kernel"] = float(np.median(kernel_ms))
         Re = max(3, min(R, 25))
-        e2e_ms, io, rsum = B.time_e2e(env, K, Re, "delta", 99 + rank)
+        e2e_ms, io, rsum = B.time_e2e(env, K, Re, "direct", 99 + rank)
+        e2e_delta_ms, io_delta, _ = B.time_e2e(env, K, Re, "delta", 149 + rank)
         e2e_full_ms, io_full, _ = B.time_e2e(env, K, max(3, Re // 3), "full", 199 + rank)
         e2e_roll_ms, rio, roll_steps = B.time_e2e_rollout(env, K, chunk, max(3, Re // 3), 299 + rank)
         res["e2e"] = float(np.median(B.max_over_ranks(e2e_ms)))
+        res["e2e_delta"] = float(np.median(B.max_over_ranks(e2e_delta_ms)))
         res["e2e_full"] = float(np.median(B.max_over_ranks(e2e_full_ms)))
         res["e2e_roll"] = float(np.median(B.max_over_ranks(e2e_roll_ms)))
         gather = None
@@ -739,10 +750,24 @@ def main():
                 "api": "per step: torch.randint on the device -> pcgrl_step (T=1 launch of k_rollout); obs / reward / "
                        "done stay in HBM where a policy would read them",
                 "graph_error": getattr(B, "graph_error", None)}
+            # direct transport: bytes the kernel stores into the host arrays per step = reward + done + cursor of every env,
+            # map cell + heat count of every edited env, map + cleared heat map of every auto-reset env (the per-step counts
+            # of edited / reset envs are the change-record counters of the delta run of the same workload just below)
+            hb = env._tens["heatmap"].element_size()
+            edited = max(0.0, io_delta.records_per_step - io_delta.resets_per_step)
+            direct_bytes = io.d2h_bytes + edited * (1 + hb) + io_delta.resets_per_step * W * H * (1 + hb)
             line["e2e"] = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": io.h2d_bytes * world,
-                           "d2h_bytes_per_step": io.d2h_bytes * world, "ms_per_step": res["e2e"] / K,
-                           "api": "pcgrl_step_host mode 1 (pinned host buffers; per-env delta records + fresh maps of reset envs "
-                                  "copied back and applied, so the host arrays hold the complete map+heatmap+pos+reward+done after every step)"}
+                           "d2h_bytes_per_step": int(round(direct_bytes)) * world, "ms_per_step": res["e2e"] / K,
+                           "edited_envs_per_step": edited, "reset_envs_per_step": io_delta.resets_per_step,
+                           "api": "pcgrl_step_host mode 2 (direct transport: pinned, device-mapped host buffers; the step kernel reads "
+                                  "the host actions and stores reward / done / cursor of every env, the edited map cell + its heat count "
+                                  "and the fresh map of auto-reset envs straight into the host arrays, which hold the complete "
+                                  "map+heatmap+pos+reward+done after every step)"}
+            line["e2e_delta"] = {"value": total_envs * K / (res["e2e_delta"] * 1e-3), "unit": "env-steps/s",
+                                 "h2d_bytes_per_step": io_delta.h2d_bytes * world, "d2h_bytes_per_step": io_delta.d2h_bytes * world,
+                                 "ms_per_step": res["e2e_delta"] / K,
+                                 "api": "pcgrl_step_host mode 1 (per-env delta records + fresh maps of reset envs in one D2H copy, "
+                                        "applied to the host arrays by the library)"}
             line["e2e_full_copy"] = {"value": total_envs * K / (res["e2e_full"] * 1e-3), "unit": "env-steps/s",
                                      "h2d_bytes_per_step": io_full.h2d_bytes * world, "d2h_bytes_per_step": io_full.d2h_bytes * world,
                                      "ms_per_step": res["e2e_full"] / K, "api": "pcgrl_step_host mode 0 (every array copied back in full)"}

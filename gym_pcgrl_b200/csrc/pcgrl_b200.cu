@@ -927,7 +927,7 @@ static int rollout_fused(const pcgrl_config* cfg, const pcgrl_buffers* b, const 
     // profiles/r02_summary.md): the per-group state machine costs ~15 instructions per wave against 10.5, a packed
     // pass lasts as long as its slower env, and half as many warps hide less latency.  Kept for A/B runs.
     static const bool packed = getenv("PCGRL_PACKED") && atoi(getenv("PCGRL_PACKED")) == 1;
-    if (packed && !sg.base && T >= PCGRL_PACKED_MIN_T && cfg->height <= 16 && cfg->representation <= PCGRL_REP_WIDE) {
+    if (packed && !sg.base && !sg.direct && T >= PCGRL_PACKED_MIN_T && cfg->height <= 16 && cfg->representation <= PCGRL_REP_WIDE) {
       if (cfg->height <= 8) {
         const int epc = PACKED_WPB * 4;
         k_rollout_packed_binary<8><<<(n + epc - 1) / epc, 32 * PACKED_WPB, 0, s>>>(*cfg, *b, actions, reward_out, done_out, T, n);
@@ -1179,6 +1179,22 @@ extern "C" size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n) {
   return staging_layout(n, staging_slots(n), cfg->width * cfg->height).total;
 }
 
+// Device-visible address of a pinned host allocation (NULL if p is NULL or not device-mapped).  The lookups of the last
+// few base pointers are cached: a binding passes the same arrays on every step.
+static void* host_device_ptr(const void* p) {
+  if (!p) return nullptr;
+  struct Entry { const void* host; void* dev; };
+  static thread_local Entry cache[16];
+  static thread_local int used = 0;
+  for (int i = 0; i < used; i++) if (cache[i].host == p) return cache[i].dev;
+  cudaPointerAttributes attr;
+  void* dev = nullptr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) dev = attr.devicePointer;
+  else cudaGetLastError();
+  if (dev && used < 16) cache[used++] = Entry{p, dev};
+  return dev;
+}
+
 // pcgrl_step_host = pcgrl_step_host_begin (enqueue: actions in, step kernels, results towards pinned host memory) +
 // pcgrl_step_host_end (wait for / poll the stream, then patch the host arrays).  io->pending carries the state between
 // the two: 0 idle, 1 delta transport in flight, 2 full copies in flight.
@@ -1208,6 +1224,27 @@ extern "C" int pcgrl_step_host_begin(const pcgrl_config* cfg, const pcgrl_buffer
   }
   if (act_ptr == d_actions) cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * (size_t)n * adim, cudaMemcpyHostToDevice, s);
   HT(0);
+
+  if (io->mode == 2 && io->synced) {
+    // direct transport: the kernels store the results straight into the caller's pinned host arrays
+    Staging sg{nullptr, 0u, 0u, 0, n};
+    sg.direct = 1;
+    sg.h_map = (uint8_t*)host_device_ptr(io->map);
+    sg.h_heat = (uint8_t*)host_device_ptr(io->heatmap);
+    sg.h_pos = wide ? nullptr : (uint8_t*)host_device_ptr(io->pos);
+    sg.h_reward = (double*)host_device_ptr(io->reward);
+    sg.h_done = (uint8_t*)host_device_ptr(io->done);
+    sg.d_heat = b->heatmap;
+    if (!sg.h_reward || !sg.h_done || (io->map && !sg.h_map) || (io->heatmap && !sg.h_heat) || (io->pos && !wide && !sg.h_pos))
+      return fail(-1, "mode 2 needs pinned (device-mapped) host arrays");
+    rc = rollout_dispatch(cfg, b, act_ptr, nullptr, nullptr, 1, n, stream, sg);
+    if (rc) return rc;
+    HT(1);
+    if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
+    HT(2);
+    io->pending = 3;
+    return 0;
+  }
 
   if (delta && io->synced) {
     if (n >= (1 << 24)) return fail(-1, "delta transport supports n < 2^24 envs per call");
@@ -1259,7 +1296,11 @@ extern "C" int pcgrl_step_host_end(const pcgrl_config* cfg, const pcgrl_buffers*
   uint16_t* const heat16 = (uint16_t*)io->heatmap;
   if (io->pending == 2) {
     io->pending = 0;
-    if (io->mode == 1) { io->synced = 1; io->reset_base = 0; io->change_base = 0; }
+    if (io->mode == 1 || io->mode == 2) { io->synced = 1; io->reset_base = 0; io->change_base = 0; }
+    return 0;
+  }
+  if (io->pending == 3) {  // direct transport: the kernel wrote the host arrays itself
+    io->pending = 0;
     return 0;
   }
   io->pending = 0;

@@ -332,16 +332,69 @@ __host__ __device__ __forceinline__ StagingLayout staging_layout(int n, int nslo
 }
 
 struct Staging {
-  uint8_t* base;         // nullptr: transport disabled
+  uint8_t* base;         // nullptr: delta transport disabled
   uint32_t reset_base;   // values of the running counters at the start of this step
   uint32_t change_base;
   int nslots;
   int n;
+  // direct transport (pcgrl_host_io mode 2): device-visible addresses of the caller's pinned host arrays; the kernel
+  // stores every result where it belongs while it runs, nothing is copied or patched afterwards
+  int direct;
+  uint8_t* h_map;
+  uint8_t* h_heat;       // uint8 or uint16 elements, like the device heat map
+  uint8_t* h_pos;        // nullptr for the wide representation
+  double* h_reward;
+  uint8_t* h_done;
+  const void* d_heat;    // device heat map (the new value of the incremented cell is read back from it)
 };
+
+// Direct transport of one env's step results into the host arrays (posted writes over PCIe, overlapped with the
+// rest of the launch).
+__device__ __forceinline__ void write_direct(const Staging& sg, const pcgrl_config& cfg, int e, int lane, double reward,
+                                             bool done, int x, int y, bool changed, bool was_reset, int cell, int tile,
+                                             const uint8_t* new_map, bool multi) {
+  const int cells = cfg.width * cfg.height, hb = heat_bytes(cfg);
+  const bool wide = cfg.representation == PCGRL_REP_WIDE;
+  if (lane == 0) {
+    sg.h_reward[e] = reward;
+    sg.h_done[e] = done ? 1 : 0;
+    if (sg.h_pos) *reinterpret_cast<uint16_t*>(sg.h_pos + 2 * (size_t)e) = (uint16_t)((uint32_t)x | ((uint32_t)y << 8));
+  }
+  multi = multi && changed && !was_reset;
+  if (!(changed || was_reset)) return;
+  if ((was_reset || multi) && sg.h_map) {  // whole map (the warp's own earlier stores are visible after the barrier)
+    __syncwarp();
+    uint8_t* dst = sg.h_map + (size_t)e * cells;
+    if ((cells & 3) == 0) {
+      for (int i = lane; i < (cells >> 2); i += 32)
+        reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(new_map)[i];
+    } else {
+      for (int i = lane; i < cells; i += 32) dst[i] = new_map[i];
+    }
+  } else if (lane == 0 && sg.h_map) {
+    sg.h_map[(size_t)e * cells + cell] = (uint8_t)tile;
+  }
+  if (!sg.h_heat) return;
+  if (was_reset) {
+    warp_fill_bytes(sg.h_heat + (size_t)e * cells * hb, cells * hb, 0, lane);   // pcgrl_env.py:72
+  } else if (lane == 0) {
+    // the heat cell was incremented by heat_increment (a reduction on the containing word); an atomic read of that word
+    // by the same thread is ordered after it
+    const size_t hi = (size_t)e * cells + (wide ? (size_t)cell : (size_t)y * cfg.width + x);
+    if (hb == 2) {
+      const uint32_t w = atomicAdd(const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(sg.d_heat)) + (hi >> 1), 0u);
+      reinterpret_cast<uint16_t*>(sg.h_heat)[hi] = (uint16_t)(w >> (16u * (uint32_t)(hi & 1)));
+    } else {
+      const uint32_t w = atomicAdd(const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(sg.d_heat)) + (hi >> 2), 0u);
+      sg.h_heat[hi] = (uint8_t)(w >> (8u * (uint32_t)(hi & 3)));
+    }
+  }
+}
 
 __device__ __forceinline__ void write_record(const Staging& sg, const pcgrl_config& cfg, int e, int lane, double reward,
                                              bool done, int x, int y, bool changed, bool was_reset, int cell, int tile,
                                              const uint8_t* new_map, bool multi = false) {
+  if (sg.direct) { write_direct(sg, cfg, e, lane, reward, done, x, y, changed, was_reset, cell, tile, new_map, multi); return; }
   if (!sg.base) return;
   const int cells = cfg.width * cfg.height;
   const StagingLayout L = staging_layout(sg.n, sg.nslots, cells);

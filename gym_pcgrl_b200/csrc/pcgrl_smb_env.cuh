@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(32 * SMB_WPB) k_smb_rollout(const __grid_const
         if (cfg.flags & PCGRL_FLAG_HEAT_U16) reinterpret_cast<uint16_t*>(b.heatmap)[hi] += 1;
         else reinterpret_cast<uint8_t*>(b.heatmap)[hi] += 1;
       }
-      if (t == T - 1 && sg.base) {  // delta transport of pcgrl_step_host: warp-uniform arguments
+      if (t == T - 1 && (sg.base || sg.direct)) {  // delta transport of pcgrl_step_host: warp-uniform arguments
         reward = shfl_double(reward, 0);
         const int rx = __shfl_sync(0xffffffffu, x, 0), ry = __shfl_sync(0xffffffffu, y, 0);
         cell = __shfl_sync(0xffffffffu, cell, 0);

@@ -346,7 +346,10 @@ class HostStepIO:
 
     mode="delta" (default): the step kernels emit one 16-byte record per env plus the fresh maps of auto-reset
     envs; one small D2H copy per step, the library patches these persistent host arrays so they always hold the
-    complete current observation.  mode="full": every array is copied back in full every step."""
+    complete current observation.  mode="full": every array is copied back in full every step.
+    mode="direct": the step kernels store every result straight into these pinned (device-mapped) arrays while they
+    run -- reward / done / cursor of every env, the edited map cell and its heat-map count, the whole map of an
+    auto-reset env -- so nothing is copied or patched after the launch."""
 
     def __init__(self, env, with_obs=True, with_info=False, mode="delta"):
         import torch
@@ -373,6 +376,10 @@ class HostStepIO:
             s.d_staging, s.h_staging, s.staging_bytes = self.d_staging.data_ptr(), self.h_staging.data_ptr(), nbytes
             s.mode, s.synced, s.reset_base = 1, 0, 0
             self.staging_bytes = nbytes
+        elif mode == "direct":
+            s.mode, s.synced = 2, 0
+        elif mode != "full":
+            raise ValueError("mode must be 'delta', 'full' or 'direct'")
         self.struct = s
         self.ref = C.byref(s)
         self.h2d_bytes = self.actions.numel() * 4
@@ -380,6 +387,8 @@ class HostStepIO:
                               (self.map, self.heatmap, self.pos, self.reward, self.done, self.info_stats) if t is not None)
         info_bytes = 0 if self.info_stats is None else self.info_stats.numel() * 4
         self.d2h_bytes = (self.staging_bytes + info_bytes) if mode == "delta" else self.full_bytes
+        if mode == "direct":   # fixed part: reward + done (+ cursor) of every env; edited cells / reset maps come on top
+            self.d2h_bytes = n * (8 + 1 + (2 if self.pos is not None else 0)) + info_bytes
 
     def invalidate(self):
         """Call after env.reset() / env.step() / env.rollout(): the next step_host re-syncs with a full copy."""

@@ -192,8 +192,8 @@ typedef struct pcgrl_host_io {
   void* d_staging;        /* mode 1: device scratch   */
   void* h_staging;        /* mode 1: pinned host scratch */
   size_t staging_bytes;
-  int32_t mode;           /* 0 full copies, 1 delta records */
-  int32_t synced;         /* in/out, mode 1: host arrays are in sync with the device state */
+  int32_t mode;           /* 0 full copies, 1 delta records, 2 direct (the kernels store into the pinned host arrays) */
+  int32_t synced;         /* in/out, modes 1 and 2: host arrays are in sync with the device state */
   int64_t reset_base;     /* in/out, mode 1: running counters of staged whole-map updates / change records */
   int64_t change_base;    /*                 (library-maintained)                                            */
   int32_t pending;        /* library-maintained: a pcgrl_step_host_begin of this block awaits its _end (init 0) */

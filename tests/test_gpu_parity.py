@@ -580,10 +580,10 @@ HOST_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["full", "delta"])
+@pytest.mark.parametrize("mode", ["full", "delta", "direct"])
 @pytest.mark.parametrize("case", HOST_CASES, ids=[c[0] for c in HOST_CASES])
 def test_step_host_equals_step(case, mode):
-    """pcgrl_step_host (host buffers in / out, full-copy and delta-record transport) == pcgrl_step on the device."""
+    """pcgrl_step_host (host buffers in / out; full-copy, delta-record and direct transport) == pcgrl_step on the device."""
     import torch
     env_id, kwargs, n, steps = case
     envs = []

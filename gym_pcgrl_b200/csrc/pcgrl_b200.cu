@@ -73,6 +73,12 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
 #define KP() do {} while (0)
 #endif
   KP();
+  // One-word actions (narrow / turtle): the first step's action is LOADED first of all -- with pcgrl_step_host it sits in
+  // pinned host memory, and its PCIe round trip then overlaps the state loads below -- and every later step's action is
+  // loaded one step ahead (software pipelining; the other representations keep the L1 prefetch).
+  constexpr bool ONE_WORD = (REPT == PCGRL_REP_NARROW || REPT == PCGRL_REP_TURTLE);
+  int a_next = 0;
+  if (ONE_WORD) a_next = actions[e];
   // all prologue loads are independent: issue them before the ballots of load_board serialise the warp
   WarpRng rng;
   rng.init(b.rng + (size_t)e * 2 * PCGRL_MT_WORDS, (rep == PCGRL_REP_NARROW || rep >= PCGRL_REP_NARROWCAST) ? lane : -1);
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   load_row<NS>(b.stats + (size_t)e * PCGRL_MAX_STATS, st);
   load_row<NS>(b.start_stats + (size_t)e * PCGRL_MAX_STATS, start);
   // first step's action: pull its line into L1 now so the load in apply_action does not add a round trip
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)e * adim));
+  if (!ONE_WORD) asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)e * adim));
   Board board = load_board<NP>(env_map, W, H, lane, sm.bits);
   KP();
 #ifdef PCGRL_PROFILE
@@ -98,8 +104,13 @@ __global__ void __launch_bounds__(32 * WPB, 7) k_rollout(const __grid_constant__
   uint32_t row = (uint32_t)e;
   for (int t = 0; t < T; t++, row += (uint32_t)n) {
     const int32_t* act = actions + (size_t)(row * (uint32_t)adim);
-    if (t + 2 < T)  // the action rows of the next steps are independent of the state: pull them towards L1 now
+    int32_t a_cur = a_next;
+    if (ONE_WORD) {
+      act = &a_cur;
+      if (t + 1 < T) a_next = actions[row + (uint32_t)n];
+    } else if (t + 2 < T) {  // the action rows of the next steps are independent of the state: pull them towards L1 now
       asm volatile("prefetch.global.L1 [%0];" ::"l"(actions + (size_t)((row + 2u * (uint32_t)n) * (uint32_t)adim)));
+    }
     iteration++;  // pcgrl_env.py:130
     // this step can end the episode through the change / iteration limits: start pulling what the reset will read
     if (auto_reset && (changes + max_change_per_step(rep) >= cfg.max_changes || iteration >= cfg.max_iterations))

@@ -1192,17 +1192,22 @@ extern "C" size_t pcgrl_host_staging_bytes(const pcgrl_config* cfg, int n) {
 
 // Device-visible address of a pinned host allocation (NULL if p is NULL or not device-mapped).  The lookups of the last
 // few base pointers are cached: a binding passes the same arrays on every step.
-static void* host_device_ptr(const void* p) {
+// refresh = true re-queries the driver and replaces the cached entry: done on every (re)synchronising call of an io block
+// (io->synced == 0), which is also the call a binding must make after it swapped its host arrays.
+static void* host_device_ptr(const void* p, bool refresh = false) {
   if (!p) return nullptr;
   struct Entry { const void* host; void* dev; };
   static thread_local Entry cache[16];
   static thread_local int used = 0;
-  for (int i = 0; i < used; i++) if (cache[i].host == p) return cache[i].dev;
+  int slot = -1;
+  for (int i = 0; i < used; i++) if (cache[i].host == p) { slot = i; break; }
+  if (slot >= 0 && !refresh) return cache[slot].dev;
   cudaPointerAttributes attr;
   void* dev = nullptr;
   if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) dev = attr.devicePointer;
   else cudaGetLastError();
-  if (dev && used < 16) cache[used++] = Entry{p, dev};
+  if (slot >= 0) cache[slot].dev = dev;
+  else if (dev && used < 16) cache[used++] = Entry{p, dev};
   return dev;
 }
 
@@ -1272,8 +1277,12 @@ extern "C" int pcgrl_step_host_begin(const pcgrl_config* cfg, const pcgrl_buffer
     return 0;
   }
 
-  // full copies (mode 0, or the first / re-arming call of mode 1)
+  // full copies (mode 0, or the first / re-arming call of modes 1 and 2)
   if (delta) cudaMemsetAsync(io->d_staging, 0, PCGRL_STAGING_HEADER, s);
+  if (io->mode == 2) {  // (re)resolve the device-visible addresses of the host arrays for the direct steps that follow
+    host_device_ptr(io->map, true); host_device_ptr(io->heatmap, true); host_device_ptr(io->pos, true);
+    host_device_ptr(io->reward, true); host_device_ptr(io->done, true);
+  }
   rc = rollout_dispatch(cfg, b, act_ptr, nullptr, nullptr, 1, n, stream, Staging{nullptr, 0u, 0u, 0, n});
   if (rc) return rc;
   if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);

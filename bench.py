@@ -775,7 +775,8 @@ def main():
                                    "h2d_bytes_per_step": rio.h2d_bytes * world // chunk, "d2h_bytes_per_step": rio.d2h_bytes * world // chunk,
                                    "ms_per_step": res["e2e_roll"] / roll_steps, "steps_per_call": chunk,
                                    "api": "pcgrl_rollout_host (open loop: %d steps per call, pinned host actions in; every step's "
-                                          "reward + done and the final map+heatmap+pos back on the host)" % chunk}
+                                          "reward + done copied back, the final map+heatmap+pos stored into the pinned host arrays "
+                                          "by the kernel as each env finishes)" % chunk}
             line["check_reward_sum"] = rsum
             line["shard_check"] = shard
             if world > 1:

@@ -1400,13 +1400,29 @@ extern "C" int pcgrl_rollout_host(const pcgrl_config* cfg, const pcgrl_buffers* 
   // round trip per env-step; the per-step call does read them in place, see pcgrl_step_host)
   cudaMemcpyAsync(d_actions, io->actions, sizeof(int32_t) * tn * adim, cudaMemcpyHostToDevice, s);
   const int32_t* act_ptr = d_actions;
-  rc = rollout_dispatch(cfg, b, act_ptr, d_reward, d_done, T, n, stream, Staging{nullptr, 0u, 0u, 0, n});
+  // Final observation: when the host arrays are pinned (device-mapped), every warp stores its env's final map / heat map /
+  // cursor into them as it finishes (posted PCIe writes that overlap the envs still running); otherwise D2H copies.
+  // PCGRL_ROLLOUT_DIRECT=0 forces the copies (A/B).
+  static const bool direct_ok = !(getenv("PCGRL_ROLLOUT_DIRECT") && atoi(getenv("PCGRL_ROLLOUT_DIRECT")) == 0);
+  Staging sg{nullptr, 0u, 0u, 0, n};
+  // (binary / zelda: the fused kernel; the solver problems' rollouts last milliseconds and keep the copies)
+  if (direct_ok && (cfg->problem == PCGRL_PROB_BINARY || cfg->problem == PCGRL_PROB_ZELDA) && (io->map || io->heatmap)) {
+    sg.h_map = (uint8_t*)host_device_ptr(io->map, true);
+    sg.h_heat = (uint8_t*)host_device_ptr(io->heatmap, true);
+    sg.h_pos = wide ? nullptr : (uint8_t*)host_device_ptr(io->pos, true);
+    sg.d_heat = b->heatmap;
+    const bool all_mapped = (!io->map || sg.h_map) && (!io->heatmap || sg.h_heat) && (!io->pos || wide || sg.h_pos);
+    sg.direct = all_mapped ? 2 : 0;
+  }
+  rc = rollout_dispatch(cfg, b, act_ptr, d_reward, d_done, T, n, stream, sg);
   if (rc) return rc;
   cudaMemcpyAsync(io->reward, d_reward, sizeof(double) * tn, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(io->done, d_done, tn, cudaMemcpyDeviceToHost, s);
-  if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
-  if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, (size_t)heat_bytes(*cfg) * cells * n, cudaMemcpyDeviceToHost, s);
-  if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
+  if (sg.direct != 2) {
+    if (io->map) cudaMemcpyAsync(io->map, b->map, cells * n, cudaMemcpyDeviceToHost, s);
+    if (io->heatmap) cudaMemcpyAsync(io->heatmap, b->heatmap, (size_t)heat_bytes(*cfg) * cells * n, cudaMemcpyDeviceToHost, s);
+    if (io->pos && !wide) cudaMemcpyAsync(io->pos, b->pos, 2 * (size_t)n, cudaMemcpyDeviceToHost, s);
+  }
   if (io->info_stats) cudaMemcpyAsync(io->info_stats, b->info_stats, sizeof(int32_t) * PCGRL_MAX_STATS * n, cudaMemcpyDeviceToHost, s);
   return cuda_rc(cudaStreamSynchronize(s), "pcgrl_rollout_host");
 }

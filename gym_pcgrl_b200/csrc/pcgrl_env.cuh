@@ -339,7 +339,7 @@ struct Staging {
   int n;
   // direct transport (pcgrl_host_io mode 2): device-visible addresses of the caller's pinned host arrays; the kernel
   // stores every result where it belongs while it runs, nothing is copied or patched afterwards
-  int direct;
+  int direct;            // 1: per-step results (pcgrl_step_host); 2: final state of a T-step rollout (pcgrl_rollout_host)
   uint8_t* h_map;
   uint8_t* h_heat;       // uint8 or uint16 elements, like the device heat map
   uint8_t* h_pos;        // nullptr for the wide representation
@@ -355,6 +355,32 @@ __device__ __forceinline__ void write_direct(const Staging& sg, const pcgrl_conf
                                              const uint8_t* new_map, bool multi) {
   const int cells = cfg.width * cfg.height, hb = heat_bytes(cfg);
   const bool wide = cfg.representation == PCGRL_REP_WIDE;
+  if (sg.direct == 2) {
+    // Final state of a T-step rollout (pcgrl_rollout_host): the env's whole map and heat map and its cursor.  The
+    // bytes were written by this warp over the T steps (plain stores and reductions, mostly by lane 0); the warp barrier
+    // orders them before the L2 loads (ld.cg) of the other lanes.
+    if (lane == 0 && sg.h_pos) *reinterpret_cast<uint16_t*>(sg.h_pos + 2 * (size_t)e) = (uint16_t)((uint32_t)x | ((uint32_t)y << 8));
+    __syncwarp();
+    if (sg.h_map) {
+      uint8_t* dst = sg.h_map + (size_t)e * cells;
+      if ((cells & 3) == 0) {
+        for (int i = lane; i < (cells >> 2); i += 32) reinterpret_cast<uint32_t*>(dst)[i] = __ldcg(reinterpret_cast<const uint32_t*>(new_map) + i);
+      } else {
+        for (int i = lane; i < cells; i += 32) dst[i] = __ldcg(new_map + i);
+      }
+    }
+    if (sg.h_heat) {
+      const int nb = cells * hb;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(sg.d_heat) + (size_t)e * nb;
+      uint8_t* dst = sg.h_heat + (size_t)e * nb;
+      if ((nb & 3) == 0) {
+        for (int i = lane; i < (nb >> 2); i += 32) reinterpret_cast<uint32_t*>(dst)[i] = __ldcg(reinterpret_cast<const uint32_t*>(src) + i);
+      } else {
+        for (int i = lane; i < nb; i += 32) dst[i] = __ldcg(src + i);
+      }
+    }
+    return;
+  }
   if (lane == 0) {
     sg.h_reward[e] = reward;
     sg.h_done[e] = done ? 1 : 0;

@@ -964,3 +964,18 @@ def test_incremental_binary_statistics_match_oracle(case, monkeypatch):
         np.testing.assert_array_equal(t2n(env._tens["stats"])[:, :S], ref["stats"][:, :S])
         np.testing.assert_array_equal(t2n(env._tens["rng"]).view(np.uint32), ref["rng"])
     env.check_status()
+
+
+def test_direct_transport_rejects_pageable_host_arrays():
+    """mode 2 stores into the host arrays from the kernel: a pageable (not device-mapped) array must fail loudly, not be
+    silently skipped."""
+    import torch
+    env = util.host_env("binary-narrow-v0", {}, num_envs=64, device="cuda")
+    env.reset()
+    io = HostStepIO(env, with_obs=True, with_info=False, mode="direct")
+    io.actions[:] = 0
+    env.step_host(io)                       # first call: full-copy sync, fine with any host memory
+    pageable = np.zeros(64, dtype=np.float64)
+    io.struct.reward = pageable.ctypes.data
+    with pytest.raises(RuntimeError, match="pinned"):
+        env.step_host(io)

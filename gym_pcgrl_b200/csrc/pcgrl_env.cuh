@@ -391,11 +391,11 @@ __device__ __forceinline__ void write_direct(const Staging& sg, const pcgrl_conf
   if ((was_reset || multi) && sg.h_map) {  // whole map (the warp's own earlier stores are visible after the barrier)
     __syncwarp();
     uint8_t* dst = sg.h_map + (size_t)e * cells;
-    if ((cells & 3) == 0) {
+    if ((cells & 3) == 0) {  // L2 loads: the bytes were stored by other lanes of this warp
       for (int i = lane; i < (cells >> 2); i += 32)
-        reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(new_map)[i];
+        reinterpret_cast<uint32_t*>(dst)[i] = __ldcg(reinterpret_cast<const uint32_t*>(new_map) + i);
     } else {
-      for (int i = lane; i < cells; i += 32) dst[i] = new_map[i];
+      for (int i = lane; i < cells; i += 32) dst[i] = __ldcg(new_map + i);
     }
   } else if (lane == 0 && sg.h_map) {
     sg.h_map[(size_t)e * cells + cell] = (uint8_t)tile;

@@ -582,4 +582,20 @@ __host__ __device__ __forceinline__ double range_reward(double nv, double ov, do
   return 0.0;
 }
 
+// get_range_reward on integer statistics with finite integer bounds: every branch of the fp64 form above yields a small
+// integer exactly, so the int32 arithmetic is value-identical (the caller converts to double before the weighted sum).
+__host__ __device__ __forceinline__ int range_reward_i(int nv, int ov, int low, int high) {
+  if (nv >= low && nv <= high && ov >= low && ov <= high) return 0;
+  if (ov <= high && nv <= high) return (nv < low ? nv : low) - (ov < low ? ov : low);
+  if (ov >= low && nv >= low) return (ov > high ? ov : high) - (nv > high ? nv : high);
+  if (nv > high && ov < low) return high - nv + ov - low;
+  if (nv < low && ov > high) return high - ov + nv - low;
+  return 0;
+}
+// the same with high = +inf: only the first two branches can be taken
+__host__ __device__ __forceinline__ int range_reward_i_hi_inf(int nv, int ov, int low) {
+  if (nv >= low && ov >= low) return 0;
+  return (nv < low ? nv : low) - (ov < low ? ov : low);
+}
+
 }  // namespace pcgrl

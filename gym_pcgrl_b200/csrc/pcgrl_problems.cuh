@@ -122,10 +122,13 @@ __host__ __device__ __forceinline__ double problem_reward(const pcgrl_config& cf
     return (double)r0 * w[0] + (double)(n[1] - o[1]) * w[1];
   }
   if (PROB == PCGRL_PROB_ZELDA)  // zelda_prob.py:124-142
-    return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 1, 1) * w[1] +
-           range_reward(n[2], o[2], 1, 1) * w[2] + range_reward(n[3], o[3], 2, ip[0]) * w[3] +
-           range_reward(n[4], o[4], 1, 1) * w[4] + range_reward(n[5], o[5], ip[1], INF) * w[5] +
-           range_reward(n[6], o[6], INF, INF) * w[6];
+    // The statistics and the finite bounds are integers, so each get_range_reward term is an exact small integer: it is
+    // computed in int32 (the fp64 min / max / compare chain was 30 % of the zelda kernel's instructions) and converted
+    // before the same fp64 products and left-to-right sum.  (inf, inf) always takes the second branch: new - old.
+    return (double)range_reward_i(n[0], o[0], 1, 1) * w[0] + (double)range_reward_i(n[1], o[1], 1, 1) * w[1] +
+           (double)range_reward_i(n[2], o[2], 1, 1) * w[2] + (double)range_reward_i(n[3], o[3], 2, ip[0]) * w[3] +
+           (double)range_reward_i(n[4], o[4], 1, 1) * w[4] + (double)range_reward_i_hi_inf(n[5], o[5], ip[1]) * w[5] +
+           (double)(n[6] - o[6]) * w[6];
   if (PROB == PCGRL_PROB_SOKOBAN)  // sokoban_prob.py:157-175
     return range_reward(n[0], o[0], 1, 1) * w[0] + range_reward(n[1], o[1], 1, ip[0]) * w[1] +
            range_reward(n[2], o[2], 1, ip[0]) * w[2] + range_reward(n[3], o[3], 1, 1) * w[3] +
